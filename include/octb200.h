@@ -1,0 +1,207 @@
+/*
+ * octb200.h -- C ABI of the B200-native OCT raw -> B-scan pipeline.
+ *
+ * This is the drop-in boundary for OCTproZ's GPU path.  It replaces the `extern "C"` set of
+ * the reference's kernels.h (octproz_project/octproz/src/kernels.h:63-84, implemented in
+ * cuda_code.cu) -- see the "replaces" note on every entry point -- but as a re-entrant,
+ * handle-based, status-returning API with plain pointers and sizes: no Qt, no torch and no
+ * CUDA types appear in the signatures (streams cross as void*).  The adapter that re-exports
+ * the reference's own symbol names on top of this header is integration/octproz_kernels_adapter.cpp
+ * (INTEGRATION.md).
+ *
+ * Data layout (identical to the reference):
+ *   raw input   : [bscansPerBuffer][ascansPerBscan][samplesPerLine] containers, little endian,
+ *                 container = u8 (bitDepth<=8), u16 (<=16) or u32 (else)   (cuda_code.cu:116-125)
+ *   output      : float [buffersPerVolume*bscansPerBuffer][ascansPerBscan][samplesPerLine/2]
+ *                 (cuda_code.cu:1118,1535: one slab per buffer of the volume)
+ *
+ * Threading: one host thread per pipeline handle at a time (as the reference: all calls come
+ * from the processing thread, processing.cpp:176-218).  Handles are independent.
+ * Errors: every call returns OCTB200_OK (0) or a negative code; octb200_last_error() has text.
+ * Nothing here ever calls exit() (the reference's checkCudaErrors does, helper_cuda.h:582-595).
+ */
+#ifndef OCTB200_H
+#define OCTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define OCTB200_API __declspec(dllexport)
+#else
+#define OCTB200_API __attribute__((visibility("default")))
+#endif
+
+#define OCTB200_VERSION 100
+
+enum {
+	OCTB200_OK = 0,
+	OCTB200_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+	OCTB200_ERR_CUDA = -2,         /* CUDA runtime / cuFFT error, text in octb200_last_error */
+	OCTB200_ERR_NOMEM = -3,        /* device allocation failed (initializeCuda returned false) */
+	OCTB200_ERR_NOT_READY = -4     /* curves / buffers not set for an enabled stage */
+};
+
+/* octalgorithmparameters.h:55-59 */
+enum { OCTB200_INTERP_LINEAR = 0, OCTB200_INTERP_CUBIC = 1, OCTB200_INTERP_LANCZOS = 2 };
+/* windowfunction.h:41-48 */
+enum { OCTB200_WIN_HANNING = 0, OCTB200_WIN_GAUSS = 1, OCTB200_WIN_SINE = 2,
+       OCTB200_WIN_LANCZOS = 3, OCTB200_WIN_RECTANGULAR = 4, OCTB200_WIN_FLATTOP = 5 };
+/* octalgorithmparameters.h:177-180 */
+enum { OCTB200_DISPLAY_AVERAGING = 0, OCTB200_DISPLAY_MIP = 1 };
+
+/* which kernels run the FFT stage */
+enum {
+	OCTB200_FFT_AUTO = 0,        /* FUSED when samplesPerLine is 1024 or 2048 and the container is u16, else best available */
+	OCTB200_FFT_FUSED = 1,       /* one kernel: raw -> resample/window/phasor -> FFT -> FPN/log -> B-scan (4 B/sample) */
+	OCTB200_FFT_SPLIT = 2,       /* fused pre-FFT kernel -> float2 in HBM -> own FFT with fused epilogue (20 B/sample) */
+	OCTB200_FFT_CUFFT = 3        /* fused pre-FFT kernel -> cufftExecC2C -> fused post kernel (32 B/sample); any N */
+};
+
+/* AcquisitionParams (octproz_devkit/src/acquisitionparameter.h:31-37) + device placement */
+typedef struct {
+	uint32_t samplesPerLine;
+	uint32_t ascansPerBscan;
+	uint32_t bscansPerBuffer;
+	uint32_t buffersPerVolume;
+	uint32_t bitDepth;
+	int32_t  device;            /* CUDA device ordinal; -1 = current device */
+	int32_t  rawSlots;          /* device raw buffers for H2D / compute overlap; 0 = default (2) */
+	int32_t  fftMode;           /* OCTB200_FFT_* */
+	uint32_t bscanIndexBase;    /* multi-GPU shards: index (within the un-sharded buffer) of this shard's
+	                               first B-scan, so "flip every even B-scan" (cuda_code.cu:795) keeps its parity */
+	uint32_t reserved[3];
+} octb200_config;
+
+/* the [processing] block of OctAlgorithmParameters (octalgorithmparameters.h:108-166, 195-199) */
+typedef struct {
+	int32_t  bitshift;
+	int32_t  bscanFlip;
+	int32_t  signalLogScaling;
+	int32_t  sinusoidalScanCorrection;
+	float    signalGrayscaleMin;
+	float    signalGrayscaleMax;
+	float    signalMultiplicator;
+	float    signalAddend;
+	int32_t  backgroundRemoval;
+	int32_t  rollingAverageWindowSize;
+	int32_t  resampling;
+	int32_t  resamplingInterpolation;      /* OCTB200_INTERP_* */
+	int32_t  dispersionCompensation;
+	int32_t  windowing;
+	int32_t  fixedPatternNoiseRemoval;
+	int32_t  continuousFixedPatternNoiseDetermination;
+	int32_t  redetermineFixedPatternNoise;  /* edge trigger, consumed by the next process call (cuda_code.cu:1521-1524) */
+	uint32_t bscansForNoiseDetermination;
+	int32_t  postProcessBackgroundRemoval;
+	int32_t  postProcessBackgroundRecordingRequested; /* edge trigger (cuda_code.cu:1558-1562) */
+	float    postProcessBackgroundWeight;
+	float    postProcessBackgroundOffset;
+	int32_t  streamToHost;                  /* converted output -> registered host buffers + callback (cuda_code.cu:1601-1604) */
+	uint32_t streamingBuffersToSkip;
+	int32_t  streamFloatToHost;             /* recParams.saveAs32bitFloat path (cuda_code.cu:1596-1598) */
+	uint32_t reserved[3];
+} octb200_params;
+
+typedef struct octb200_pipeline octb200_pipeline;
+
+/* host callback: same shape as the Gpu2HostNotifier static callbacks (gpu2hostnotifier.h:47-49) */
+typedef void (*octb200_host_callback)(void* hostBuffer);
+
+/* ---------- lifecycle ---------- */
+/* replaces initializeCuda (kernels.h:63, cuda_code.cu:1067-1162): allocates every device buffer, streams, events */
+OCTB200_API int octb200_create(const octb200_config* cfg, octb200_pipeline** out);
+/* replaces cleanupCuda / releaseBuffers / destroyStreamsAndEvents (kernels.h:65-67, cuda_code.cu:1164-1212) */
+OCTB200_API int octb200_destroy(octb200_pipeline* p);
+OCTB200_API const char* octb200_last_error(const octb200_pipeline* p);   /* p may be NULL: error of the last failed create */
+OCTB200_API int octb200_version(void);
+OCTB200_API void octb200_default_params(octb200_params* out);           /* octalgorithmparameters.cpp:36-112 defaults */
+OCTB200_API int octb200_effective_fft_mode(const octb200_pipeline* p);
+
+/* ---------- parameters and curves ---------- */
+/* replaces the unsynchronised reads of the OctAlgorithmParameters singleton inside octCudaPipeline */
+OCTB200_API int octb200_set_params(octb200_pipeline* p, const octb200_params* prm);
+/* replace cuda_updateResampleCurve / cuda_updateDispersionCurve / cuda_updateWindowCurve /
+   cuda_updatePostProcessBackground (cuda_code.cu:636-650,969-973): host fp32 LUTs of length n */
+OCTB200_API int octb200_set_resample_curve(octb200_pipeline* p, const float* curve, int n);
+OCTB200_API int octb200_set_dispersion_curve(octb200_pipeline* p, const float* phase, int n);
+OCTB200_API int octb200_set_window_curve(octb200_pipeline* p, const float* window, int n);
+OCTB200_API int octb200_set_postprocess_background(octb200_pipeline* p, const float* bg, int n);
+OCTB200_API int octb200_get_postprocess_background(octb200_pipeline* p, float* bg, int n);
+/* fixed-pattern-noise mean line (complex, n = samplesPerLine pairs).  Used by the multi-GPU host to
+   broadcast rank 0's line; set marks the line as determined (cuda_code.cu:1523). */
+OCTB200_API int octb200_get_fpn_mean_line(octb200_pipeline* p, float* reIm, int n);
+OCTB200_API int octb200_set_fpn_mean_line(octb200_pipeline* p, const float* reIm, int n);
+
+/* curve generators = OctAlgorithmParameters::update*Curve (octalgorithmparameters.cpp:141-249),
+   Polynomial (polynomial.cpp:108-145), WindowFunction (windowfunction.cpp:121-253),
+   fillSinusoidalScanCorrectionCurve (cuda_code.cu:516-521).  Pure host functions. */
+OCTB200_API int octb200_make_resample_curve(int n, float c0, float c1, float c2, float c3, float* out);
+OCTB200_API int octb200_make_dispersion_curve(int n, float d0, float d1, float d2, float d3, float* out);
+OCTB200_API int octb200_make_window_curve(int type, float centerPosition, float fillFactor, int n, float* out);
+OCTB200_API int octb200_make_sinusoidal_curve(int ascansPerBscan, float* out);
+
+/* ---------- host buffers and callbacks ---------- */
+/* replaces the cudaHostRegister of the plugin's two acquisition buffers (cuda_code.cu:1135-1136,1200-1207) */
+OCTB200_API int octb200_register_host_buffers(octb200_pipeline* p, void* h1, void* h2);
+OCTB200_API int octb200_unregister_host_buffers(octb200_pipeline* p);
+/* replace cuda_register[Float]StreamingBuffers / cuda_unregister... (kernels.h:68-71) */
+OCTB200_API int octb200_register_streaming_buffers(octb200_pipeline* p, void* h1, void* h2, size_t bytesPerBuffer);
+OCTB200_API int octb200_unregister_streaming_buffers(octb200_pipeline* p);
+OCTB200_API int octb200_register_float_streaming_buffers(octb200_pipeline* p, void* h1, void* h2, size_t bytesPerBuffer);
+OCTB200_API int octb200_unregister_float_streaming_buffers(octb200_pipeline* p);
+/* replace the hard-wired Gpu2HostNotifier::{dh2StreamingCallback, dh2FloatStreamingCallback, backgroundSignalCallback} */
+OCTB200_API int octb200_set_callbacks(octb200_pipeline* p, octb200_host_callback streaming,
+                                      octb200_host_callback floatStreaming, octb200_host_callback background);
+
+/* ---------- the hot path ---------- */
+/* replaces octCudaPipeline(void* h_inputSignal) (kernels.h:64, cuda_code.cu:1389-1605).
+   h_raw: host buffer of one raw buffer.  The H2D copy runs on its own stream into one of `rawSlots`
+   device slots; the call returns once the copy has finished (the producer may then refill h_raw, the
+   contract of cuda_code.cu:1416-1419) while the kernels keep running asynchronously.
+   h_raw == NULL re-processes the slot that was filled last (cuda_code.cu:1400). */
+OCTB200_API int octb200_process_host(octb200_pipeline* p, const void* h_raw);
+/* device-resident variant: d_raw is already in HBM (any 16-byte aligned device pointer) */
+OCTB200_API int octb200_process_device(octb200_pipeline* p, const void* d_raw);
+/* wait for everything issued so far (kernels, D2H streaming, callbacks) */
+OCTB200_API int octb200_sync(octb200_pipeline* p);
+OCTB200_API uint32_t octb200_current_buffer_nr(const octb200_pipeline* p);   /* params->currentBufferNr (cuda_code.cu:1602) */
+
+/* ---------- results ---------- */
+/* the processed volume in HBM (d_processedBuffer, cuda_code.cu:98); slab = buffer number in volume */
+OCTB200_API float* octb200_output_device_ptr(octb200_pipeline* p, uint32_t bufferNrInVolume);
+OCTB200_API int octb200_copy_output(octb200_pipeline* p, float* host, uint32_t bufferNrInVolume);
+/* let the caller own the volume (e.g. a torch tensor): floats = buffersPerVolume * samplesPerBuffer/2; NULL restores the internal one */
+OCTB200_API int octb200_bind_output(octb200_pipeline* p, void* d_volume);
+
+/* replace changeDisplayedBscanFrame / changeDisplayedEnFaceFrame + updateDisplayed*Frame kernels
+   (kernels.h:79-82, cuda_code.cu:810-912,1223-1308).  out is a DEVICE pointer (the mapped PBO in the
+   Qt host): B-scan frame = N/2 * A floats, en-face frame = A * Btot floats. */
+OCTB200_API int octb200_bscan_frame(octb200_pipeline* p, uint32_t frameNr, uint32_t displayFunctionFrames,
+                                    int displayFunction, float* d_out);
+OCTB200_API int octb200_enface_frame(octb200_pipeline* p, uint32_t frameNr, uint32_t displayFunctionFrames,
+                                     int displayFunction, float* d_out);
+/* replaces updateDisplayedVolume (cuda_code.cu:915-941): u8 voxels of one buffer into a linear device
+   array laid out like the GL_R8 3-D texture: index = ((z * Btot) + y) * A + x, x = A-scan, y = B-scan in
+   volume, z = (N/2-1) - depth */
+OCTB200_API int octb200_volume_u8(octb200_pipeline* p, uint32_t bufferNrInVolume, uint8_t* d_out);
+/* replaces floatToOutput (cuda_code.cu:943-967): saturate * (2^bits-1) into a device container array */
+OCTB200_API int octb200_float_to_output(octb200_pipeline* p, uint32_t bufferNrInVolume, void* d_out);
+
+/* ---------- timing helpers (CUDA events on the pipeline's compute stream) ---------- */
+OCTB200_API void* octb200_compute_stream(octb200_pipeline* p);           /* cudaStream_t as void* */
+OCTB200_API int octb200_event_record(octb200_pipeline* p, int slot);     /* slot 0..7 */
+OCTB200_API int octb200_event_elapsed_ms(octb200_pipeline* p, int slotStart, int slotStop, float* ms);
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
+OCTB200_API uint64_t octb200_launch_count(const octb200_pipeline* p);
+/* time ONE named stage in isolation with events: 0 = whole process_device, 1 = dominant kernel only */
+OCTB200_API int octb200_time_kernel(octb200_pipeline* p, const void* d_raw, int iters, float* msPerIter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCTB200_H */

@@ -1,0 +1,383 @@
+/*
+ * k_aux.cu -- the lighter kernels around the fused hot kernel (all sm_100a, hand written):
+ *   fill_phase          : fillDispersivePhase                           (cuda_code.cu:624-634)
+ *   oct_pre_kernel      : fused pre-FFT kernel, any N / container       (cuda_code.cu:109-489) -> float2 FFT input
+ *   oct_post_kernel     : FPN subtract + truncate + log/lin + flip      (cuda_code.cu:567-584,699-807) after cuFFT
+ *   fpn_minvar_kernel   : getMinimumVarianceMean                        (cuda_code.cu:523-565)
+ *   sinusoidal_kernel   : sinusoidalScanCorrection (+ folded background)(cuda_code.cu:491-514,757-767)
+ *   ppbg_*              : getPostProcessBackground / ...Removal         (cuda_code.cu:743-767)
+ *   bscan/enface/volume : updateDisplayed*                              (cuda_code.cu:810-941)
+ *   float_to_output     : floatToOutput                                 (cuda_code.cu:943-967)
+ */
+#include "k_aux.cuh"
+#include <cfloat>
+
+namespace octb200 {
+
+/* ------------------------------------------------------------------ dispersion phasor */
+__global__ void fill_phase_kernel(float2* __restrict__ ph, const float* __restrict__ phase, int n) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		/* cosf(1.0*phase) / sinf(..)*1 under --use_fast_math == __cosf/__sinf (cuda_code.cu:631-632, cuda.pri:54) */
+		const float a = phase[i];
+		ph[i] = make_float2(__cosf(a), __sinf(a));
+	}
+}
+void launch_fill_phase(float2* ph, const float* phase, int n, cudaStream_t st) {
+	fill_phase_kernel<<<(n + 127) / 128, 128, 0, st>>>(ph, phase, n);
+}
+
+/* ------------------------------------------------------------------ generic pre-FFT kernel */
+template <typename RawT> struct RawTraits;
+template <> struct RawTraits<uint8_t> { static constexpr int kBytes = 1; };
+template <> struct RawTraits<uint16_t> { static constexpr int kBytes = 2; };
+template <> struct RawTraits<uint32_t> { static constexpr int kBytes = 4; };
+
+template <typename RawT>
+__device__ __forceinline__ float convert_raw(RawT v, int shiftBits) {
+	if constexpr (sizeof(RawT) == 4) {
+		if (shiftBits) return (float)((double)v / 4294967296.0);   /* cuda_code.cu:144 */
+		return __uint2float_rd(v);                                  /* cuda_code.cu:124 */
+	} else {
+		return __uint2float_rd((unsigned)v >> shiftBits);           /* cuda_code.cu:118-121,138-141 */
+	}
+}
+
+/* per-warp shared layout of the pre kernel */
+__host__ __device__ inline int pre_warp_bytes(int SE, int rawBytes, bool roll) {
+	return 2 * align_up(SE * rawBytes, 128) + align_up(SE * 4, 128) + (roll ? align_up((SE + 1) * 8, 128) : 0) + 128;
+}
+
+template <typename RawT, int SA, bool ROLL>
+__global__ void __launch_bounds__(256) oct_pre_kernel(const PreArgs a) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	constexpr int RB = sizeof(RawT);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int N = a.N, SE = a.HB + N + a.HA;
+	unsigned char* wbase = smem + warp * pre_warp_bytes(SE, RB, ROLL);
+	const int slotBytes = align_up(SE * RB, 128);
+	unsigned char* slots[2] = { wbase, wbase + slotBytes };
+	float* fslot = reinterpret_cast<float*>(wbase + 2 * slotBytes);
+	unsigned long long* prefix = reinterpret_cast<unsigned long long*>(wbase + 2 * slotBytes + align_up(SE * 4, 128));
+	uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + pre_warp_bytes(SE, RB, ROLL) - 128);
+
+	const int G = gridDim.x * (blockDim.x >> 5);
+	const int g0 = blockIdx.x * (blockDim.x >> 5) + warp;
+	const RawT* raw = reinterpret_cast<const RawT*>(a.raw);
+
+	auto issue = [&](int gline, int s) {
+		const long long lo = (long long)gline * N - a.HB, hi = (long long)gline * N + N + a.HA;
+		const long long clo = lo < 0 ? 0 : lo, chi = hi > a.totalSamples ? a.totalSamples : hi;
+		RawT* dst = reinterpret_cast<RawT*>(slots[s]);
+		if (a.useBulk) {
+			if (lane == 0) {
+				for (long long q = 0; q < clo - lo; ++q) dst[q] = 0;
+				for (long long q = chi - lo; q < hi - lo; ++q) dst[q] = 0;
+				const uint32_t bytes = (uint32_t)((chi - clo) * RB);
+				mbar_arrive_expect_tx(&bars[s], bytes);
+				bulk_g2s(dst + (clo - lo), raw + clo, bytes, &bars[s]);
+			}
+		} else {
+			/* unaligned geometry: plain coalesced loads straight into the slot */
+			for (long long q = lo + lane; q < hi; q += 32) dst[q - lo] = (q >= 0 && q < a.totalSamples) ? raw[q] : (RawT)0;
+		}
+	};
+
+	if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+	__syncwarp();
+	if (g0 < a.lines) issue(g0, 0);
+	if (a.useBulk && g0 + G < a.lines) issue(g0 + G, 1);
+
+	int it = 0;
+	for (int gline = g0; gline < a.lines; gline += G, ++it) {
+		const int s = a.useBulk ? (it & 1) : 0;
+		if (a.useBulk) mbar_wait(&bars[s], (uint32_t)((it >> 1) & 1));
+		else __syncwarp();
+		const RawT* rs = reinterpret_cast<const RawT*>(slots[s]);
+		if constexpr (ROLL) {
+			unsigned long long carry = 0;
+			if (lane == 0) prefix[0] = 0;
+			for (int c = 0; c < SE; c += 32) {
+				const int q = c + lane;
+				unsigned long long x = 0;
+				if (q < SE) x = (sizeof(RawT) == 4) ? (unsigned long long)rs[q] : (unsigned long long)((unsigned)rs[q] >> a.shiftBits);
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+				if (q < SE) prefix[q + 1] = carry + x;
+				carry += __shfl_sync(0xffffffffu, x, 31);
+			}
+		}
+		for (int q = lane; q < SE; q += 32) fslot[q] = convert_raw<RawT>(rs[q], a.shiftBits);
+		__syncwarp();
+		if (a.useBulk) { if (gline + 2 * G < a.lines) issue(gline + 2 * G, s); }
+		if constexpr (ROLL) {
+			const int W = a.W;
+			for (int q = lane; q < SE; q += 32) {
+				int lo, hi;
+				if (q < a.HB) { lo = 0; hi = a.HB - 1; }
+				else if (q >= a.HB + N) { lo = a.HB + N; hi = SE - 1; }
+				else { lo = a.HB; hi = a.HB + N - 1; }
+				const int ss = max(lo, q - W + 1), e = min(hi, q + W);
+				const unsigned long long d = prefix[e + 1] - prefix[ss];
+				float sum;
+				if (sizeof(RawT) == 4 && a.shiftBits) sum = (float)((double)d / 4294967296.0);
+				else sum = (float)d;
+				fslot[q] -= __fdividef(sum, (float)(e - ss + 1));
+			}
+			__syncwarp();
+		}
+		const float* f = fslot + a.HB;
+		const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
+		float2* o = a.out + (size_t)gline * N;
+		for (int m = lane; m < N; m += 32) {
+			const float4 B = __ldg(a.lutB + m);
+			float2 val;
+			if constexpr (SA == SA_TAPS4) val = sample_taps4(f, __ldg(a.lutW + m), B);
+			else if constexpr (SA == SA_NONE) val = sample_none(f, m, B);
+			else val = sample_lanczos(f, shift, B);
+			o[m] = val;
+		}
+		__syncwarp();
+		if (!a.useBulk) { if (gline + G < a.lines) issue(gline + G, 0); }
+	}
+}
+
+template <typename RawT, int SA, bool ROLL>
+static cudaError_t launch_pre_t(const PreArgs& a, int smCount, cudaStream_t st) {
+	const int SE = a.HB + a.N + a.HA;
+	const int perWarp = pre_warp_bytes(SE, (int)sizeof(RawT), ROLL);
+	int warps = 8;
+	while (warps > 1 && warps * perWarp > 200 * 1024) warps >>= 1;
+	if (warps * perWarp > 227 * 1024) return cudaErrorInvalidConfiguration;
+	const int smem = warps * perWarp;
+	auto k = oct_pre_kernel<RawT, SA, ROLL>;
+	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	if (e != cudaSuccess) return e;
+	int ctasPerSm = (220 * 1024) / (smem + 1024);
+	if (ctasPerSm < 1) ctasPerSm = 1;
+	if (ctasPerSm > 4) ctasPerSm = 4;
+	int grid = smCount * ctasPerSm;
+	const int maxGrid = (a.lines + warps - 1) / warps;
+	if (grid > maxGrid) grid = maxGrid;
+	if (grid < 1) grid = 1;
+	k<<<grid, warps * 32, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+template <typename RawT>
+static cudaError_t launch_pre_raw(const PreArgs& a, int sa, bool roll, int smCount, cudaStream_t st) {
+	if (sa == SA_TAPS4) return roll ? launch_pre_t<RawT, SA_TAPS4, true>(a, smCount, st) : launch_pre_t<RawT, SA_TAPS4, false>(a, smCount, st);
+	if (sa == SA_NONE) return roll ? launch_pre_t<RawT, SA_NONE, true>(a, smCount, st) : launch_pre_t<RawT, SA_NONE, false>(a, smCount, st);
+	return roll ? launch_pre_t<RawT, SA_LANCZOS, true>(a, smCount, st) : launch_pre_t<RawT, SA_LANCZOS, false>(a, smCount, st);
+}
+
+cudaError_t launch_pre(const PreArgs& a, int rawBytes, int sa, bool roll, int smCount, cudaStream_t st) {
+	if (rawBytes == 1) return launch_pre_raw<uint8_t>(a, sa, roll, smCount, st);
+	if (rawBytes == 2) return launch_pre_raw<uint16_t>(a, sa, roll, smCount, st);
+	return launch_pre_raw<uint32_t>(a, sa, roll, smCount, st);
+}
+
+/* ------------------------------------------------------------------ post kernel (after cuFFT) */
+__global__ void __launch_bounds__(256) oct_post_kernel(const PostArgs a) {
+	const int H = a.N / 2;
+	const long long total = (long long)a.lines * H;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const int line = (int)(i / H), z = (int)(i - (long long)line * H);
+		float2 c = a.in[(size_t)line * a.N + z];
+		if (a.epi.fpn) { const float2 m = __ldg(a.meanLine + z); c.x -= m.x; c.y -= m.y; }
+		float o = scale_output(c.x, c.y, a.epi);
+		if (a.epi.ppbg) o = saturate01(o - fmaf(a.epi.ppbgWeight, __ldg(a.ppbg + z), a.epi.ppbgOffset));
+		int b = line / a.A, al = line - b * a.A;
+		if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u) al = a.A - 1 - al;
+		a.out[((size_t)b * a.A + al) * H + z] = o;
+	}
+}
+cudaError_t launch_post(const PostArgs& a, int smCount, cudaStream_t st) {
+	const long long total = (long long)a.lines * (a.N / 2);
+	long long blocks = (total + 255) / 256;
+	if (blocks > (long long)smCount * 16) blocks = (long long)smCount * 16;
+	if (blocks < 1) blocks = 1;
+	oct_post_kernel<<<(int)blocks, 256, 0, st>>>(a);
+	return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ fixed-pattern noise: minimum-variance mean */
+/* block = 32 bins x 9 segments.  Each thread sums its segment in line order (same order as cuda_code.cu:544-551),
+ * then the 9 candidates of a bin are compared with the reference's strict '<' starting from FLT_MAX. */
+__global__ void __launch_bounds__(32 * 9) fpn_minvar_kernel(float2* __restrict__ meanLine, const float2* __restrict__ in,
+                                                             int bins, int stride, int segW) {
+	__shared__ float sVar[9][32];
+	__shared__ float2 sMean[9][32];
+	const int bx = threadIdx.x, s = threadIdx.y;
+	const int bin = blockIdx.x * 32 + bx;
+	float var = 0.f; float2 mean = make_float2(0.f, 0.f);
+	if (bin < bins && segW > 0) {
+		const float factor = 1.0f / (float)segW;
+		float sx = 0.f, sy = 0.f, sxx = 0.f;
+		const float2* ptr = in + (size_t)s * segW * stride + bin;
+		for (int j = 0; j < segW; ++j) {
+			const float2 v = ptr[(size_t)j * stride];
+			sx += v.x; sy += v.y; sxx += v.x * v.x + v.y * v.y;
+		}
+		mean.x = sx * factor; mean.y = sy * factor;
+		var = sxx * factor - (mean.x * mean.x + mean.y * mean.y);
+	}
+	sVar[s][bx] = var; sMean[s][bx] = mean;
+	__syncthreads();
+	if (s == 0 && bin < bins) {
+		float minVar = FLT_MAX; float2 best = make_float2(0.f, 0.f);
+		if (segW > 0) {
+#pragma unroll
+			for (int i = 0; i < 9; ++i) if (sVar[i][bx] < minVar) { minVar = sVar[i][bx]; best = sMean[i][bx]; }
+		}
+		meanLine[bin] = best;
+	}
+}
+cudaError_t launch_fpn_minvar(float2* meanLine, const float2* in, int bins, int stride, int height, cudaStream_t st) {
+	const int segW = height / 9;   /* FIXED_PATTERN_NOISE_REMOVAL_SEGMENTS, octalgorithmparameters.h:35; integer division cuda_code.cu:531 */
+	fpn_minvar_kernel<<<(bins + 31) / 32, dim3(32, 9), 0, st>>>(meanLine, in, bins, stride, segW);
+	return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ sinusoidal scan correction */
+__global__ void __launch_bounds__(256) sinusoidal_kernel(float* __restrict__ out, const float* __restrict__ in,
+                                                         const float* __restrict__ curve, int H, int A, long long samples,
+                                                         int ppbgOn, const float* __restrict__ ppbg, float w, float o) {
+	for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < samples; idx += (long long)gridDim.x * blockDim.x) {
+		float r;
+		const int j = (int)(idx % H);
+		if (idx < samples - H) {
+			const int k = (int)((idx / H) % A);
+			const long long l = idx / ((long long)H * A);
+			const float x = __ldg(curve + k);
+			const long long x0 = (long long)((int)x) * H + j + l * (long long)H * A;
+			const float f0 = in[x0], f1 = in[x0 + H];
+			r = f0 + (f1 - f0) * (x - (float)(int)x);
+		} else {
+			r = in[idx];   /* the last line keeps its uncorrected value (cuda_code.cu:499) */
+		}
+		if (ppbgOn) r = saturate01(r - fmaf(w, __ldg(ppbg + j), o));
+		out[idx] = r;
+	}
+}
+cudaError_t launch_sinusoidal(float* out, const float* in, const float* curve, int H, int A, long long samples,
+                              int ppbgOn, const float* ppbg, float w, float o, int smCount, cudaStream_t st) {
+	long long blocks = (samples + 255) / 256;
+	if (blocks > (long long)smCount * 16) blocks = (long long)smCount * 16;
+	sinusoidal_kernel<<<(int)blocks, 256, 0, st>>>(out, in, curve, H, A, samples, ppbgOn, ppbg, w, o);
+	return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ post-process background */
+__global__ void ppbg_record_kernel(float* __restrict__ bg, const float* __restrict__ data, int H, int A) {
+	const int z = blockIdx.x * blockDim.x + threadIdx.x;
+	if (z < H) {
+		float sum = 0.f;
+		for (int i = 0; i < A; ++i) sum += data[z + (size_t)i * H];
+		bg[z] = __fdividef(sum, (float)A);
+	}
+}
+cudaError_t launch_ppbg_record(float* bg, const float* data, int H, int A, cudaStream_t st) {
+	ppbg_record_kernel<<<(H + 127) / 128, 128, 0, st>>>(bg, data, H, A);
+	return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256) ppbg_remove_kernel(float* __restrict__ data, const float* __restrict__ bg, float w, float o,
+                                                          int H, long long samples) {
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < samples; i += (long long)gridDim.x * blockDim.x)
+		data[i] = saturate01(data[i] - fmaf(w, __ldg(bg + (int)(i % H)), o));
+}
+cudaError_t launch_ppbg_remove(float* data, const float* bg, float w, float o, int H, long long samples, int smCount, cudaStream_t st) {
+	long long blocks = (samples + 255) / 256;
+	if (blocks > (long long)smCount * 16) blocks = (long long)smCount * 16;
+	ppbg_remove_kernel<<<(int)blocks, 256, 0, st>>>(data, bg, w, o, H, samples);
+	return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ display extraction */
+__global__ void bscan_frame_kernel(float* __restrict__ disp, const float* __restrict__ vol, unsigned Btot, unsigned F,
+                                   unsigned frameNr, unsigned nFrames, int fn) {
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= F) return;
+	if (nFrames > 1) {
+		if (fn == 0) {
+			int cnt = 0; float sum = 0.f;
+			for (unsigned j = 0; j < nFrames; ++j) { const unsigned f = frameNr + j; if (f < Btot) { sum += vol[(size_t)f * F + (F - 1) - i]; ++cnt; } }
+			disp[i] = __fdividef(sum, (float)cnt);
+		} else if (fn == 1) {
+			float mx = 0.f;
+			for (unsigned j = 0; j < nFrames; ++j) { const unsigned f = frameNr + j; if (f < Btot) { const float v = vol[(size_t)f * F + (F - 1) - i]; if (mx < v) mx = v; } }
+			disp[i] = mx;
+		}
+	} else {
+		disp[i] = vol[(size_t)frameNr * F + (F - 1) - i];
+	}
+}
+cudaError_t launch_bscan_frame(float* disp, const float* vol, unsigned Btot, unsigned F, unsigned frameNr, unsigned nFrames, int fn, cudaStream_t st) {
+	bscan_frame_kernel<<<(F + 255) / 256, 256, 0, st>>>(disp, vol, Btot, F, frameNr, nFrames, fn);
+	return cudaGetLastError();
+}
+
+/* en-face: one thread per lateral position i (A-scan of the volume); reads nFrames consecutive depth bins of its line */
+__global__ void enface_frame_kernel(float* __restrict__ disp, const float* __restrict__ vol, unsigned W, unsigned E,
+                                    unsigned frameNr, unsigned nFrames, int fn) {
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= E) return;
+	if (nFrames > 1) {
+		if (fn == 0) {
+			int cnt = 0; float sum = 0.f;
+			for (unsigned j = 0; j < nFrames; ++j) { const unsigned f = frameNr + j; if (f < W) { sum += vol[f + (size_t)i * W]; ++cnt; } }
+			disp[(E - 1) - i] = __fdividef(sum, (float)cnt);
+		} else if (fn == 1) {
+			float mx = 0.f;
+			for (unsigned j = 0; j < nFrames; ++j) { const unsigned f = frameNr + j; if (f < W) { const float v = vol[f + (size_t)i * W]; if (mx < v) mx = v; } }
+			disp[(E - 1) - i] = mx;
+		}
+	} else {
+		disp[(E - 1) - i] = vol[frameNr + (size_t)i * W];
+	}
+}
+cudaError_t launch_enface_frame(float* disp, const float* vol, unsigned W, unsigned E, unsigned frameNr, unsigned nFrames, int fn, cudaStream_t st) {
+	enface_frame_kernel<<<(E + 255) / 256, 256, 0, st>>>(disp, vol, W, E, frameNr, nFrames, fn);
+	return cudaGetLastError();
+}
+
+/* u8 voxels in the layout of the GL_R8 3-D texture (x = A-scan, y = B-scan in volume, z flipped depth), cuda_code.cu:928-940 */
+__global__ void __launch_bounds__(256) volume_u8_kernel(uint8_t* __restrict__ tex, const float* __restrict__ buf, long long samples,
+                                                         unsigned bufferNr, unsigned B, unsigned A, unsigned Btot, unsigned depth) {
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < samples; i += (long long)gridDim.x * blockDim.x) {
+		const unsigned y = (unsigned)((i / depth) % A);
+		const unsigned z = (depth - 1) - (unsigned)(i % depth);
+		const unsigned x = (unsigned)(i / ((long long)A * depth)) + bufferNr * B;
+		const unsigned char voxel = (unsigned char)((double)buf[i] * 255.0);
+		/* surf3Dwrite(voxel, surf, y, x, z): texture dims (width=A, height=Btot, depth) */
+		tex[((size_t)z * Btot + x) * A + y] = voxel;
+	}
+}
+cudaError_t launch_volume_u8(uint8_t* tex, const float* buf, long long samples, unsigned bufferNr, unsigned B, unsigned A, unsigned Btot,
+                             unsigned depth, int smCount, cudaStream_t st) {
+	long long blocks = (samples + 255) / 256;
+	if (blocks > (long long)smCount * 16) blocks = (long long)smCount * 16;
+	volume_u8_kernel<<<(int)blocks, 256, 0, st>>>(tex, buf, samples, bufferNr, B, A, Btot, depth);
+	return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ float -> output container */
+__global__ void __launch_bounds__(256) float_to_output_kernel(void* __restrict__ out, const float* __restrict__ in, int bitDepth, long long n) {
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const float s = __saturatef(in[i]);
+		if (bitDepth <= 8) reinterpret_cast<unsigned char*>(out)[i] = (unsigned char)((double)s * 255.0);
+		else if (bitDepth <= 10) reinterpret_cast<unsigned short*>(out)[i] = (unsigned short)((double)s * 1023.0);
+		else if (bitDepth <= 12) reinterpret_cast<unsigned short*>(out)[i] = (unsigned short)((double)s * 4095.0);
+		else if (bitDepth <= 16) reinterpret_cast<unsigned short*>(out)[i] = (unsigned short)((double)s * 65535.0);
+		else if (bitDepth <= 24) reinterpret_cast<unsigned int*>(out)[i] = (unsigned int)(s * 16777215.0f);
+		else reinterpret_cast<unsigned int*>(out)[i] = (unsigned int)(s * 4294967295.0f);
+	}
+}
+cudaError_t launch_float_to_output(void* out, const float* in, int bitDepth, long long n, int smCount, cudaStream_t st) {
+	long long blocks = (n + 255) / 256;
+	if (blocks > (long long)smCount * 16) blocks = (long long)smCount * 16;
+	float_to_output_kernel<<<(int)blocks, 256, 0, st>>>(out, in, bitDepth, n);
+	return cudaGetLastError();
+}
+
+}  // namespace octb200

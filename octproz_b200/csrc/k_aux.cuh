@@ -1,0 +1,56 @@
+/*
+ * k_aux.cuh -- argument blocks and launchers of the kernels in k_aux.cu and k_fused_*.cu.
+ */
+#pragma once
+#include "k_fused.cuh"
+
+namespace octb200 {
+
+/* generic pre-FFT kernel (any N, u8/u16/u32 container): raw -> float2 FFT input in HBM */
+struct PreArgs {
+	const void* raw;
+	float2* out;            /* [lines][N] */
+	const float4* lutW;     /* N entries, natural order (R = 1 layout), global memory */
+	const float4* lutB;
+	long long totalSamples;
+	int lines;
+	int N;
+	int shiftBits;
+	int W;
+	int HB, HA;
+	int useBulk;            /* 1: cp.async.bulk staging (16-byte aligned geometry), 0: plain loads */
+};
+
+/* post kernel after cuFFT: complex [lines][N] -> float [lines][N/2] */
+struct PostArgs {
+	const float2* in;
+	float* out;
+	const float2* meanLine;
+	const float* ppbg;
+	EpiConsts epi;
+	int lines, N, A;
+	int flip;
+	unsigned bscanBase;
+};
+
+void launch_fill_phase(float2* ph, const float* phase, int n, cudaStream_t st);
+cudaError_t launch_pre(const PreArgs& a, int rawBytes, int sa, bool roll, int smCount, cudaStream_t st);
+cudaError_t launch_post(const PostArgs& a, int smCount, cudaStream_t st);
+cudaError_t launch_fpn_minvar(float2* meanLine, const float2* in, int bins, int stride, int height, cudaStream_t st);
+cudaError_t launch_sinusoidal(float* out, const float* in, const float* curve, int H, int A, long long samples,
+                              int ppbgOn, const float* ppbg, float w, float o, int smCount, cudaStream_t st);
+cudaError_t launch_ppbg_record(float* bg, const float* data, int H, int A, cudaStream_t st);
+cudaError_t launch_ppbg_remove(float* data, const float* bg, float w, float o, int H, long long samples, int smCount, cudaStream_t st);
+cudaError_t launch_bscan_frame(float* disp, const float* vol, unsigned Btot, unsigned F, unsigned frameNr, unsigned nFrames, int fn, cudaStream_t st);
+cudaError_t launch_enface_frame(float* disp, const float* vol, unsigned W, unsigned E, unsigned frameNr, unsigned nFrames, int fn, cudaStream_t st);
+cudaError_t launch_volume_u8(uint8_t* tex, const float* buf, long long samples, unsigned bufferNr, unsigned B, unsigned A, unsigned Btot,
+                             unsigned depth, int smCount, cudaStream_t st);
+cudaError_t launch_float_to_output(void* out, const float* in, int bitDepth, long long n, int smCount, cudaStream_t st);
+
+/* fused / own-FFT kernel.  R = N/1024 (1 or 2).  Returns cudaErrorInvalidConfiguration if the shared
+ * memory budget cannot hold even one line group (huge rolling window). */
+cudaError_t launch_fused(int R, int sa, bool roll, int src, const FusedArgs& a, int smCount, cudaStream_t st);
+/* the CTA shape launch_fused will use (for reports): */
+void fused_launch_shape(int R, int sa, bool roll, int src, int HB, int HA, int smCount, int lines, int* grid, int* threads, int* smem);
+
+}  // namespace octb200

@@ -1,0 +1,238 @@
+/*
+ * k_fused.cuh -- the hot kernel: one launch takes raw u16 spectra to finished B-scan lines.
+ *
+ *   raw line --cp.async.bulk (TMA 1-D) + mbarrier, double buffered per line group--> shared memory
+ *     -> exact u16->fp32 slot conversion [+ rolling-mean background removal]          (cuda_code.cu:109-211)
+ *     -> 4-tap / 16-tap resampling x window x dispersion phasor from LUTs             (cuda_code.cu:213-489)
+ *     -> 32x32 four-step inverse FFT, registers + one shared-memory transpose          (cuda_code.cu:1514-1515)
+ *     -> fixed-pattern-noise subtract, |.|^2, log/linear scale, truncate to N/2,
+ *        B-scan flip folded into the store address, optional background removal        (cuda_code.cu:567-584,699-807)
+ *     -> coalesced fp32 stores.   HBM traffic: 2 B in + 2 B out per raw sample, nothing in between.
+ *
+ * A "line group" is R = N/1024 warps working on one A-scan (R = 1: N = 1024, R = 2: N = 2048: two interleaved
+ * 1024-point transforms combined by one radix-2 step).  Groups never synchronise with each other: each owns
+ * its two TMA slots, its mbarriers and its exchange tile; the CTA is persistent and strides over the lines.
+ *
+ * SRC_CPLX variant (OCTB200_FFT_SPLIT): the FFT input comes as float2 from HBM (written by the pre-FFT
+ * kernel) -- "own Stockham-style FFT with fused epilogue", BASELINE config 3.
+ */
+#pragma once
+#include "oct_device.cuh"
+
+namespace octb200 {
+
+template <int R> struct FusedCfg {
+	static constexpr int N = 1024 * R;
+	static constexpr int MAX_THREADS = (R == 1) ? 384 : 256;
+};
+
+/* shared-memory layout, shared by host (sizing) and device (carving) */
+struct FusedSmem {
+	int offW, offB, offTw, offCtw, offMean, offPpbg, offGroups;
+	int slotBytes, workBytes, groupBytes;
+	int total;
+};
+__host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll, int src, int HB, int HA, int groups) {
+	const int N = 1024 * R, H = N / 2;
+	FusedSmem L;
+	int off = 0;
+	L.offW = off;    off += (src == SRC_RAW16 && sa == SA_TAPS4) ? N * 16 : 0;
+	L.offB = off;    off += (src == SRC_RAW16) ? N * 16 : 0;
+	L.offTw = off;   off += 1024 * 8;
+	L.offCtw = off;  off += (R == 2) ? 1024 * 8 : 0;
+	L.offMean = off; off += H * 8;
+	L.offPpbg = off; off += H * 4;
+	off = align_up(off, 128);
+	L.offGroups = off;
+	const int SE = HB + N + HA;
+	L.slotBytes = (src == SRC_RAW16) ? align_up(SE * 2, 128) : 0;
+	int work = R * XBUF_BYTES;
+	if (src == SRC_RAW16) {
+		int w2 = align_up(SE * 4, 16) + (roll ? align_up((SE + 1) * 4, 16) : 0);
+		if (w2 > work) work = w2;
+	}
+	L.workBytes = align_up(work, 128);
+	L.groupBytes = 2 * L.slotBytes + L.workBytes + 128 /* mbarriers */;
+	L.total = L.offGroups + groups * L.groupBytes;
+	return L;
+}
+
+template <int R>
+__device__ __forceinline__ void group_sync(int barId) {
+	if constexpr (R == 1) __syncwarp();
+	else named_bar_sync(barId, 32 * R);
+}
+
+/* one lane: start the asynchronous load of raw line `gline` (with halos) into `slot` */
+template <int R>
+__device__ __forceinline__ void issue_line_load(const FusedArgs& a, int gline, unsigned char* slot, uint64_t* bar) {
+	constexpr int N = 1024 * R;
+	const long long lo = (long long)gline * N - a.HB;
+	const long long hi = (long long)gline * N + N + a.HA;
+	const long long clo = lo < 0 ? 0 : lo;
+	const long long chi = hi > a.totalSamples ? a.totalSamples : hi;
+	if (clo > lo) { for (long long q = 0; q < clo - lo; q += 8) *reinterpret_cast<uint4*>(slot + q * 2) = make_uint4(0, 0, 0, 0); }
+	if (chi < hi) { for (long long q = chi - lo; q < hi - lo; q += 8) *reinterpret_cast<uint4*>(slot + q * 2) = make_uint4(0, 0, 0, 0); }
+	const uint32_t bytes = (uint32_t)((chi - clo) * 2);
+	mbar_arrive_expect_tx(bar, bytes);
+	bulk_g2s(slot + (clo - lo) * 2, a.raw + clo, bytes, bar);
+}
+
+template <int R, int SA, bool ROLL, int SRC>
+__global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(const FusedArgs a) {
+	constexpr int N = 1024 * R;
+	constexpr int H = N / 2;
+	extern __shared__ __align__(128) unsigned char smem[];
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int groupsPerCta = (blockDim.x >> 5) / R;
+	const int grp = warp / R;          /* line group within the CTA */
+	const int p = warp % R;            /* warp within the group = sub-sequence parity */
+	const int tig = p * 32 + lane;     /* thread in group */
+	const FusedSmem L = fused_smem_layout(R, SA, ROLL, SRC, a.HB, a.HA, groupsPerCta);
+
+	const float4* sW = reinterpret_cast<const float4*>(smem + L.offW);
+	const float4* sB = reinterpret_cast<const float4*>(smem + L.offB);
+	const float2* sTw = reinterpret_cast<const float2*>(smem + L.offTw);
+	const float2* sCtw = reinterpret_cast<const float2*>(smem + L.offCtw);
+	const float2* sMean = reinterpret_cast<const float2*>(smem + L.offMean);
+	const float* sPpbg = reinterpret_cast<const float*>(smem + L.offPpbg);
+
+	/* ---- one-time table fill (all threads) ---- */
+	{
+		auto fill = [&](int off, const void* src, int bytes) {
+			const uint4* s = reinterpret_cast<const uint4*>(src);
+			uint4* d = reinterpret_cast<uint4*>(smem + off);
+			for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
+		};
+		if constexpr (SRC == SRC_RAW16) {
+			if constexpr (SA == SA_TAPS4) fill(L.offW, a.lutW, N * 16);
+			fill(L.offB, a.lutB, N * 16);
+		}
+		fill(L.offTw, a.tw, 1024 * 8);
+		if constexpr (R == 2) fill(L.offCtw, a.ctw, 1024 * 8);
+		if (a.epi.fpn && a.cplxOut == nullptr) fill(L.offMean, a.meanLine, H * 8);
+		if (a.epi.ppbg) fill(L.offPpbg, a.ppbg, H * 4);
+	}
+
+	unsigned char* gbase = smem + L.offGroups + grp * L.groupBytes;
+	unsigned char* slot0 = gbase;
+	unsigned char* slot1 = gbase + L.slotBytes;
+	unsigned char* work = gbase + 2 * L.slotBytes;
+	uint64_t* bars = reinterpret_cast<uint64_t*>(work + L.workBytes);
+	float2* tile = reinterpret_cast<float2*>(work) + p * XBUF_FLOAT2;
+	float2* partnerTile = reinterpret_cast<float2*>(work) + (R == 2 ? (1 - p) : 0) * XBUF_FLOAT2;
+	const int barId = 1 + grp;
+
+	const int SE = a.HB + N + a.HA;
+	float* fslot = reinterpret_cast<float*>(work);
+	unsigned* prefix = reinterpret_cast<unsigned*>(work + align_up(SE * 4, 16));
+
+	const int G = gridDim.x * groupsPerCta;
+	const int g0 = blockIdx.x * groupsPerCta + grp;
+
+	if constexpr (SRC == SRC_RAW16) {
+		if (tig == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+	}
+	__syncthreads();
+	if constexpr (SRC == SRC_RAW16) {
+		if (tig == 0) {
+			if (g0 < a.lines) issue_line_load<R>(a, g0, slot0, &bars[0]);
+			if (g0 + G < a.lines) issue_line_load<R>(a, g0 + G, slot1, &bars[1]);
+		}
+	}
+
+	int it = 0;
+	for (int gline = g0; gline < a.lines; gline += G, ++it) {
+		float2 v[32];
+
+		if constexpr (SRC == SRC_RAW16) {
+			unsigned char* slot = (it & 1) ? slot1 : slot0;
+			uint64_t* bar = &bars[it & 1];
+			mbar_wait(bar, (uint32_t)((it >> 1) & 1));
+
+			/* ---- slot conversion: inputToCufftComplex[_and_bitshift] once per sample (cuda_code.cu:109-147) ---- */
+			{
+				const uint2* s2 = reinterpret_cast<const uint2*>(slot);
+				float4* f4 = reinterpret_cast<float4*>(fslot);
+				for (int q4 = tig; q4 < SE / 4; q4 += 32 * R) {
+					uint2 w = s2[q4];
+					if (a.shiftBits) { w.x = (w.x >> 4) & 0x0FFF0FFFu; w.y = (w.y >> 4) & 0x0FFF0FFFu; }
+					f4[q4] = make_float4(u16lo_to_float(w.x), u16hi_to_float(w.x), u16lo_to_float(w.y), u16hi_to_float(w.y));
+				}
+			}
+			if constexpr (ROLL) {
+				/* ---- rolling-mean background (cuda_code.cu:165-211): exact integer prefix sums, windows clipped per line ---- */
+				if (p == 0) {
+					const uint16_t* s16 = reinterpret_cast<const uint16_t*>(slot);
+					unsigned carry = 0;
+					if (lane == 0) prefix[0] = 0;
+					for (int c = 0; c < SE; c += 32) {
+						const int q = c + lane;
+						unsigned x = (q < SE) ? ((unsigned)s16[q] >> a.shiftBits) : 0u;
+#pragma unroll
+						for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+						if (q < SE) prefix[q + 1] = carry + x;
+						carry += __shfl_sync(0xffffffffu, x, 31);
+					}
+				}
+			}
+			group_sync<R>(barId);
+			/* raw slot consumed: refill it with the line this group handles two iterations from now */
+			if (tig == 0 && gline + 2 * G < a.lines) issue_line_load<R>(a, gline + 2 * G, slot, bar);
+			if constexpr (ROLL) {
+				const int W = a.W;
+				for (int q = tig; q < SE; q += 32 * R) {
+					int lo, hi;
+					if (q < a.HB) { lo = 0; hi = a.HB - 1; }
+					else if (q >= a.HB + N) { lo = a.HB + N; hi = SE - 1; }
+					else { lo = a.HB; hi = a.HB + N - 1; }
+					const int s = max(lo, q - W + 1), e = min(hi, q + W);
+					const float mean = __fdividef((float)(prefix[e + 1] - prefix[s]), (float)(e - s + 1));
+					fslot[q] -= mean;
+				}
+				group_sync<R>(barId);
+			}
+
+			const float* f = fslot + a.HB;
+			/* the reference clamps the Lanczos line offset to >= 8 (cuda_code.cu:313): line 0 of the buffer is read 8 samples late */
+			const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
+			stage_a<SA, R>(lane, p, f, shift, sW, sB, v);
+			group_sync<R>(barId);          /* all gathers done before the exchange tile (aliasing the slot) is written */
+		} else {
+			const float2* in = a.cin + (size_t)gline * N;
+#pragma unroll
+			for (int j = 0; j < 32; ++j) v[j] = __ldg(in + R * (lane + 32 * j) + p);
+		}
+
+		/* ---- 1024-point inverse FFT of this warp's sub-sequence ---- */
+		fft32_inv_dif(v);
+		exchange_store(lane, v, tile, sTw);
+		__syncwarp();
+		exchange_load(lane, v, tile);
+		fft32_inv_dif(v);
+
+		if constexpr (R == 2) {
+			__syncwarp();                  /* own tile fully read before it is reused for the hand-over */
+			combine_store(lane, p, v, tile, sCtw);
+			group_sync<R>(barId);
+			combine_load(lane, p, v, partnerTile);
+		}
+
+		/* ---- epilogue ---- */
+		if (a.cplxOut != nullptr) {
+			float2* o = a.cplxOut + (size_t)gline * H;
+			if (R == 1 || p == 0) epilogue_complex<0>(lane, v, o); else epilogue_complex<16>(lane, v, o);
+		} else {
+			int b = gline / a.A, al = gline - b * a.A;
+			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u) al = a.A - 1 - al;
+			float* o = a.out + ((size_t)b * a.A + al) * H;
+			if (R == 1 || p == 0) epilogue_scaled<0>(lane, v, a.epi, sMean, sPpbg, o); else epilogue_scaled<16>(lane, v, a.epi, sMean, sPpbg, o);
+		}
+		group_sync<R>(barId);              /* tile / slot reads finished before the next line's conversion overwrites them */
+	}
+}
+
+}  // namespace octb200

@@ -1,0 +1,77 @@
+/*
+ * oct_device.cuh -- sm_100a device helpers: mbarrier + bulk-copy (TMA, UBLKCP) staging, named barriers,
+ * exact integer->float conversion on the ALU pipes, kernel argument blocks.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "oct_phases.cuh"
+
+namespace octb200 {
+
+/* ---------------- mbarrier / bulk async copy (cp.async.bulk = TMA 1-D, SASS UBLKCP) ---------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred p;\n\t"
+	    "OCT_WAIT:\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+	    "@p bra OCT_DONE;\n\t"
+	    "bra OCT_WAIT;\n\t"
+	    "OCT_DONE:\n\t"
+	    "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* global -> shared bulk copy completing on an mbarrier; dst/src 16-byte aligned, bytes % 16 == 0 */
+__device__ __forceinline__ void bulk_g2s(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+/* sub-block barrier among `threads` threads (multiple of 32) */
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+/* ---------------- exact u16 -> fp32 without the conversion pipe ----------------
+ * 0x4B000000 | v is the float 2^23 + v; subtracting 2^23 is exact for v < 2^23.  Same value as
+ * __uint2float_rd(in[index]) of inputToCufftComplex (cuda_code.cu:118-121). */
+__device__ __forceinline__ float u16lo_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.0f; }
+__device__ __forceinline__ float u16hi_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f; }
+
+/* ---------------- argument block of the fused / own-FFT kernels ---------------- */
+struct FusedArgs {
+	const uint16_t* raw;     /* SRC_RAW16: [lines][N] u16 (whole raw buffer, halo reads clip to [0,totalSamples)) */
+	const float2* cin;       /* SRC_CPLX : [lines][N] float2 FFT input written by the pre-FFT kernel */
+	float* out;              /* [lines][N/2] processed output slab (flip folded into the line address) */
+	float2* cplxOut;         /* != NULL: write the pre-FPN complex bins [lines][N/2] instead (FPN determination pass) */
+	const float4* lutW;      /* N tap-weight entries (SA_TAPS4) */
+	const float4* lutB;      /* N entries */
+	const float2* tw;        /* 1024 inter-pass twiddles */
+	const float2* ctw;       /* 1024 combine twiddles (R == 2) */
+	const float2* meanLine;  /* N/2 */
+	const float* ppbg;       /* N/2 */
+	EpiConsts epi;
+	long long totalSamples;
+	int lines;
+	int A;
+	int flip;
+	unsigned bscanBase;
+	int shiftBits;
+	int W;
+	int HB, HA;
+};
+
+enum { SRC_RAW16 = 0, SRC_CPLX = 1 };
+
+}  // namespace octb200

@@ -1,0 +1,214 @@
+/*
+ * oct_phases.cuh -- the per-lane phases of the fused OCT kernel, written as
+ * __host__ __device__ functions of (lane, register file, shared-memory views) so that the
+ * lane/register/bank maps can be executed on the CPU by tests/emu (test-only emulator).
+ *
+ * What each phase restates of the reference (paths under /root/reference/octproz_project/octproz/src):
+ *   stage A   : inputToCufftComplex (cuda_code.cu:109-147, done once per sample in the slot conversion),
+ *               klinearization{,Cubic,Lanczos}AndWindowingAndDispersionCompensation (cuda_code.cu:413-489)
+ *               and every other branch of the dispatch table (cuda_code.cu:1448-1511) through LUT contents
+ *   FFT       : cufftExecC2C CUFFT_INVERSE (cuda_code.cu:1514-1515), as a 32x32 four-step transform
+ *   epilogue  : meanALineSubtraction (567-584), postProcessTruncateLog/Lin (699-741), cuda_bscanFlip (787-807,
+ *               folded into the store address), postProcessBackgroundRemoval (757-767)
+ */
+#pragma once
+#include "fft_core.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace octb200 {
+/* transcendental forms the reference gets from --use_fast_math (octproz/pri/cuda.pri:54): MUFU approximations */
+OCT_HD float oct_lg2(float x) {
+#if defined(__CUDA_ARCH__)
+	return __log2f(x);
+#else
+	return log2f(x);
+#endif
+}
+OCT_HD float oct_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+	float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+	return sqrtf(x);
+#endif
+}
+}  // namespace octb200
+#define OCT_LG2(x) oct_lg2(x)
+#define OCT_SQRT(x) oct_sqrt(x)
+#define OCT_FMA(a, b, c) fmaf(a, b, c)
+
+namespace octb200 {
+
+constexpr int XPITCH = 34;                         /* float2 pitch of the 32x32 exchange tile (bank-conflict free for 128-bit reads) */
+constexpr int XBUF_FLOAT2 = 32 * XPITCH;           /* per warp */
+constexpr int XBUF_BYTES = XBUF_FLOAT2 * 8;
+
+/* stage-A selector */
+enum { SA_NONE = 0, SA_TAPS4 = 1, SA_LANCZOS = 2 };
+
+struct EpiConsts {
+	float scaleA;      /* log: coeff*10*log10(2)/(max-min) applied to log2(p);  lin: coeff/((N/2)*(max-min)) applied to sqrt(p) */
+	float scaleB;      /* additive constant (cuda_code.cu:718 / :739 folded on the host in double) */
+	int logMode;
+	int fpn;           /* subtract meanLine[z] before the magnitude */
+	int ppbg;          /* fold postProcessBackgroundRemoval into the store */
+	float ppbgWeight, ppbgOffset;
+};
+
+OCT_HD int lut_int(float f) {
+#if defined(__CUDA_ARCH__)
+	return __float_as_int(f);
+#else
+	int i; std::memcpy(&i, &f, 4); return i;
+#endif
+}
+
+/* ---- stage A, one sample.  f points at slot element 0 of the CURRENT line (halo before it). ----
+ * LUT B = { tap base (int bits), window*cos(phi), window*sin(phi), frac }  (per sample m)
+ * LUT W = { w0, w1, w2, w3 }  four tap weights (linear / Catmull-Rom, cuda_code.cu:213-295) */
+OCT_HD float2 sample_taps4(const float* f, float4 W, float4 B) {
+	const int nb = lut_int(B.x);
+	float y = W.x * f[nb];
+	y = OCT_FMA(W.y, f[nb + 1], y);
+	y = OCT_FMA(W.z, f[nb + 2], y);
+	y = OCT_FMA(W.w, f[nb + 3], y);
+	return make_float2(y * B.y, y * B.z);
+}
+
+OCT_HD float2 sample_none(const float* f, int m, float4 B) {
+	const float y = f[m];
+	return make_float2(y * B.y, y * B.z);
+}
+
+/* cuda_code.cu:297-302 + 304-326: 16 taps i=-7..8 around n0, kernel sinc(pi u) sinc(pi u / 8).
+ * shift = 8 for the very first line of the buffer (the reference's offset clamp, cuda_code.cu:313). */
+OCT_HD float lanczos8(float x) {
+	const float PI_F = 3.141592654f, PI8_F = 0.3926990817f;
+	const float ax = fabsf(x);
+#if defined(__CUDA_ARCH__)
+	const float s1 = __fdividef(__sinf(PI_F * ax), PI_F * ax);
+	const float s8 = __fdividef(__sinf(PI8_F * ax), PI8_F * ax);
+#else
+	const float s1 = sinf(PI_F * ax) / (PI_F * ax);
+	const float s8 = sinf(PI8_F * ax) / (PI8_F * ax);
+#endif
+	return (ax < 0.00001f) ? 1.0f : (s1 * s8);
+}
+
+OCT_HD float2 sample_lanczos(const float* f, int shift, float4 B) {
+	const int n0 = lut_int(B.x);
+	const float t = B.w;
+	float sum = 0.0f;
+#pragma unroll
+	for (int i = -7; i <= 8; ++i) {
+		const float y = f[shift + n0 + i];
+		sum += y * lanczos8(t - (float)i);
+	}
+	return make_float2(sum * B.y, sum * B.z);
+}
+
+/* ---- stage A for one lane: 32 samples s = lane + 32 j of sub-sequence p (m = R*s + p) ----
+ * LUTs are stored de-interleaved: entry of sample m lives at (m % R) * (N/R) + m / R. */
+template <int SA, int R>
+OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lutW, const float4* lutB,
+                    float2 (&v)[32]) {
+	const int base = p * 1024;
+#pragma unroll
+	for (int j = 0; j < 32; ++j) {
+		const int s = lane + 32 * j;
+		const float4 B = lutB[base + s];
+		if constexpr (SA == SA_TAPS4) v[j] = sample_taps4(f, lutW[base + s], B);
+		else if constexpr (SA == SA_NONE) v[j] = sample_none(f, R * s + p, B);
+		else v[j] = sample_lanczos(f, shift, B);
+	}
+}
+
+/* ---- four-step exchange: after pass 1, v[r] = V[k1 = bitrev5(r)] for column n2 = lane ----
+ * multiply by w_1024^{k1*n2} (tw[k1*32+n2]) and store row-major [k1][n2]. */
+OCT_HD void exchange_store(int lane, const float2 (&v)[32], float2* xbuf, const float2* tw) {
+	static_for<0, 32>([&](auto rc) {
+		constexpr int r = decltype(rc)::value;
+		constexpr int k1 = bitrev5(r);
+		float2 val = v[r];
+		if constexpr (k1 != 0) val = cmul(val, tw[k1 * 32 + lane]);
+		xbuf[k1 * XPITCH + lane] = val;
+	});
+}
+
+/* thread u = lane reads row k1 = u: v[n2] = Y[u][n2] */
+OCT_HD void exchange_load(int lane, float2 (&v)[32], const float2* xbuf) {
+	const float4* row = reinterpret_cast<const float4*>(xbuf + lane * XPITCH);
+#pragma unroll
+	for (int q = 0; q < 16; ++q) {
+		const float4 t = row[q];
+		v[2 * q] = make_float2(t.x, t.y);
+		v[2 * q + 1] = make_float2(t.z, t.w);
+	}
+}
+
+/* ---- R = 2 combine: X[k'] = E0[k'] + w_2048^{k'} E1[k'], k' = lane + 32*k2 < 1024 ----
+ * warp 0 finalises k2 < 16, warp 1 finalises k2 >= 16; each hands the other half over through its own tile. */
+OCT_HD void combine_store(int lane, int p, float2 (&v)[32], float2* ownTile, const float2* ctw) {
+	static_for<0, 32>([&](auto rc) {
+		constexpr int r = decltype(rc)::value;
+		constexpr int k2 = bitrev5(r);
+		if (p == 1) v[r] = cmul(v[r], ctw[lane + 32 * k2]);
+		if constexpr (k2 < 16) { if (p == 1) ownTile[k2 * 32 + lane] = v[r]; }
+		else                   { if (p == 0) ownTile[(k2 - 16) * 32 + lane] = v[r]; }
+	});
+}
+OCT_HD void combine_load(int lane, int p, float2 (&v)[32], const float2* partnerTile) {
+	static_for<0, 32>([&](auto rc) {
+		constexpr int r = decltype(rc)::value;
+		constexpr int k2 = bitrev5(r);
+		if constexpr (k2 < 16) {
+			if (p == 0) { const float2 o = partnerTile[k2 * 32 + lane]; v[r].x += o.x; v[r].y += o.y; }
+		} else {
+			if (p == 1) { const float2 o = partnerTile[(k2 - 16) * 32 + lane]; v[r].x += o.x; v[r].y += o.y; }
+		}
+	});
+}
+
+/* ---- epilogue for 16 outputs per lane: z = zBase + lane + 32*(k2 - K2LO), k2 in [K2LO, K2LO+16) ---- */
+OCT_HD float scale_output(float re, float im, const EpiConsts& e) {
+	const float pw = re * re + im * im;
+	return e.logMode ? OCT_FMA(OCT_LG2(pw), e.scaleA, e.scaleB) : OCT_FMA(OCT_SQRT(pw), e.scaleA, e.scaleB);
+}
+OCT_HD float saturate01(float v) {
+#if defined(__CUDA_ARCH__)
+	return __saturatef(v);
+#else
+	if (!(v > 0.0f)) return 0.0f;
+	return v > 1.0f ? 1.0f : v;
+#endif
+}
+
+template <int K2LO>
+OCT_HD void epilogue_scaled(int lane, const float2 (&v)[32], const EpiConsts& e, const float2* meanLine,
+                            const float* ppbg, float* outLine) {
+	static_for<0, 32>([&](auto rc) {
+		constexpr int r = decltype(rc)::value;
+		constexpr int k2 = bitrev5(r);
+		if constexpr (k2 >= K2LO && k2 < K2LO + 16) {
+			const int z = lane + 32 * k2;
+			float re = v[r].x, im = v[r].y;
+			if (e.fpn) { const float2 m = meanLine[z]; re -= m.x; im -= m.y; }
+			float o = scale_output(re, im, e);
+			if (e.ppbg) o = saturate01(o - OCT_FMA(e.ppbgWeight, ppbg[z], e.ppbgOffset));
+			outLine[z] = o;
+		}
+	});
+}
+
+/* complex store of the same 16 bins (fixed-pattern-noise determination pre-pass) */
+template <int K2LO>
+OCT_HD void epilogue_complex(int lane, const float2 (&v)[32], float2* outLine) {
+	static_for<0, 32>([&](auto rc) {
+		constexpr int r = decltype(rc)::value;
+		constexpr int k2 = bitrev5(r);
+		if constexpr (k2 >= K2LO && k2 < K2LO + 16) outLine[lane + 32 * k2] = v[r];
+	});
+}
+
+}  // namespace octb200

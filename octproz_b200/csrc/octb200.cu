@@ -1,0 +1,746 @@
+/*
+ * octb200.cu -- the C ABI (include/octb200.h): host orchestration of the B200 pipeline.
+ *
+ * Replaces, behind a handle, the file-scope-global state machine of the reference
+ * (cuda_code.cu:39-105 globals, :1067-1162 initializeCuda, :1389-1605 octCudaPipeline,
+ *  :1164-1212 cleanup).  Differences by design: per-handle state (re-entrant), status codes
+ * instead of exit(), per-slot raw buffers and events instead of eight round-robin streams sharing
+ * one set of buffers (latent cross-stream hazard), one fused kernel instead of 6-12.
+ */
+#include "../../include/octb200.h"
+#include "k_aux.cuh"
+#include "oct_curves.hpp"
+#include "oct_luts.hpp"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace octb200;
+
+namespace {
+
+std::string g_createError;
+
+/* ---- lazily bound cuFFT (only OCTB200_FFT_CUFFT touches it; the measured library baseline) ---- */
+struct CufftApi {
+	void* lib = nullptr;
+	int (*Plan1d)(int*, int, int, int) = nullptr;
+	int (*SetStream)(int, cudaStream_t) = nullptr;
+	int (*ExecC2C)(int, float2*, float2*, int) = nullptr;
+	int (*Destroy)(int) = nullptr;
+	bool load(std::string& err) {
+		if (lib) return true;
+		const char* names[] = { "libcufft.so.11", "/usr/local/cuda/lib64/libcufft.so.11", "libcufft.so" };
+		for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (lib) break; }
+		if (!lib) { err = "cannot load libcufft.so.11"; return false; }
+		Plan1d = (int (*)(int*, int, int, int))dlsym(lib, "cufftPlan1d");
+		SetStream = (int (*)(int, cudaStream_t))dlsym(lib, "cufftSetStream");
+		ExecC2C = (int (*)(int, float2*, float2*, int))dlsym(lib, "cufftExecC2C");
+		Destroy = (int (*)(int))dlsym(lib, "cufftDestroy");
+		if (!Plan1d || !SetStream || !ExecC2C || !Destroy) { err = "libcufft symbols missing"; return false; }
+		return true;
+	}
+};
+CufftApi g_cufft;
+constexpr int kCufftC2C = 0x29, kCufftInverse = 1;
+
+int rup(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct octb200_pipeline {
+	octb200_config cfg{};
+	octb200_params prm{};
+	int N = 0, A = 0, B = 0, V = 1, H = 0, lines = 0, rawBytes = 2, R = 1;
+	long long S = 0;
+	int device = 0, smCount = 148;
+	int mode = OCTB200_FFT_FUSED;
+	std::string err;
+
+	cudaStream_t sCompute = nullptr, sH2D = nullptr, sD2H = nullptr;
+	std::vector<void*> dRaw;
+	std::vector<cudaEvent_t> evRawReady, evRawFree;
+	int slot = -1;
+	const void* lastDeviceRaw = nullptr;
+	cudaEvent_t evTiming[8] = {};
+	cudaEvent_t evComputeDone = nullptr, evFloatCopied = nullptr, evConvFree[2] = {};
+	bool floatCopyPending = false, convPending[2] = { false, false };
+
+	float* dVolumeOwned = nullptr;
+	float* dVolume = nullptr;
+	float* dTmp = nullptr;            /* S/2 floats: sinusoidal source */
+	float2* dFft = nullptr;           /* S float2: SPLIT / CUFFT intermediate */
+	float2* dFpnScratch = nullptr; size_t fpnScratchElems = 0;
+	float2* dMeanLine = nullptr;
+	float* dPpbg = nullptr;
+	float* dPhase = nullptr; float2* dPhasor = nullptr;
+	float4 *dLutW = nullptr, *dLutB = nullptr;       /* fused layout (de-interleaved by R) */
+	float4 *dLutW1 = nullptr, *dLutB1 = nullptr;     /* natural order for the generic pre kernel */
+	float2 *dTw = nullptr, *dCtw = nullptr;
+	float* dSinCurve = nullptr;
+	void* dOutConv[2] = { nullptr, nullptr };
+	int cufftPlan = -1;
+
+	std::vector<float> hResample, hDispersion, hWindow, hPpbg;
+	bool haveResample = false, haveDispersion = false, haveWindow = false;
+	bool lutsDirty = true;
+	int lutSa = -1, lutInterp = -1; bool lutWin = false, lutDisp = false;
+
+	bool fpnDetermined = false;
+	unsigned bufferNumberInVolume = 0, streamedBuffers = 0, streamingBufferNumber = 0, floatStreamingBufferNumber = 0, currentBufferNr = 0;
+	void *hostBuf[2] = { nullptr, nullptr }; bool hostRegistered = false;
+	void *hostStream[2] = { nullptr, nullptr }; size_t hostStreamBytes = 0; bool hostStreamRegistered = false;
+	void *hostFloat[2] = { nullptr, nullptr }; size_t hostFloatBytes = 0; bool hostFloatRegistered = false;
+	octb200_host_callback cbStreaming = nullptr, cbFloat = nullptr, cbBackground = nullptr;
+	unsigned long long launches = 0;
+};
+
+namespace {
+
+int fail(octb200_pipeline* p, int code, const char* fmt, ...) {
+	char buf[512];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+	if (p) p->err = buf; else g_createError = buf;
+	return code;
+}
+
+#define CK(p, call)                                                                                   \
+	do {                                                                                              \
+		cudaError_t e_ = (call);                                                                      \
+		if (e_ != cudaSuccess) return fail((p), (e_ == cudaErrorMemoryAllocation) ? OCTB200_ERR_NOMEM : OCTB200_ERR_CUDA, \
+		                                   "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+	} while (0)
+
+template <typename T> int dalloc(octb200_pipeline* p, T** ptr, size_t count) {
+	CK(p, cudaMalloc((void**)ptr, count * sizeof(T)));
+	CK(p, cudaMemset(*ptr, 0, count * sizeof(T)));     /* allocateAndInitializeBuffer, cuda_code.cu:975-1015 */
+	return OCTB200_OK;
+}
+template <typename T> void dfree(T*& ptr) { if (ptr) { cudaFree(ptr); ptr = nullptr; } }
+
+void CUDART_CB host_cb_trampoline(void* data) {
+	auto* pair = static_cast<std::pair<octb200_host_callback, void*>*>(data);
+	if (pair->first) pair->first(pair->second);
+	delete pair;
+}
+int enqueue_callback(octb200_pipeline* p, cudaStream_t st, octb200_host_callback cb, void* buf) {
+	if (!cb) return OCTB200_OK;
+	auto* pair = new std::pair<octb200_host_callback, void*>(cb, buf);
+	CK(p, cudaLaunchHostFunc(st, host_cb_trampoline, pair));
+	return OCTB200_OK;
+}
+
+/* stage selection from the parameter block == the dispatch table of cuda_code.cu:1448-1511 */
+struct Stage { int sa; bool roll; int W; int HB, HA; };
+Stage select_stage(const octb200_pipeline* p) {
+	Stage s{};
+	const octb200_params& q = p->prm;
+	s.sa = q.resampling ? (q.resamplingInterpolation == OCTB200_INTERP_LANCZOS ? SA_LANCZOS : SA_TAPS4) : SA_NONE;
+	s.roll = q.backgroundRemoval != 0;
+	s.W = q.rollingAverageWindowSize < 1 ? 1 : q.rollingAverageWindowSize;
+	if (s.sa == SA_LANCZOS) { s.HB = 16 + (s.roll ? rup(s.W, 16) : 0); s.HA = s.HB; }
+	else { s.HB = 0; s.HA = 0; }
+	return s;
+}
+
+int rebuild_luts(octb200_pipeline* p) {
+	const octb200_params& q = p->prm;
+	const Stage st = select_stage(p);
+	const int N = p->N;
+	if (q.resampling && !p->haveResample) return fail(p, OCTB200_ERR_NOT_READY, "resampling enabled but no resample curve set");
+	if (q.dispersionCompensation && !p->haveDispersion) return fail(p, OCTB200_ERR_NOT_READY, "dispersion compensation enabled but no dispersion curve set");
+	if (q.windowing && !p->haveWindow) return fail(p, OCTB200_ERR_NOT_READY, "windowing enabled but no window curve set");
+	std::vector<float2> phasor;
+	if (q.dispersionCompensation) {
+		/* fillDispersivePhase on the device so that cos/sin are the same MUFU approximations the reference uses */
+		CK(p, cudaMemcpyAsync(p->dPhase, p->hDispersion.data(), sizeof(float) * N, cudaMemcpyHostToDevice, p->sCompute));
+		launch_fill_phase(p->dPhasor, p->dPhase, N, p->sCompute); p->launches++;
+		phasor.resize(N);
+		CK(p, cudaMemcpyAsync(phasor.data(), p->dPhasor, sizeof(float2) * N, cudaMemcpyDeviceToHost, p->sCompute));
+		CK(p, cudaStreamSynchronize(p->sCompute));
+	}
+	const float* res = q.resampling ? p->hResample.data() : nullptr;
+	const float* win = q.windowing ? p->hWindow.data() : nullptr;
+	const float2* ph = q.dispersionCompensation ? phasor.data() : nullptr;
+	const int interp = q.resamplingInterpolation == OCTB200_INTERP_CUBIC ? 1 : 0;
+	StageLuts l;
+	if (p->R >= 1 && (p->N == 1024 || p->N == 2048)) {
+		build_stage_luts(N, p->R, st.sa, interp, res, win, ph, l);
+		CK(p, cudaMemcpyAsync(p->dLutW, l.W.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
+		CK(p, cudaMemcpyAsync(p->dLutB, l.B.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
+		CK(p, cudaStreamSynchronize(p->sCompute));
+	}
+	build_stage_luts(N, 1, st.sa, interp, res, win, ph, l);
+	CK(p, cudaMemcpyAsync(p->dLutW1, l.W.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
+	CK(p, cudaMemcpyAsync(p->dLutB1, l.B.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	p->lutsDirty = false;
+	p->lutSa = st.sa; p->lutInterp = interp; p->lutWin = q.windowing != 0; p->lutDisp = q.dispersionCompensation != 0;
+	return OCTB200_OK;
+}
+
+EpiConsts epi_for(const octb200_pipeline* p, bool fpn, bool ppbg) {
+	const octb200_params& q = p->prm;
+	EpiConsts e = make_epi_consts(p->N, q.signalLogScaling, q.signalGrayscaleMin, q.signalGrayscaleMax, q.signalMultiplicator, q.signalAddend);
+	e.fpn = fpn ? 1 : 0; e.ppbg = ppbg ? 1 : 0;
+	e.ppbgWeight = q.postProcessBackgroundWeight; e.ppbgOffset = q.postProcessBackgroundOffset;
+	return e;
+}
+
+int ensure_fft_buffer(octb200_pipeline* p) {
+	if (!p->dFft) return dalloc(p, &p->dFft, (size_t)p->S);
+	return OCTB200_OK;
+}
+int ensure_fpn_scratch(octb200_pipeline* p, size_t elems) {
+	if (p->fpnScratchElems >= elems) return OCTB200_OK;
+	dfree(p->dFpnScratch); p->fpnScratchElems = 0;
+	int rc = dalloc(p, &p->dFpnScratch, elems);
+	if (rc == OCTB200_OK) p->fpnScratchElems = elems;
+	return rc;
+}
+
+FusedArgs fused_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, int lines) {
+	FusedArgs a{};
+	a.raw = static_cast<const uint16_t*>(dRaw);
+	a.cin = p->dFft;
+	a.lutW = p->dLutW; a.lutB = p->dLutB; a.tw = p->dTw; a.ctw = p->dCtw;
+	a.meanLine = p->dMeanLine; a.ppbg = p->dPpbg;
+	a.totalSamples = p->S; a.lines = lines; a.A = p->A;
+	a.flip = p->prm.bscanFlip; a.bscanBase = p->cfg.bscanIndexBase;
+	a.shiftBits = p->prm.bitshift ? 4 : 0; a.W = st.W; a.HB = st.HB; a.HA = st.HA;
+	return a;
+}
+PreArgs pre_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, int lines) {
+	PreArgs a{};
+	a.raw = dRaw; a.out = p->dFft; a.lutW = p->dLutW1; a.lutB = p->dLutB1;
+	a.totalSamples = p->S; a.lines = lines; a.N = p->N;
+	a.shiftBits = p->prm.bitshift ? 4 : 0; a.W = st.W;
+	/* halos in elements, multiples of 16 so every container type keeps 16-byte alignment */
+	a.HB = st.HB; a.HA = st.HA;
+	const bool aligned = ((reinterpret_cast<uintptr_t>(dRaw) & 15) == 0) && (((size_t)p->N * p->rawBytes) % 16 == 0);
+	a.useBulk = aligned ? 1 : 0;
+	return a;
+}
+
+/* the whole per-buffer chain on the compute stream; dRaw is device memory */
+int run_chain(octb200_pipeline* p, const void* dRaw) {
+	octb200_params& q = p->prm;
+	const Stage st = select_stage(p);
+	if (p->lutsDirty || st.sa != p->lutSa) { int rc = rebuild_luts(p); if (rc) return rc; }
+	if (q.postProcessBackgroundRemoval && p->hPpbg.empty() && !q.postProcessBackgroundRecordingRequested) {
+		/* the reference starts with a zeroed background line (cuda_code.cu:1122) */
+	}
+
+	/* slab of the processed volume (cuda_code.cu:1530-1535) */
+	if (p->V > 1) p->bufferNumberInVolume = (p->bufferNumberInVolume + 1) % (unsigned)p->V;
+	float* slab = p->dVolume + (size_t)(p->S / 2) * p->bufferNumberInVolume;
+
+	int mode = p->mode;
+	if (mode == OCTB200_FFT_FUSED) {
+		/* a huge rolling window with Lanczos halos may not fit the fused kernel's shared memory */
+		int g = 0, t = 0, sm = 0;
+		fused_launch_shape(p->R, st.sa, st.roll, SRC_RAW16, st.HB, st.HA, p->smCount, p->lines, &g, &t, &sm);
+		if (t < 32 * p->R) mode = OCTB200_FFT_SPLIT;
+	}
+	if (mode != OCTB200_FFT_FUSED) { int rc = ensure_fft_buffer(p); if (rc) return rc; }
+
+	if (p->floatCopyPending) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evFloatCopied, 0)); p->floatCopyPending = false; }
+
+	const bool fpn = q.fixedPatternNoiseRemoval != 0;
+	const bool sinus = q.sinusoidalScanCorrection != 0;
+	const bool ppbgOn = q.postProcessBackgroundRemoval != 0;
+	const bool ppbgRecord = ppbgOn && q.postProcessBackgroundRecordingRequested;
+	const bool ppbgFoldMain = ppbgOn && !ppbgRecord && !sinus;
+	const bool ppbgFoldSinus = ppbgOn && !ppbgRecord && sinus;
+	float* mainOut = slab;
+	if (sinus) { if (!p->dTmp) { int rc = dalloc(p, &p->dTmp, (size_t)(p->S / 2)); if (rc) return rc; } mainOut = p->dTmp; }
+
+	const bool determine = fpn && ((!q.continuousFixedPatternNoiseDetermination && !p->fpnDetermined) ||
+	                               q.continuousFixedPatternNoiseDetermination || q.redetermineFixedPatternNoise);   /* cuda_code.cu:1521 */
+	int fpnHeight = (int)q.bscansForNoiseDetermination * p->A;
+	if (fpnHeight > p->lines) fpnHeight = p->lines;
+
+	if (mode == OCTB200_FFT_CUFFT) {
+		PreArgs pa = pre_args(p, st, dRaw, p->lines);
+		CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++;
+		if (p->cufftPlan < 0) {
+			if (!g_cufft.load(p->err)) return OCTB200_ERR_CUDA;
+			int plan = 0;
+			if (g_cufft.Plan1d(&plan, p->N, kCufftC2C, p->lines) != 0) return fail(p, OCTB200_ERR_CUDA, "cufftPlan1d failed");
+			p->cufftPlan = plan;
+			g_cufft.SetStream(plan, p->sCompute);
+		}
+		if (g_cufft.ExecC2C(p->cufftPlan, p->dFft, p->dFft, kCufftInverse) != 0) return fail(p, OCTB200_ERR_CUDA, "cufftExecC2C failed");
+		p->launches++;
+		if (determine) {
+			CK(p, launch_fpn_minvar(p->dMeanLine, p->dFft, p->N, p->N, fpnHeight, p->sCompute)); p->launches++;
+			p->fpnDetermined = true; q.redetermineFixedPatternNoise = 0;
+		}
+		PostArgs po{};
+		po.in = p->dFft; po.out = mainOut; po.meanLine = p->dMeanLine; po.ppbg = p->dPpbg;
+		po.epi = epi_for(p, fpn, ppbgFoldMain); po.lines = p->lines; po.N = p->N; po.A = p->A;
+		po.flip = q.bscanFlip; po.bscanBase = p->cfg.bscanIndexBase;
+		CK(p, launch_post(po, p->smCount, p->sCompute)); p->launches++;
+	} else {
+		const int src = (mode == OCTB200_FFT_FUSED) ? SRC_RAW16 : SRC_CPLX;
+		if (determine) {
+			int rc = ensure_fpn_scratch(p, (size_t)fpnHeight * p->H); if (rc) return rc;
+			if (src == SRC_CPLX) { PreArgs pa = pre_args(p, st, dRaw, fpnHeight); CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++; }
+			FusedArgs fa = fused_args(p, st, dRaw, fpnHeight);
+			fa.cplxOut = p->dFpnScratch; fa.epi = epi_for(p, false, false);
+			CK(p, launch_fused(p->R, st.sa, st.roll, src, fa, p->smCount, p->sCompute)); p->launches++;
+			CK(p, launch_fpn_minvar(p->dMeanLine, p->dFpnScratch, p->H, p->H, fpnHeight, p->sCompute)); p->launches++;
+			p->fpnDetermined = true; q.redetermineFixedPatternNoise = 0;
+		}
+		if (src == SRC_CPLX) { PreArgs pa = pre_args(p, st, dRaw, p->lines); CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++; }
+		FusedArgs fa = fused_args(p, st, dRaw, p->lines);
+		fa.out = mainOut; fa.epi = epi_for(p, fpn, ppbgFoldMain);
+		CK(p, launch_fused(p->R, st.sa, st.roll, src, fa, p->smCount, p->sCompute)); p->launches++;
+	}
+
+	if (sinus) {
+		CK(p, launch_sinusoidal(slab, p->dTmp, p->dSinCurve, p->H, p->A, p->S / 2, ppbgFoldSinus ? 1 : 0, p->dPpbg,
+		                        q.postProcessBackgroundWeight, q.postProcessBackgroundOffset, p->smCount, p->sCompute)); p->launches++;
+	}
+	if (ppbgRecord) {
+		/* cuda_code.cu:1558-1567: record from the first B-scan of this buffer, hand it to the host, then remove */
+		CK(p, launch_ppbg_record(p->dPpbg, slab, p->H, p->A, p->sCompute)); p->launches++;
+		p->hPpbg.resize(p->H);
+		CK(p, cudaMemcpyAsync(p->hPpbg.data(), p->dPpbg, sizeof(float) * p->H, cudaMemcpyDeviceToHost, p->sCompute));
+		int rc = enqueue_callback(p, p->sCompute, p->cbBackground, p->hPpbg.data()); if (rc) return rc;
+		q.postProcessBackgroundRecordingRequested = 0;
+		CK(p, launch_ppbg_remove(slab, p->dPpbg, q.postProcessBackgroundWeight, q.postProcessBackgroundOffset, p->H, p->S / 2, p->smCount, p->sCompute)); p->launches++;
+	}
+
+	/* ---- streaming to the host (cuda_code.cu:1357-1386,1595-1604) ---- */
+	const bool wantFloat = q.streamFloatToHost && p->hostFloat[0] && p->hostFloat[1];
+	const bool wantConv = q.streamToHost && p->hostStream[0] && p->hostStream[1];
+	if (wantFloat || wantConv) CK(p, cudaEventRecord(p->evComputeDone, p->sCompute));
+	if (wantFloat) {
+		p->floatStreamingBufferNumber = (p->floatStreamingBufferNumber + 1) % 2;
+		void* dst = p->hostFloat[p->floatStreamingBufferNumber];
+		CK(p, cudaStreamWaitEvent(p->sD2H, p->evComputeDone, 0));
+		CK(p, cudaMemcpyAsync(dst, slab, (size_t)(p->S / 2) * sizeof(float), cudaMemcpyDeviceToHost, p->sD2H));
+		CK(p, cudaEventRecord(p->evFloatCopied, p->sD2H)); p->floatCopyPending = true;
+		int rc = enqueue_callback(p, p->sD2H, p->cbFloat, dst); if (rc) return rc;
+	}
+	if (wantConv) {
+		p->currentBufferNr = p->bufferNumberInVolume;
+		if (p->streamedBuffers % (q.streamingBuffersToSkip + 1) == 0) {
+			p->streamedBuffers = 0;
+			p->streamingBufferNumber = (p->streamingBufferNumber + 1) % 2;
+			const int i = (int)p->streamingBufferNumber;
+			if (p->convPending[i]) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evConvFree[i], 0)); p->convPending[i] = false; }
+			CK(p, launch_float_to_output(p->dOutConv[i], slab, (int)p->cfg.bitDepth, p->S / 2, p->smCount, p->sCompute)); p->launches++;
+			CK(p, cudaEventRecord(p->evComputeDone, p->sCompute));
+			CK(p, cudaStreamWaitEvent(p->sD2H, p->evComputeDone, 0));
+			CK(p, cudaMemcpyAsync(p->hostStream[i], p->dOutConv[i], (size_t)(p->S / 2) * p->rawBytes, cudaMemcpyDeviceToHost, p->sD2H));
+			CK(p, cudaEventRecord(p->evConvFree[i], p->sD2H)); p->convPending[i] = true;
+			int rc = enqueue_callback(p, p->sD2H, p->cbStreaming, p->hostStream[i]); if (rc) return rc;
+		}
+		p->streamedBuffers++;
+	}
+	return OCTB200_OK;
+}
+
+int use_device(const octb200_pipeline* p) { return cudaSetDevice(p->device) == cudaSuccess ? 0 : -1; }
+
+}  // namespace
+
+/* ====================================================================== C ABI */
+
+extern "C" {
+
+int octb200_version(void) { return OCTB200_VERSION; }
+
+void octb200_default_params(octb200_params* o) {
+	if (!o) return;
+	std::memset(o, 0, sizeof(*o));
+	o->signalGrayscaleMin = 0.0f; o->signalGrayscaleMax = 60.0f; o->signalMultiplicator = 1.0f; o->signalAddend = 0.0f;
+	o->rollingAverageWindowSize = 1; o->bscansForNoiseDetermination = 1;
+	o->postProcessBackgroundWeight = 1.0f; o->postProcessBackgroundOffset = 0.0f;
+}
+
+const char* octb200_last_error(const octb200_pipeline* p) { return p ? p->err.c_str() : g_createError.c_str(); }
+int octb200_effective_fft_mode(const octb200_pipeline* p) { return p ? p->mode : OCTB200_ERR_INVALID; }
+
+int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
+	if (!cfg || !out) return fail(nullptr, OCTB200_ERR_INVALID, "null argument");
+	*out = nullptr;
+	if (cfg->samplesPerLine < 8 || (cfg->samplesPerLine & 1) || cfg->ascansPerBscan < 1 || cfg->bscansPerBuffer < 1 ||
+	    cfg->buffersPerVolume < 1 || cfg->bitDepth < 1 || cfg->bitDepth > 32)
+		return fail(nullptr, OCTB200_ERR_INVALID, "invalid acquisition geometry");
+	const long long S = (long long)cfg->samplesPerLine * cfg->ascansPerBscan * cfg->bscansPerBuffer;
+	if (S >= (1LL << 31)) return fail(nullptr, OCTB200_ERR_INVALID, "samples per buffer must be < 2^31 (as in the reference)");
+	int dev = cfg->device;
+	if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, OCTB200_ERR_CUDA, "no CUDA device"); }
+	if (cudaSetDevice(dev) != cudaSuccess) return fail(nullptr, OCTB200_ERR_CUDA, "cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(cudaGetLastError()));
+
+	auto* p = new octb200_pipeline();
+	p->cfg = *cfg; p->device = dev;
+	octb200_default_params(&p->prm);
+	p->N = (int)cfg->samplesPerLine; p->A = (int)cfg->ascansPerBscan; p->B = (int)cfg->bscansPerBuffer; p->V = (int)cfg->buffersPerVolume;
+	p->H = p->N / 2; p->lines = p->A * p->B; p->S = S;
+	p->rawBytes = cfg->bitDepth <= 8 ? 1 : (cfg->bitDepth <= 16 ? 2 : 4);   /* bytesPerSample, cuda_code.cu:1077 */
+	p->R = p->N == 2048 ? 2 : 1;
+	const bool fftSize = (p->N == 1024 || p->N == 2048);
+	int mode = cfg->fftMode;
+	if (mode == OCTB200_FFT_AUTO) mode = fftSize ? (p->rawBytes == 2 ? OCTB200_FFT_FUSED : OCTB200_FFT_SPLIT) : OCTB200_FFT_CUFFT;
+	if ((mode == OCTB200_FFT_FUSED && !(fftSize && p->rawBytes == 2)) || (mode == OCTB200_FFT_SPLIT && !fftSize) ||
+	    mode < OCTB200_FFT_FUSED || mode > OCTB200_FFT_CUFFT) {
+		delete p;
+		return fail(nullptr, OCTB200_ERR_INVALID, "fftMode %d unsupported for samplesPerLine=%u bitDepth=%u (FUSED: N in {1024,2048} and 9..16 bit; SPLIT: N in {1024,2048})",
+		            cfg->fftMode, cfg->samplesPerLine, cfg->bitDepth);
+	}
+	p->mode = mode;
+
+	int rc = OCTB200_OK;
+	auto bail = [&](int code) { g_createError = p->err; octb200_destroy(p); return code; };
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(p, OCTB200_ERR_CUDA, "cudaGetDeviceProperties failed"));
+	p->smCount = prop.multiProcessorCount;
+	if (prop.major < 10) return bail(fail(p, OCTB200_ERR_INVALID, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor));
+
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(p, e_ == cudaErrorMemoryAllocation ? OCTB200_ERR_NOMEM : OCTB200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
+#define RCC(call) do { rc = (call); if (rc) return bail(rc); } while (0)
+	CKC(cudaStreamCreateWithFlags(&p->sCompute, cudaStreamNonBlocking));
+	CKC(cudaStreamCreateWithFlags(&p->sH2D, cudaStreamNonBlocking));
+	CKC(cudaStreamCreateWithFlags(&p->sD2H, cudaStreamNonBlocking));
+	for (auto& e : p->evTiming) CKC(cudaEventCreate(&e));
+	CKC(cudaEventCreateWithFlags(&p->evComputeDone, cudaEventDisableTiming));
+	CKC(cudaEventCreateWithFlags(&p->evFloatCopied, cudaEventDisableTiming));
+	for (auto& e : p->evConvFree) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+	const int slots = cfg->rawSlots > 0 ? cfg->rawSlots : 2;
+	p->dRaw.assign(slots, nullptr); p->evRawReady.assign(slots, nullptr); p->evRawFree.assign(slots, nullptr);
+	for (int i = 0; i < slots; ++i) {
+		unsigned char* r = nullptr;
+		RCC(dalloc(p, &r, (size_t)S * p->rawBytes + 64)); p->dRaw[i] = r;
+		CKC(cudaEventCreateWithFlags(&p->evRawReady[i], cudaEventDisableTiming));
+		CKC(cudaEventCreateWithFlags(&p->evRawFree[i], cudaEventDisableTiming));
+	}
+	RCC(dalloc(p, &p->dVolumeOwned, (size_t)(S / 2) * p->V)); p->dVolume = p->dVolumeOwned;
+	RCC(dalloc(p, &p->dMeanLine, (size_t)p->N));
+	RCC(dalloc(p, &p->dPpbg, (size_t)p->H));
+	RCC(dalloc(p, &p->dPhase, (size_t)p->N));
+	RCC(dalloc(p, &p->dPhasor, (size_t)p->N));
+	RCC(dalloc(p, &p->dLutW, (size_t)p->N)); RCC(dalloc(p, &p->dLutB, (size_t)p->N));
+	RCC(dalloc(p, &p->dLutW1, (size_t)p->N)); RCC(dalloc(p, &p->dLutB1, (size_t)p->N));
+	RCC(dalloc(p, &p->dTw, (size_t)1024)); RCC(dalloc(p, &p->dCtw, (size_t)1024));
+	RCC(dalloc(p, &p->dSinCurve, (size_t)p->A));
+	{
+		unsigned char* c0 = nullptr; unsigned char* c1 = nullptr;
+		RCC(dalloc(p, &c0, (size_t)(S / 2) * p->rawBytes)); p->dOutConv[0] = c0;
+		RCC(dalloc(p, &c1, (size_t)(S / 2) * p->rawBytes)); p->dOutConv[1] = c1;
+	}
+	{
+		std::vector<float2> tw, ctw; build_twiddles_1024(tw); build_combine_twiddles_2048(ctw);
+		CKC(cudaMemcpy(p->dTw, tw.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
+		CKC(cudaMemcpy(p->dCtw, ctw.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
+		std::vector<float> sc(p->A); curves::sinusoidal(p->A, sc.data());    /* cuda_code.cu:1093 */
+		CKC(cudaMemcpy(p->dSinCurve, sc.data(), sizeof(float) * p->A, cudaMemcpyHostToDevice));
+	}
+#undef CKC
+#undef RCC
+	p->bufferNumberInVolume = (unsigned)p->V - 1;   /* cuda_code.cu:1146 */
+	*out = p;
+	return OCTB200_OK;
+}
+
+int octb200_destroy(octb200_pipeline* p) {
+	if (!p) return OCTB200_OK;
+	cudaSetDevice(p->device);
+	cudaDeviceSynchronize();
+	if (p->hostRegistered) octb200_unregister_host_buffers(p);
+	if (p->hostStreamRegistered) octb200_unregister_streaming_buffers(p);
+	if (p->hostFloatRegistered) octb200_unregister_float_streaming_buffers(p);
+	if (p->cufftPlan >= 0 && g_cufft.Destroy) g_cufft.Destroy(p->cufftPlan);
+	for (void*& r : p->dRaw) { if (r) cudaFree(r); r = nullptr; }
+	for (auto e : p->evRawReady) if (e) cudaEventDestroy(e);
+	for (auto e : p->evRawFree) if (e) cudaEventDestroy(e);
+	for (auto e : p->evTiming) if (e) cudaEventDestroy(e);
+	if (p->evComputeDone) cudaEventDestroy(p->evComputeDone);
+	if (p->evFloatCopied) cudaEventDestroy(p->evFloatCopied);
+	for (auto e : p->evConvFree) if (e) cudaEventDestroy(e);
+	dfree(p->dVolumeOwned); dfree(p->dTmp); dfree(p->dFft); dfree(p->dFpnScratch); dfree(p->dMeanLine); dfree(p->dPpbg);
+	dfree(p->dPhase); dfree(p->dPhasor); dfree(p->dLutW); dfree(p->dLutB); dfree(p->dLutW1); dfree(p->dLutB1);
+	dfree(p->dTw); dfree(p->dCtw); dfree(p->dSinCurve);
+	for (void*& c : p->dOutConv) { if (c) cudaFree(c); c = nullptr; }
+	if (p->sCompute) cudaStreamDestroy(p->sCompute);
+	if (p->sH2D) cudaStreamDestroy(p->sH2D);
+	if (p->sD2H) cudaStreamDestroy(p->sD2H);
+	delete p;
+	return OCTB200_OK;
+}
+
+/* ---------- parameters and curves ---------- */
+int octb200_set_params(octb200_pipeline* p, const octb200_params* prm) {
+	if (!p || !prm) return fail(p, OCTB200_ERR_INVALID, "null argument");
+	const octb200_params old = p->prm;
+	p->prm = *prm;
+	if (old.resampling != prm->resampling || old.resamplingInterpolation != prm->resamplingInterpolation ||
+	    old.windowing != prm->windowing || old.dispersionCompensation != prm->dispersionCompensation)
+		p->lutsDirty = true;
+	return OCTB200_OK;
+}
+
+static int set_curve(octb200_pipeline* p, std::vector<float>& dst, bool& have, const float* src, int n, const char* what) {
+	if (!p || !src) return fail(p, OCTB200_ERR_INVALID, "null argument");
+	if (n != p->N) return fail(p, OCTB200_ERR_INVALID, "%s curve length %d != samplesPerLine %d", what, n, p->N);
+	dst.assign(src, src + n); have = true; p->lutsDirty = true;
+	return OCTB200_OK;
+}
+int octb200_set_resample_curve(octb200_pipeline* p, const float* c, int n) {
+	int rc = set_curve(p, p->hResample, p->haveResample, c, n, "resample");
+	if (rc == OCTB200_OK) curves::clamp_resample(n, p->hResample.data());   /* octalgorithmparameters.cpp:167 also clamps custom curves */
+	return rc;
+}
+int octb200_set_dispersion_curve(octb200_pipeline* p, const float* c, int n) { return set_curve(p, p->hDispersion, p->haveDispersion, c, n, "dispersion"); }
+int octb200_set_window_curve(octb200_pipeline* p, const float* c, int n) { return set_curve(p, p->hWindow, p->haveWindow, c, n, "window"); }
+
+int octb200_set_postprocess_background(octb200_pipeline* p, const float* bg, int n) {
+	if (!p || !bg) return fail(p, OCTB200_ERR_INVALID, "null argument");
+	if (n != p->H) return fail(p, OCTB200_ERR_INVALID, "background length %d != samplesPerLine/2 %d", n, p->H);
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	p->hPpbg.assign(bg, bg + n);
+	CK(p, cudaMemcpyAsync(p->dPpbg, p->hPpbg.data(), sizeof(float) * n, cudaMemcpyHostToDevice, p->sCompute));
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	return OCTB200_OK;
+}
+int octb200_get_postprocess_background(octb200_pipeline* p, float* bg, int n) {
+	if (!p || !bg || n != p->H) return fail(p, OCTB200_ERR_INVALID, "bad argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	CK(p, cudaMemcpy(bg, p->dPpbg, sizeof(float) * n, cudaMemcpyDeviceToHost));
+	return OCTB200_OK;
+}
+int octb200_get_fpn_mean_line(octb200_pipeline* p, float* reIm, int n) {
+	if (!p || !reIm || n != p->N) return fail(p, OCTB200_ERR_INVALID, "bad argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	CK(p, cudaMemcpy(reIm, p->dMeanLine, sizeof(float2) * n, cudaMemcpyDeviceToHost));
+	return OCTB200_OK;
+}
+int octb200_set_fpn_mean_line(octb200_pipeline* p, const float* reIm, int n) {
+	if (!p || !reIm || n != p->N) return fail(p, OCTB200_ERR_INVALID, "bad argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	CK(p, cudaMemcpy(p->dMeanLine, reIm, sizeof(float2) * n, cudaMemcpyHostToDevice));
+	p->fpnDetermined = true;
+	return OCTB200_OK;
+}
+
+int octb200_make_resample_curve(int n, float c0, float c1, float c2, float c3, float* out) {
+	if (n < 4 || !out) return OCTB200_ERR_INVALID;
+	curves::resample(n, c0, c1, c2, c3, out); return OCTB200_OK;
+}
+int octb200_make_dispersion_curve(int n, float d0, float d1, float d2, float d3, float* out) {
+	if (n < 2 || !out) return OCTB200_ERR_INVALID;
+	curves::dispersion(n, d0, d1, d2, d3, out); return OCTB200_OK;
+}
+int octb200_make_window_curve(int type, float center, float fill, int n, float* out) {
+	if (n < 2 || !out || type < 0 || type > 5) return OCTB200_ERR_INVALID;
+	curves::window(type, center, fill, n, out); return OCTB200_OK;
+}
+int octb200_make_sinusoidal_curve(int ascans, float* out) {
+	if (ascans < 1 || !out) return OCTB200_ERR_INVALID;
+	curves::sinusoidal(ascans, out); return OCTB200_OK;
+}
+
+/* ---------- host buffers ---------- */
+int octb200_register_host_buffers(octb200_pipeline* p, void* h1, void* h2) {
+	if (!p || !h1) return fail(p, OCTB200_ERR_INVALID, "null argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	if (p->hostRegistered) octb200_unregister_host_buffers(p);
+	const size_t bytes = (size_t)p->S * p->rawBytes;
+	CK(p, cudaHostRegister(h1, bytes, cudaHostRegisterPortable));
+	if (h2 && h2 != h1) { cudaError_t e = cudaHostRegister(h2, bytes, cudaHostRegisterPortable); if (e != cudaSuccess) { cudaHostUnregister(h1); return fail(p, OCTB200_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); } }
+	p->hostBuf[0] = h1; p->hostBuf[1] = (h2 && h2 != h1) ? h2 : nullptr; p->hostRegistered = true;
+	return OCTB200_OK;
+}
+int octb200_unregister_host_buffers(octb200_pipeline* p) {
+	if (!p) return OCTB200_ERR_INVALID;
+	if (p->hostRegistered) { for (void*& h : p->hostBuf) { if (h) cudaHostUnregister(h); h = nullptr; } p->hostRegistered = false; }
+	return OCTB200_OK;
+}
+static int reg_pair(octb200_pipeline* p, void* h1, void* h2, size_t bytes, void** dst, size_t* dstBytes, bool* flag) {
+	if (!p || !h1 || !h2) return fail(p, OCTB200_ERR_INVALID, "null argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, cudaHostRegister(h1, bytes, cudaHostRegisterPortable));
+	cudaError_t e = cudaHostRegister(h2, bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) { cudaHostUnregister(h1); return fail(p, OCTB200_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+	dst[0] = h1; dst[1] = h2; *dstBytes = bytes; *flag = true;
+	return OCTB200_OK;
+}
+int octb200_register_streaming_buffers(octb200_pipeline* p, void* h1, void* h2, size_t bytes) {
+	if (p && bytes < (size_t)(p->S / 2) * p->rawBytes) return fail(p, OCTB200_ERR_INVALID, "streaming buffer too small");
+	return reg_pair(p, h1, h2, bytes, p ? p->hostStream : nullptr, p ? &p->hostStreamBytes : nullptr, p ? &p->hostStreamRegistered : nullptr);
+}
+int octb200_unregister_streaming_buffers(octb200_pipeline* p) {
+	if (!p) return OCTB200_ERR_INVALID;
+	if (p->hostStreamRegistered) { cudaStreamSynchronize(p->sD2H); for (void*& h : p->hostStream) { if (h) cudaHostUnregister(h); h = nullptr; } p->hostStreamRegistered = false; }
+	return OCTB200_OK;
+}
+int octb200_register_float_streaming_buffers(octb200_pipeline* p, void* h1, void* h2, size_t bytes) {
+	if (p && bytes < (size_t)(p->S / 2) * sizeof(float)) return fail(p, OCTB200_ERR_INVALID, "float streaming buffer too small");
+	return reg_pair(p, h1, h2, bytes, p ? p->hostFloat : nullptr, p ? &p->hostFloatBytes : nullptr, p ? &p->hostFloatRegistered : nullptr);
+}
+int octb200_unregister_float_streaming_buffers(octb200_pipeline* p) {
+	if (!p) return OCTB200_ERR_INVALID;
+	if (p->hostFloatRegistered) { cudaStreamSynchronize(p->sD2H); for (void*& h : p->hostFloat) { if (h) cudaHostUnregister(h); h = nullptr; } p->hostFloatRegistered = false; }
+	return OCTB200_OK;
+}
+int octb200_set_callbacks(octb200_pipeline* p, octb200_host_callback s, octb200_host_callback f, octb200_host_callback b) {
+	if (!p) return OCTB200_ERR_INVALID;
+	p->cbStreaming = s; p->cbFloat = f; p->cbBackground = b;
+	return OCTB200_OK;
+}
+
+/* ---------- hot path ---------- */
+int octb200_process_host(octb200_pipeline* p, const void* hRaw) {
+	if (!p) return OCTB200_ERR_INVALID;
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	if (!hRaw) {
+		if (p->slot < 0 && !p->lastDeviceRaw) return fail(p, OCTB200_ERR_NOT_READY, "no buffer has been uploaded yet");
+		return run_chain(p, p->slot >= 0 ? p->dRaw[p->slot] : p->lastDeviceRaw);
+	}
+	const int s = (p->slot + 1) % (int)p->dRaw.size();
+	const size_t bytes = (size_t)p->S * p->rawBytes;
+	CK(p, cudaStreamWaitEvent(p->sH2D, p->evRawFree[s], 0));       /* kernels that still read this slot */
+	CK(p, cudaMemcpyAsync(p->dRaw[s], hRaw, bytes, cudaMemcpyHostToDevice, p->sH2D));   /* cuda_code.cu:1404 */
+	CK(p, cudaEventRecord(p->evRawReady[s], p->sH2D));
+	CK(p, cudaStreamWaitEvent(p->sCompute, p->evRawReady[s], 0));
+	p->slot = s;
+	int rc = run_chain(p, p->dRaw[s]);
+	if (rc) return rc;
+	CK(p, cudaEventRecord(p->evRawFree[s], p->sCompute));
+	/* the producer may overwrite hRaw as soon as we return (processing.cpp:191) -- same contract as cuda_code.cu:1416-1419 */
+	CK(p, cudaEventSynchronize(p->evRawReady[s]));
+	return OCTB200_OK;
+}
+
+int octb200_process_device(octb200_pipeline* p, const void* dRaw) {
+	if (!p) return OCTB200_ERR_INVALID;
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	if (!dRaw) {
+		dRaw = p->lastDeviceRaw ? p->lastDeviceRaw : (p->slot >= 0 ? p->dRaw[p->slot] : nullptr);
+		if (!dRaw) return fail(p, OCTB200_ERR_NOT_READY, "no device buffer to re-process");
+	}
+	if (reinterpret_cast<uintptr_t>(dRaw) & 15) return fail(p, OCTB200_ERR_INVALID, "device raw pointer must be 16-byte aligned");
+	p->lastDeviceRaw = dRaw;
+	return run_chain(p, dRaw);
+}
+
+int octb200_sync(octb200_pipeline* p) {
+	if (!p) return OCTB200_ERR_INVALID;
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, cudaStreamSynchronize(p->sH2D));
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	CK(p, cudaStreamSynchronize(p->sD2H));
+	return OCTB200_OK;
+}
+uint32_t octb200_current_buffer_nr(const octb200_pipeline* p) { return p ? p->bufferNumberInVolume : 0; }
+
+/* ---------- results ---------- */
+float* octb200_output_device_ptr(octb200_pipeline* p, uint32_t nr) {
+	if (!p || nr >= (uint32_t)p->V) return nullptr;
+	return p->dVolume + (size_t)(p->S / 2) * nr;
+}
+int octb200_copy_output(octb200_pipeline* p, float* host, uint32_t nr) {
+	if (!p || !host || nr >= (uint32_t)p->V) return fail(p, OCTB200_ERR_INVALID, "bad argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	CK(p, cudaMemcpy(host, p->dVolume + (size_t)(p->S / 2) * nr, (size_t)(p->S / 2) * sizeof(float), cudaMemcpyDeviceToHost));
+	return OCTB200_OK;
+}
+int octb200_bind_output(octb200_pipeline* p, void* dVolume) {
+	if (!p) return OCTB200_ERR_INVALID;
+	if (dVolume && (reinterpret_cast<uintptr_t>(dVolume) & 15)) return fail(p, OCTB200_ERR_INVALID, "volume pointer must be 16-byte aligned");
+	p->dVolume = dVolume ? static_cast<float*>(dVolume) : p->dVolumeOwned;
+	return OCTB200_OK;
+}
+
+int octb200_bscan_frame(octb200_pipeline* p, uint32_t frameNr, uint32_t nFrames, int fn, float* dOut) {
+	if (!p || !dOut) return fail(p, OCTB200_ERR_INVALID, "null argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	const unsigned Btot = (unsigned)(p->B * p->V);
+	if (frameNr >= Btot) frameNr = 0;                                /* cuda_code.cu:1278 */
+	CK(p, launch_bscan_frame(dOut, p->dVolume, Btot, (unsigned)(p->H * p->A), frameNr, nFrames, fn, p->sCompute)); p->launches++;
+	return OCTB200_OK;
+}
+int octb200_enface_frame(octb200_pipeline* p, uint32_t frameNr, uint32_t nFrames, int fn, float* dOut) {
+	if (!p || !dOut) return fail(p, OCTB200_ERR_INVALID, "null argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	if (frameNr >= (unsigned)p->H) frameNr = 0;                      /* cuda_code.cu:1302 */
+	CK(p, launch_enface_frame(dOut, p->dVolume, (unsigned)p->H, (unsigned)(p->A * p->B * p->V), frameNr, nFrames, fn, p->sCompute)); p->launches++;
+	return OCTB200_OK;
+}
+int octb200_volume_u8(octb200_pipeline* p, uint32_t nr, uint8_t* dOut) {
+	if (!p || !dOut || nr >= (uint32_t)p->V) return fail(p, OCTB200_ERR_INVALID, "bad argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, launch_volume_u8(dOut, p->dVolume + (size_t)(p->S / 2) * nr, p->S / 2, nr, (unsigned)p->B, (unsigned)p->A, (unsigned)(p->B * p->V),
+	                       (unsigned)p->H, p->smCount, p->sCompute)); p->launches++;
+	return OCTB200_OK;
+}
+int octb200_float_to_output(octb200_pipeline* p, uint32_t nr, void* dOut) {
+	if (!p || !dOut || nr >= (uint32_t)p->V) return fail(p, OCTB200_ERR_INVALID, "bad argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, launch_float_to_output(dOut, p->dVolume + (size_t)(p->S / 2) * nr, (int)p->cfg.bitDepth, p->S / 2, p->smCount, p->sCompute)); p->launches++;
+	return OCTB200_OK;
+}
+
+/* ---------- timing ---------- */
+void* octb200_compute_stream(octb200_pipeline* p) { return p ? (void*)p->sCompute : nullptr; }
+int octb200_event_record(octb200_pipeline* p, int slot) {
+	if (!p || slot < 0 || slot >= 8) return OCTB200_ERR_INVALID;
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, cudaEventRecord(p->evTiming[slot], p->sCompute));
+	return OCTB200_OK;
+}
+int octb200_event_elapsed_ms(octb200_pipeline* p, int a, int b, float* ms) {
+	if (!p || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) return OCTB200_ERR_INVALID;
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, cudaEventSynchronize(p->evTiming[b]));
+	CK(p, cudaEventElapsedTime(ms, p->evTiming[a], p->evTiming[b]));
+	return OCTB200_OK;
+}
+uint64_t octb200_launch_count(const octb200_pipeline* p) { return p ? p->launches : 0; }
+
+int octb200_time_kernel(octb200_pipeline* p, const void* dRaw, int iters, float* msPerIter) {
+	if (!p || !dRaw || iters < 1 || !msPerIter) return fail(p, OCTB200_ERR_INVALID, "bad argument");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	const Stage st = select_stage(p);
+	if (p->lutsDirty || st.sa != p->lutSa) { int rc = rebuild_luts(p); if (rc) return rc; }
+	const bool fpn = p->prm.fixedPatternNoiseRemoval != 0;
+	float* slab = p->dVolume + (size_t)(p->S / 2) * p->bufferNumberInVolume;
+	CK(p, cudaEventRecord(p->evTiming[6], p->sCompute));
+	for (int i = 0; i < iters; ++i) {
+		if (p->mode == OCTB200_FFT_CUFFT) {
+			PreArgs pa = pre_args(p, st, dRaw, p->lines);
+			int rc = ensure_fft_buffer(p); if (rc) return rc;
+			CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute));
+		} else {
+			const int src = (p->mode == OCTB200_FFT_FUSED) ? SRC_RAW16 : SRC_CPLX;
+			if (src == SRC_CPLX) { int rc = ensure_fft_buffer(p); if (rc) return rc; }
+			FusedArgs fa = fused_args(p, st, dRaw, p->lines);
+			fa.out = slab; fa.epi = epi_for(p, fpn && p->fpnDetermined, false);
+			CK(p, launch_fused(p->R, st.sa, st.roll, src, fa, p->smCount, p->sCompute));
+		}
+		p->launches++;
+	}
+	CK(p, cudaEventRecord(p->evTiming[7], p->sCompute));
+	CK(p, cudaEventSynchronize(p->evTiming[7]));
+	float ms = 0.f;
+	CK(p, cudaEventElapsedTime(&ms, p->evTiming[6], p->evTiming[7]));
+	*msPerIter = ms / (float)iters;
+	return OCTB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+"""Development harness run on the B200 box through gpurun (not part of the product, not a test):
+   python tools/gpu_check.py parity   -> every mode x parameter variant against the fp64 oracle
+   python tools/gpu_check.py refcuda  -> against the reference's unmodified cuda_code.cu (oracle/_ref/libref_cuda.so)
+   python tools/gpu_check.py timing   -> device-resident / end-to-end timings of all modes and of the reference CUDA build
+Results are printed and written to gpurun_out/*.json."""
+from __future__ import annotations
+
+import copy
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from octproz_b200 import OctPipeline, _lib, benchmark_params, synth  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+MODES = {"fused": _lib.FFT_FUSED, "split": _lib.FFT_SPLIT, "cufft": _lib.FFT_CUFFT}
+
+
+def variants(n):
+    v = {}
+    b = benchmark_params(n, 64, 8)
+    v["benchmark"] = b
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; v["nofpn"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.resamplingInterpolation = 0; v["linear"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.resamplingInterpolation = 2; v["lanczos"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.resampling = False; v["noresample"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.windowing = False; q.dispersionCompensation = False; v["klin_only"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.backgroundRemoval = True; q.rollingAverageWindowSize = 64; v["rolling64"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.backgroundRemoval = True; q.rollingAverageWindowSize = 8; q.resamplingInterpolation = 2; v["rolling8_lanczos"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.bscanFlip = True; q.sinusoidalScanCorrection = True; v["flip_sinus"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.bscanFlip = True; v["flip"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.signalLogScaling = False; q.signalGrayscaleMin = 0.0; q.signalGrayscaleMax = 400.0; v["linscale"] = q
+    q = copy.deepcopy(b); q.fixedPatternNoiseRemoval = False; q.bitshift = True; q.bitDepth = 16; v["bitshift16"] = q
+    return v
+
+
+def stats(a, b):
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    fin = np.isfinite(d)
+    d = d[fin]
+    return {"max": float(d.max()), "p9999": float(np.quantile(d, 0.9999)), "p99": float(np.quantile(d, 0.99)),
+            "median": float(np.median(d)), "frac_gt_1e-4": float((d > 1e-4).mean()), "nonfinite": int((~fin).sum())}
+
+
+def run_mine(q, raw, mode, mean_line=None):
+    p = OctPipeline(fft_mode=mode)
+    h = np.ascontiguousarray(raw)
+    assert p.initializeCuda(None, None, q), getattr(p, "_create_error", "")
+    if mean_line is not None:
+        p.set_fpn_mean_line(mean_line)
+    p.octCudaPipeline(h)
+    p.sync()
+    out = p.copy_output(0)
+    ml = p.fpn_mean_line()
+    p.cleanupCuda()
+    return out, ml
+
+
+def cmd_parity():
+    res = {}
+    for n in (1024, 2048):
+        for name, q in variants(n).items():
+            q = copy.deepcopy(q); q.update_all_curves()
+            raw = synth.make_volume(n, q.ascansPerBscan, q.bscansPerBuffer, q.bitDepth, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+            ref, ml, _ = orc.process(q, raw)
+            for mname, mode in MODES.items():
+                key = f"N{n}/{name}/{mname}"
+                try:
+                    out, mml = run_mine(copy.deepcopy(q), raw, mode)
+                    s = stats(out, ref)
+                    if q.fixedPatternNoiseRemoval:
+                        h = n // 2
+                        s["meanline_max_diff"] = float(np.abs(mml[:h] - ml[:h]).max())
+                        out2, _ = run_mine(copy.deepcopy(q), raw, mode, mean_line=ml.astype(np.float32))
+                        s["with_oracle_meanline"] = stats(out2, ref)
+                    res[key] = s
+                    print(key, json.dumps(s), flush=True)
+                except Exception as e:  # noqa: BLE001
+                    res[key] = {"error": str(e)}
+                    print(key, "ERROR", e, flush=True)
+    json.dump(res, open(os.path.join(OUT, "parity_oracle.json"), "w"), indent=1)
+
+
+def cmd_refcuda():
+    res = {}
+    rc = orc.RefCuda()
+    for n in (1024, 2048):
+        for name, q in variants(n).items():
+            q = copy.deepcopy(q)
+            rc.configure(q)
+            q.resampleCurve, q.dispersionCurve, q.windowCurve = rc.curves()   # identical LUTs for both sides
+            raw = synth.make_volume(n, q.ascansPerBscan, q.bscansPerBuffer, q.bitDepth, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+            h1 = np.ascontiguousarray(raw).copy(); h2 = h1.copy()
+            rc.init(h1, h2)
+            rc.process(h1)
+            ref = rc.output(0)
+            rc.cleanup()
+            orc64, _, _ = orc.process(q, raw)
+            sref = stats(ref, orc64)
+            print(f"N{n}/{name}/REFCUDA-vs-oracle", json.dumps(sref), flush=True)
+            res[f"N{n}/{name}/refcuda_vs_oracle"] = sref
+            for mname, mode in MODES.items():
+                key = f"N{n}/{name}/{mname}"
+                try:
+                    out, _ = run_mine(copy.deepcopy(q), raw, mode)
+                    s = stats(out, ref)
+                    res[key] = s
+                    print(key, "vs REFCUDA", json.dumps(s), flush=True)
+                except Exception as e:  # noqa: BLE001
+                    res[key] = {"error": str(e)}
+                    print(key, "ERROR", e, flush=True)
+    json.dump(res, open(os.path.join(OUT, "parity_refcuda.json"), "w"), indent=1)
+
+
+def cmd_timing():
+    import torch
+    res = {}
+    for (n, a, b, bits) in ((1024, 512, 256, 12), (2048, 1024, 128, 16)):
+        q = benchmark_params(n, a, b, bits); q.update_all_curves()
+        t0 = time.time()
+        small = synth.make_volume(n, a, 8, bits, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+        raw = np.ascontiguousarray(np.tile(small, (b // 8, 1, 1)))
+        h1 = torch.from_numpy(raw).pin_memory(); h2 = torch.from_numpy(raw.copy()).pin_memory()
+        print("synth", time.time() - t0, raw.shape, flush=True)
+        ascans = a * b
+        for mname, mode in MODES.items():
+            p = OctPipeline(fft_mode=mode)
+            assert p.initializeCuda(None, None, copy.deepcopy(q)), getattr(p, "_create_error", "")
+            p.octCudaPipeline(h1.numpy()); p.sync()
+            for _ in range(3):
+                p.process_device(None)
+            p.sync()
+            iters = 20
+            p.event_record(0)
+            for _ in range(iters):
+                p.process_device(None)
+            p.event_record(1)
+            ms = p.event_elapsed_ms(0, 1) / iters
+            kms = p.time_kernel(p._lib.octb200_output_device_ptr(p.handle, 0) and torch.from_numpy(raw).cuda(), 10) if False else None
+            # end to end: pinned host -> H2D -> kernels
+            for _ in range(2):
+                p.octCudaPipeline(h1.numpy()); p.octCudaPipeline(h2.numpy())
+            p.sync()
+            t0 = time.perf_counter()
+            for i in range(10):
+                p.octCudaPipeline((h1 if i % 2 == 0 else h2).numpy())
+            p.sync()
+            e2e = (time.perf_counter() - t0) / 10
+            key = f"N{n}x{a}x{b}/{mname}"
+            res[key] = {"resident_ms": ms, "resident_MHz": ascans / ms / 1e3, "e2e_ms": e2e * 1e3, "e2e_MHz": ascans / e2e / 1e6,
+                        "algorithmic_GBs": ascans * n * 4 / ms / 1e6}
+            print(key, json.dumps(res[key]), flush=True)
+            p.cleanupCuda()
+        # reference CUDA build, same box
+        try:
+            rc = orc.RefCuda(); rc.configure(q)
+            a1 = np.ascontiguousarray(raw).copy(); a2 = a1.copy()
+            rc.init(a1, a2)
+            rc.process(a1); rc.L.refcuda_sync()
+            tres = rc.time(None, None, 20, 3) / 20
+            te2e = rc.time(a1, a2, 10, 2) / 10
+            rc.cleanup()
+            key = f"N{n}x{a}x{b}/refcuda"
+            res[key] = {"resident_ms": tres * 1e3, "resident_MHz": ascans / tres / 1e6, "e2e_ms": te2e * 1e3, "e2e_MHz": ascans / te2e / 1e6}
+            print(key, json.dumps(res[key]), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print("refcuda timing failed", e, flush=True)
+        del h1, h2
+    json.dump(res, open(os.path.join(OUT, "timing.json"), "w"), indent=1)
+
+
+def cmd_quick():
+    for n in (1024, 2048):
+        q = benchmark_params(n, 16, 2); q.update_all_curves()
+        raw = synth.make_volume(n, 16, 2, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+        ref, ml, _ = orc.process(q, raw)
+        for mname, mode in MODES.items():
+            out, mml = run_mine(copy.deepcopy(q), raw, mode)
+            print("quick", n, mname, json.dumps(stats(out, ref)), flush=True)
+
+
+if __name__ == "__main__":
+    {"quick": cmd_quick, "parity": cmd_parity, "refcuda": cmd_refcuda, "timing": cmd_timing}[sys.argv[1]]()
