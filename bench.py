@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- A-scan throughput of the raw -> B-scan hot path on the reference's headline workload.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (liboctb200.so on B200)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's own CPU path on the host cores
+
+Workload (BASELINE.json configs[1], the config the metric is quoted on): the 1024 x 512 x 256 12-bit test
+volume of the reference's published benchmark (performance/v180/.../20250504_octproz_settings.ini): cubic
+k-linearisation + dispersion + Hann window + FPN (1 B-scan, determined once) + log scaling.  The reference's
+dataset is an external download, so the raw buffer is synthetic with that geometry (octproz_b200/synth.py).
+A "step" = one pass of the hot path over one raw buffer (one volume = 131072 A-scans) per GPU.
+
+One JSON line on stdout (rank 0).  `value` = device-resident rate (raw already in HBM), `e2e` = through the
+reference-facing call octCudaPipeline(host buffer) with the pinned H2D copy and the D2H of the converted
+output (the reference's stream-to-host path) inside the timed region.  Multi-GPU: weak scaling, every rank
+processes its own buffer (slab of a G-times larger volume) and the en-face slice is all-gathered over NCCL
+inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (samplesPerLine, ascansPerBscan, bscansPerBuffer, bitDepth)
+    "1024x512x256-12bit": (1024, 512, 256, 12),
+    "2048x1024x128-16bit": (2048, 1024, 128, 16),
+}
+DEFAULT_WORKLOAD = "1024x512x256-12bit"
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_raw(q, bscans_unique=8, seed_offset=0):
+    from octproz_b200 import synth
+    small = synth.make_volume(q.samplesPerLine, q.ascansPerBscan, bscans_unique, q.bitDepth, resample=q.resampleCurve,
+                              dispersion=q.dispersionCurve, b_offset=seed_offset)
+    reps = (q.bscansPerBuffer + bscans_unique - 1) // bscans_unique
+    return np.ascontiguousarray(np.tile(small, (reps, 1, 1))[: q.bscansPerBuffer])
+
+
+def cpu_reference_run(q, threads, bscans, repeats=1):
+    """time the reference's own CPU path (oracle/_ref/libref_cpu.so, FFTW-API substitute) on `bscans` B-scans"""
+    from oracle import oracle as orc
+    kind = "reference"
+    if orc.have_ref("libref_cpu.so"):
+        rc = orc.RefCpu()
+        threads = min(threads, rc.max_threads) if threads > 0 else rc.max_threads
+        run = lambda raw: rc.process(q, raw, threads=threads)
+    else:
+        kind, threads = "port", 1
+        run = lambda raw: orc.process(q, raw, precision=32)
+    q2 = copy.copy(q); q2.bscansPerBuffer = bscans
+    raw = make_raw(q2, bscans_unique=min(8, bscans))
+    run(raw[: max(1, min(bscans, threads))])   # warm caches / thread pool / per-thread arenas
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        run(raw)
+    dt = (time.perf_counter() - t0) / repeats
+    ascans = bscans * q.ascansPerBscan
+    return {"seconds": dt, "ascans": ascans, "mhz": ascans / dt / 1e6, "threads": threads, "kind": kind,
+            "sample": f"{bscans} B-scans ({ascans} A-scans) of the workload, reference CPU path "
+                      f"(processor.tpp, FFTW-API substitute), {threads} thread(s)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--mode", default="fused", choices=["fused", "split", "cufft"])
+    ap.add_argument("--cpu-bscans", type=int, default=0, help="B-scans in the cpu_baseline sample (0 = auto)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    n, a, b, bits = WORKLOADS[args.workload]
+    from octproz_b200 import benchmark_params
+    q = benchmark_params(n, a, b, bits)
+    q.update_all_curves()
+    ncores = os.cpu_count() or 1
+    ascans_per_step = a * b
+    config = {"workload": f"{args.workload} volume, benchmark INI settings (cubic k-lin + dispersion + Hann + FPN once + log), "
+                          f"u16 container, synthetic", "samples_per_ascan": n, "ascans_per_bscan": a, "bscans_per_buffer": b,
+              "bit_depth": bits}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        bscans = args.cpu_bscans or max(8, min(b, 2 * ncores))
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_run(q, ncores, bscans)
+        t = []
+        for _ in range(args.steps):
+            t.append(cpu_reference_run(q, ncores, bscans))
+        sec = float(np.mean([x["seconds"] for x in t])); mhz = t[0]["ascans"] / sec / 1e6
+        line = {"impl": "reference", "metric": "A-scan rate (raw -> B-scan hot path)", "value": mhz, "unit": "MHz (1e6 A-scans/s)",
+                "volumes_per_s": mhz * 1e6 / ascans_per_step, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(config, step=f"bounded sample: {t[0]['ascans']} A-scans per step"),
+                "cpu_baseline": {"value": mhz, "unit": "MHz (1e6 A-scans/s)", "cores": t[0]["threads"], "kind": t[0]["kind"], "sample": t[0]["sample"]},
+                "e2e": {"value": mhz, "unit": "MHz (1e6 A-scans/s)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "host_cores": ncores}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm (B200)
+    import torch
+    from octproz_b200 import OctPipeline, _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode = {"fused": _lib.FFT_FUSED, "split": _lib.FFT_SPLIT, "cufft": _lib.FFT_CUFFT}[args.mode]
+
+    raw_np = [make_raw(q, seed_offset=16 * rank), make_raw(q, seed_offset=16 * rank + 8)]
+    h_raw = [torch.from_numpy(x).pin_memory() for x in raw_np]
+    d_raw = [x.cuda(non_blocking=False) for x in h_raw]             # two distinct 256 MiB inputs: larger than L2 (126 MB)
+    bytes_in = raw_np[0].nbytes
+    conv_bytes = (n // 2) * a * b * 2
+    h_stream = [torch.empty(conv_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    qq = copy.deepcopy(q)
+    p = OctPipeline(fft_mode=mode, device=local, bscan_index_base=(rank * b) % 2)
+    if not p.initializeCuda(None, None, qq):
+        raise SystemExit("initializeCuda failed: " + getattr(p, "_create_error", ""))
+    enface = torch.empty(a * b, dtype=torch.float32, device="cuda")
+    gathered = torch.empty(world * a * b, dtype=torch.float32, device="cuda") if world > 1 else None
+    stream = torch.cuda.ExternalStream(int(p._lib.octb200_compute_stream(p.handle)), device=torch.device("cuda", local))
+
+    def sync_all():
+        p.sync(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def fpn_share():
+        # FPN line of the first buffer: rank 0 determines, everyone uses it (8 KB broadcast)
+        if dist is None:
+            return
+        ml = torch.from_numpy(p.fpn_mean_line()).cuda()
+        dist.broadcast(ml, 0)
+        p.set_fpn_mean_line(ml.cpu().numpy())
+
+    def step_resident(i):
+        p.process_device(d_raw[i & 1])
+        if dist is not None:
+            p.changeDisplayedEnFaceFrame(100, 1, 0, enface)
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, enface)
+
+    # warm-up (includes LUT build, FPN determination, cuFFT plan if any)
+    p.process_device(d_raw[0]); p.sync(); fpn_share()
+    for i in range(max(3, args.warmup)):
+        step_resident(i)
+    sync_all()
+
+    # ---- device-resident timed region: CUDA events on the launching stream, max over ranks ----
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = p.launch_count()
+    sync_all()
+    p.event_record(0)
+    for i in range(args.steps):
+        step_resident(i)
+    p.event_record(1)
+    ms_total = p.event_elapsed_ms(0, 1)
+    sync_all()
+    launches = p.launch_count() - launches0
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * ascans_per_step / (ms_step * 1e3)   # MHz
+
+    # ---- dominant kernel alone (roofline): events around back-to-back launches of the fused kernel ----
+    kern_ms = p.time_kernel(d_raw[1], 20)
+    alg_bytes = ascans_per_step * n * 4                  # 2 B in + 2 B out per raw sample
+    peak, peak_src = hbm_peak()
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.mode}:{args.workload}")
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"bound": "hbm", "kernel": {"fused": "oct_fused_kernel", "split": "oct_fused_kernel<SRC_CPLX>", "cufft": "oct_pre_kernel"}[args.mode],
+                "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peak,
+                "traffic": traffic, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
+
+    # ---- end to end through octCudaPipeline(host buffer): pinned H2D + converted-output D2H inside the timed region ----
+    p.sync()
+    qq.streamToHost = True
+    p.cuda_registerStreamingBuffers(h_stream[0], h_stream[1], conv_bytes)
+    for i in range(max(3, args.warmup)):
+        p.octCudaPipeline(h_raw[i & 1].numpy())
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        p.octCudaPipeline(h_raw[i & 1].numpy())
+        if dist is not None:
+            p.changeDisplayedEnFaceFrame(100, 1, 0, enface)
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, enface)
+    p.sync(); torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e_mhz = world * ascans_per_step * args.steps / e2e_s / 1e6
+    checksum = int(np.frombuffer(h_stream[0].numpy()[:4096].tobytes(), np.uint16).sum())
+    p.cuda_unregisterStreamingBuffers()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1:
+        bscans = args.cpu_bscans or b            # one full volume per repeat: ~3 s of CPU work each
+        c = cpu_reference_run(q, ncores, bscans, repeats=4)
+        cpu = {"value": c["mhz"], "unit": "MHz (1e6 A-scans/s)", "cores": c["threads"], "kind": c["kind"], "sample": c["sample"]}
+
+    p.cleanupCuda()
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    line = {"metric": "A-scan rate (raw -> B-scan hot path)", "value": value, "unit": "MHz (1e6 A-scans/s)",
+            "volumes_per_s": value * 1e6 / ascans_per_step, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "ours",
+            "config": dict(config, mode=args.mode, l2="two alternating 256 MiB inputs and 256 MiB outputs per GPU: larger than the 126 MB L2",
+                           parallelism=f"b-scan sharding x{world}" + (", NCCL all-gather of the en-face slice every step" if world > 1 else "")),
+            "e2e": {"value": e2e_mhz, "unit": "MHz (1e6 A-scans/s)", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": conv_bytes,
+                    "ms_per_step": e2e_s * 1e3 / args.steps, "timer": "host wall clock between device synchronisations, max over ranks",
+                    "checksum": checksum},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "host_cores": ncores}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

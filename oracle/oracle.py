@@ -236,6 +236,13 @@ class RefCuda:
             raise RuntimeError(f"reference copy_output: cuda error {rc}")
         return out
 
+    def mean_line(self) -> np.ndarray:
+        n = int(self.q.samplesPerLine)
+        out = np.empty((n, 2), np.float32)
+        self.L.refcuda_get_mean_line.argtypes = [C.c_void_p, C.c_int]
+        self.L.refcuda_get_mean_line(out.ctypes.data, n)
+        return out
+
     def time(self, h_a, h_b, iters: int, warmup: int) -> float:
         return float(self.L.refcuda_time(h_a.ctypes.data if h_a is not None else None,
                                          h_b.ctypes.data if h_b is not None else None, iters, warmup))

@@ -16,6 +16,7 @@
 
 extern float* d_processedBuffer;   /* cuda_code.cu:98 */
 extern void* d_inputBuffer[];      /* cuda_code.cu:60 */
+extern cufftComplex* d_meanALine;  /* cuda_code.cu:84 */
 
 struct refcuda_cfg {
 	int samplesPerLine, ascansPerBscan, bscansPerBuffer, buffersPerVolume, bitDepth;
@@ -120,6 +121,12 @@ extern "C" double refcuda_time(void* h_in_a, void* h_in_b, int iters, int warmup
 	cudaDeviceSynchronize();
 	auto t1 = std::chrono::steady_clock::now();
 	return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/* the fixed-pattern-noise mean line the reference determined (N complex values) */
+extern "C" int refcuda_get_mean_line(float* reIm, int n) {
+	cudaDeviceSynchronize();
+	return (int)cudaMemcpy(reIm, d_meanALine, sizeof(cufftComplex) * n, cudaMemcpyDeviceToHost);
 }
 
 extern "C" void refcuda_cleanup() { cleanupCuda(); }

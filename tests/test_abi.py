@@ -1,0 +1,61 @@
+"""The C-ABI library loads on a machine without a GPU and exports exactly what include/octb200.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from octproz_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "octb200.h")).read()
+    return re.findall(r"OCTB200_API\s+[\w\s\*]+?\b(octb200_\w+)\s*\(", txt)
+
+
+def test_every_declared_symbol_is_exported():
+    L = _lib.load()
+    declared = header_symbols()
+    assert len(declared) >= 40
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(set(declared)) == sorted(set(_lib.SYMBOLS))
+
+
+def test_version_and_defaults():
+    L = _lib.load()
+    assert L.octb200_version() == 100
+    p = _lib.Params()
+    L.octb200_default_params(C.byref(p))
+    # octalgorithmparameters.cpp:36-112
+    assert p.signalGrayscaleMax == 60.0 and p.signalMultiplicator == 1.0 and p.rollingAverageWindowSize == 1
+    assert p.bscansForNoiseDetermination == 1 and p.postProcessBackgroundWeight == 1.0 and p.resampling == 0
+
+
+def test_struct_layout_is_plain_c():
+    assert C.sizeof(_lib.Config) == 48
+    assert C.sizeof(_lib.Params) == 112
+
+
+def test_create_rejects_bad_geometry_without_touching_the_gpu():
+    L = _lib.load()
+    h = C.c_void_p()
+    cfg = _lib.Config(7, 4, 1, 1, 12, -1, 0, 0, 0)            # odd / tiny samplesPerLine
+    assert L.octb200_create(C.byref(cfg), C.byref(h)) == _lib.ERR_INVALID and not h
+    assert b"geometry" in L.octb200_last_error(None)
+    cfg = _lib.Config(1 << 16, 1 << 10, 1 << 6, 1, 12, -1, 0, 0, 0)   # >= 2^31 samples (the reference's int indexing limit)
+    assert L.octb200_create(C.byref(cfg), C.byref(h)) == _lib.ERR_INVALID
+    assert L.octb200_create(None, C.byref(h)) == _lib.ERR_INVALID
+
+
+def test_no_cpu_fallback_without_gpu():
+    from tests.conftest import has_gpu
+    if has_gpu():
+        pytest.skip("GPU present")
+    L = _lib.load()
+    h = C.c_void_p()
+    cfg = _lib.Config(1024, 16, 2, 1, 12, -1, 0, 0, 0)
+    rc = L.octb200_create(C.byref(cfg), C.byref(h))
+    assert rc == _lib.ERR_CUDA and not h        # fails loudly, never computes on the host

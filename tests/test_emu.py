@@ -1,0 +1,67 @@
+"""CPU execution of the fused kernel's per-lane phases (octproz_b200/csrc/oct_phases.cuh, compiled for the host by
+tests/emu/emu_phases.cpp): validates the register / lane / shared-memory index maps of the 32x32 four-step FFT, the
+R=2 radix-2 combine, the LUT folding of stage A and the epilogue against numpy and the oracle -- without a GPU.
+TEST-ONLY emulator; the product never runs these functions on the host."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from octproz_b200 import benchmark_params, synth
+from oracle import oracle as orc
+from tests.util import assert_parity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libemu.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I/usr/local/cuda/include",
+                           "-I" + os.path.join(ROOT, "octproz_b200", "csrc"), os.path.join(ROOT, "tests", "emu", "emu_phases.cpp"), "-o", so])
+    L = C.CDLL(so)
+    f = C.c_float
+    L.emu_fused_line.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, f, f, f, f,
+                                 C.c_void_p, C.c_void_p, f, f, C.c_void_p, C.c_void_p]
+    return L
+
+
+def test_fft32_register_network(emu):
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(32) + 1j * rng.standard_normal(32)).astype(np.complex64)
+    o = np.zeros(32, np.complex64)
+    emu.emu_fft32(x.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+    ref = np.fft.ifft(x.astype(np.complex128)) * 32
+    assert np.abs(o - ref).max() < 5e-7 * np.abs(ref).max()
+
+
+def test_four_step_1024(emu):
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal(1024) + 1j * rng.standard_normal(1024)).astype(np.complex64)
+    o = np.zeros(1024, np.complex64)
+    emu.emu_ifft_1024(x.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+    ref = np.fft.ifft(x.astype(np.complex128)) * 1024
+    assert np.abs(o - ref).max() < 1e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [1024, 2048])
+@pytest.mark.parametrize("case", ["cubic", "linear", "lanczos", "none"])
+def test_fused_line_matches_oracle(emu, n, case):
+    interp, sa = {"cubic": (1, 1), "linear": (0, 1), "lanczos": (2, 2), "none": (0, 0)}[case]
+    q = benchmark_params(n, 1, 1); q.fixedPatternNoiseRemoval = False
+    q.resampling = case != "none"; q.resamplingInterpolation = interp
+    q.update_all_curves()
+    raw = synth.make_volume(n, 1, 1, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+    ref, _, _ = orc.process(q, raw)
+    fs = np.zeros(n + 64, np.float32); fs[16:16 + n] = raw.reshape(-1)
+    d = q.dispersionCurve.astype(np.float64)
+    ph = np.stack([np.cos(d), np.sin(d)], 1).astype(np.float32)
+    out = np.zeros(n // 2, np.float32)
+    rc = emu.emu_fused_line(n, sa, interp, fs[16:].ctypes.data, 8 if sa == 2 else 0,
+                            q.resampleCurve.ctypes.data if q.resampling else None, q.windowCurve.ctypes.data, ph.ctypes.data,
+                            1, q.signalGrayscaleMin, q.signalGrayscaleMax, q.signalMultiplicator, q.signalAddend,
+                            None, None, 0.0, 0.0, out.ctypes.data, None)
+    assert rc == 0
+    assert_parity(out.reshape(1, 1, -1), ref, q, what=f"emulated fused line N={n} {case}")
