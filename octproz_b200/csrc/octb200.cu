@@ -95,9 +95,9 @@ struct octb200_pipeline {
 
 	bool fpnDetermined = false;
 	unsigned bufferNumberInVolume = 0, streamedBuffers = 0, streamingBufferNumber = 0, floatStreamingBufferNumber = 0, currentBufferNr = 0;
-	void *hostBuf[2] = { nullptr, nullptr }; bool hostRegistered = false;
-	void *hostStream[2] = { nullptr, nullptr }; size_t hostStreamBytes = 0; bool hostStreamRegistered = false;
-	void *hostFloat[2] = { nullptr, nullptr }; size_t hostFloatBytes = 0; bool hostFloatRegistered = false;
+	void *hostBuf[2] = { nullptr, nullptr }; bool hostRegistered = false; bool hostBufMine[2] = { false, false };
+	void *hostStream[2] = { nullptr, nullptr }; size_t hostStreamBytes = 0; bool hostStreamRegistered = false; bool hostStreamMine[2] = { false, false };
+	void *hostFloat[2] = { nullptr, nullptr }; size_t hostFloatBytes = 0; bool hostFloatRegistered = false; bool hostFloatMine[2] = { false, false };
 	octb200_host_callback cbStreaming = nullptr, cbFloat = nullptr, cbBackground = nullptr;
 	unsigned long long launches = 0;
 };
@@ -124,6 +124,19 @@ template <typename T> int dalloc(octb200_pipeline* p, T** ptr, size_t count) {
 	return OCTB200_OK;
 }
 template <typename T> void dfree(T*& ptr) { if (ptr) { cudaFree(ptr); ptr = nullptr; } }
+
+/* pin a caller-owned host buffer unless the caller already did (cudaHostAlloc / cudaHostRegister / torch pin_memory).
+ * *mine tells whether we have to unpin it later. */
+cudaError_t pin_host(void* h, size_t bytes, bool* mine) {
+	*mine = false;
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost) return cudaSuccess;
+	cudaGetLastError();
+	cudaError_t e = cudaHostRegister(h, bytes, cudaHostRegisterPortable);
+	if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return cudaSuccess; }
+	if (e == cudaSuccess) *mine = true;
+	return e;
+}
 
 void CUDART_CB host_cb_trampoline(void* data) {
 	auto* pair = static_cast<std::pair<octb200_host_callback, void*>*>(data);
@@ -560,41 +573,60 @@ int octb200_register_host_buffers(octb200_pipeline* p, void* h1, void* h2) {
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	if (p->hostRegistered) octb200_unregister_host_buffers(p);
 	const size_t bytes = (size_t)p->S * p->rawBytes;
-	CK(p, cudaHostRegister(h1, bytes, cudaHostRegisterPortable));
-	if (h2 && h2 != h1) { cudaError_t e = cudaHostRegister(h2, bytes, cudaHostRegisterPortable); if (e != cudaSuccess) { cudaHostUnregister(h1); return fail(p, OCTB200_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); } }
-	p->hostBuf[0] = h1; p->hostBuf[1] = (h2 && h2 != h1) ? h2 : nullptr; p->hostRegistered = true;
+	CK(p, pin_host(h1, bytes, &p->hostBufMine[0]));
+	p->hostBuf[0] = h1; p->hostBuf[1] = nullptr; p->hostBufMine[1] = false;
+	if (h2 && h2 != h1) {
+		cudaError_t e = pin_host(h2, bytes, &p->hostBufMine[1]);
+		if (e != cudaSuccess) { if (p->hostBufMine[0]) cudaHostUnregister(h1); p->hostBuf[0] = nullptr; return fail(p, OCTB200_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+		p->hostBuf[1] = h2;
+	}
+	p->hostRegistered = true;
 	return OCTB200_OK;
 }
 int octb200_unregister_host_buffers(octb200_pipeline* p) {
 	if (!p) return OCTB200_ERR_INVALID;
-	if (p->hostRegistered) { for (void*& h : p->hostBuf) { if (h) cudaHostUnregister(h); h = nullptr; } p->hostRegistered = false; }
+	if (p->hostRegistered) {
+		cudaStreamSynchronize(p->sH2D);
+		for (int i = 0; i < 2; ++i) { if (p->hostBuf[i] && p->hostBufMine[i]) cudaHostUnregister(p->hostBuf[i]); p->hostBuf[i] = nullptr; p->hostBufMine[i] = false; }
+		p->hostRegistered = false;
+	}
 	return OCTB200_OK;
 }
-static int reg_pair(octb200_pipeline* p, void* h1, void* h2, size_t bytes, void** dst, size_t* dstBytes, bool* flag) {
+static int reg_pair(octb200_pipeline* p, void* h1, void* h2, size_t bytes, void** dst, bool* mine, size_t* dstBytes, bool* flag) {
 	if (!p || !h1 || !h2) return fail(p, OCTB200_ERR_INVALID, "null argument");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
-	CK(p, cudaHostRegister(h1, bytes, cudaHostRegisterPortable));
-	cudaError_t e = cudaHostRegister(h2, bytes, cudaHostRegisterPortable);
-	if (e != cudaSuccess) { cudaHostUnregister(h1); return fail(p, OCTB200_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+	CK(p, pin_host(h1, bytes, &mine[0]));
+	cudaError_t e = pin_host(h2, bytes, &mine[1]);
+	if (e != cudaSuccess) { if (mine[0]) cudaHostUnregister(h1); return fail(p, OCTB200_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
 	dst[0] = h1; dst[1] = h2; *dstBytes = bytes; *flag = true;
 	return OCTB200_OK;
 }
+static void unreg_pair(octb200_pipeline* p, void** dst, bool* mine, bool* flag) {
+	if (!*flag) return;
+	cudaStreamSynchronize(p->sD2H);
+	for (int i = 0; i < 2; ++i) { if (dst[i] && mine[i]) cudaHostUnregister(dst[i]); dst[i] = nullptr; mine[i] = false; }
+	*flag = false;
+}
 int octb200_register_streaming_buffers(octb200_pipeline* p, void* h1, void* h2, size_t bytes) {
-	if (p && bytes < (size_t)(p->S / 2) * p->rawBytes) return fail(p, OCTB200_ERR_INVALID, "streaming buffer too small");
-	return reg_pair(p, h1, h2, bytes, p ? p->hostStream : nullptr, p ? &p->hostStreamBytes : nullptr, p ? &p->hostStreamRegistered : nullptr);
+	if (!p) return OCTB200_ERR_INVALID;
+	if (bytes < (size_t)(p->S / 2) * p->rawBytes) return fail(p, OCTB200_ERR_INVALID, "streaming buffer too small");
+	unreg_pair(p, p->hostStream, p->hostStreamMine, &p->hostStreamRegistered);
+	return reg_pair(p, h1, h2, bytes, p->hostStream, p->hostStreamMine, &p->hostStreamBytes, &p->hostStreamRegistered);
 }
 int octb200_unregister_streaming_buffers(octb200_pipeline* p) {
 	if (!p) return OCTB200_ERR_INVALID;
-	if (p->hostStreamRegistered) { cudaStreamSynchronize(p->sD2H); for (void*& h : p->hostStream) { if (h) cudaHostUnregister(h); h = nullptr; } p->hostStreamRegistered = false; }
+	unreg_pair(p, p->hostStream, p->hostStreamMine, &p->hostStreamRegistered);
 	return OCTB200_OK;
 }
 int octb200_register_float_streaming_buffers(octb200_pipeline* p, void* h1, void* h2, size_t bytes) {
-	if (p && bytes < (size_t)(p->S / 2) * sizeof(float)) return fail(p, OCTB200_ERR_INVALID, "float streaming buffer too small");
-	return reg_pair(p, h1, h2, bytes, p ? p->hostFloat : nullptr, p ? &p->hostFloatBytes : nullptr, p ? &p->hostFloatRegistered : nullptr);
+	if (!p) return OCTB200_ERR_INVALID;
+	if (bytes < (size_t)(p->S / 2) * sizeof(float)) return fail(p, OCTB200_ERR_INVALID, "float streaming buffer too small");
+	unreg_pair(p, p->hostFloat, p->hostFloatMine, &p->hostFloatRegistered);
+	return reg_pair(p, h1, h2, bytes, p->hostFloat, p->hostFloatMine, &p->hostFloatBytes, &p->hostFloatRegistered);
 }
 int octb200_unregister_float_streaming_buffers(octb200_pipeline* p) {
 	if (!p) return OCTB200_ERR_INVALID;
-	if (p->hostFloatRegistered) { cudaStreamSynchronize(p->sD2H); for (void*& h : p->hostFloat) { if (h) cudaHostUnregister(h); h = nullptr; } p->hostFloatRegistered = false; }
+	unreg_pair(p, p->hostFloat, p->hostFloatMine, &p->hostFloatRegistered);
 	return OCTB200_OK;
 }
 int octb200_set_callbacks(octb200_pipeline* p, octb200_host_callback s, octb200_host_callback f, octb200_host_callback b) {
