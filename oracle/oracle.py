@@ -191,8 +191,10 @@ class RefCudaCfg(C.Structure):
 class RefCuda:
     """the reference's unmodified cuda_code.cu (sm_100, --use_fast_math) behind a headless driver.  GPU only."""
 
-    def __init__(self):
-        self.L = C.CDLL(os.path.join(REF_DIR, "libref_cuda.so"))
+    def __init__(self, lib: str = "libref_cuda.so"):
+        """lib = "libadapter_api.so": the same harness and the reference's own parameter code, but the kernels.h symbols
+        come from integration/octproz_kernels_adapter.cpp on top of liboctb200.so (drop-in check)"""
+        self.L = C.CDLL(os.path.join(REF_DIR, lib))
         self.L.refcuda_configure.argtypes = [C.POINTER(RefCudaCfg)]
         self.L.refcuda_get_curves.argtypes = [C.c_void_p] * 3
         self.L.refcuda_init.argtypes = [C.c_void_p, C.c_void_p]

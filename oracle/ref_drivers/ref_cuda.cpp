@@ -15,8 +15,12 @@
 #include <cstring>
 
 extern float* d_processedBuffer;   /* cuda_code.cu:98 */
-extern void* d_inputBuffer[];      /* cuda_code.cu:60 */
+#ifndef REFCUDA_NO_MEANLINE_GLOBAL
 extern cufftComplex* d_meanALine;  /* cuda_code.cu:84 */
+#else
+extern "C" int octb200_adapter_get_mean_line(float* reIm, int n);
+extern "C" int octb200_adapter_sync();
+#endif
 
 struct refcuda_cfg {
 	int samplesPerLine, ascansPerBscan, bscansPerBuffer, buffersPerVolume, bitDepth;
@@ -126,7 +130,11 @@ extern "C" double refcuda_time(void* h_in_a, void* h_in_b, int iters, int warmup
 /* the fixed-pattern-noise mean line the reference determined (N complex values) */
 extern "C" int refcuda_get_mean_line(float* reIm, int n) {
 	cudaDeviceSynchronize();
+#ifndef REFCUDA_NO_MEANLINE_GLOBAL
 	return (int)cudaMemcpy(reIm, d_meanALine, sizeof(cufftComplex) * n, cudaMemcpyDeviceToHost);
+#else
+	return octb200_adapter_get_mean_line(reIm, n);
+#endif
 }
 
 extern "C" void refcuda_cleanup() { cleanupCuda(); }
