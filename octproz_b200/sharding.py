@@ -1,0 +1,102 @@
+"""Multi-GPU host side: shard a buffer by B-scan, one process per GPU.
+
+Every stage of the path is per A-scan or per B-scan, so the shards never exchange sample data.  What crosses ranks:
+  * the fixed-pattern-noise line (N complex floats, 8 KB): determined by rank 0 from the first B-scans of the buffer
+    (cuda_code.cu:1520-1522) and broadcast once (or per buffer in continuous mode);
+  * the displayed en-face slice: each rank extracts its A x B_local floats, one all_gather assembles the frame
+    (the only collective on the display path; the volume itself stays sharded in HBM).
+`dist` is a torch.distributed-like module (NCCL on GPUs, gloo in the CPU tests); `pipeline_factory` builds the
+per-rank engine (OctPipeline on a B200; the tests inject an oracle-backed stand-in to check the host logic).
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+
+def shard_bounds(total_bscans: int, world: int, rank: int) -> tuple[int, int]:
+    """B-scans [start, start+count) of rank `rank`.  Shares are equal when world divides total; starts are kept even
+    where possible so that the parity of 'flip every even B-scan' (cuda_code.cu:795) needs no special casing."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(total_bscans, world)
+    counts = [base + (1 if r < rem else 0) for r in range(world)]
+    start = sum(counts[:rank])
+    return start, counts[rank]
+
+
+class ShardedPipeline:
+    def __init__(self, params, rank: int, world: int, dist=None, pipeline_factory=None, device: int = -1, fft_mode: int = 0):
+        self.rank, self.world, self.dist = rank, world, dist
+        self.full = params
+        self.start, self.count = shard_bounds(int(params.bscansPerBuffer), world, rank)
+        self.local = copy.deepcopy(params)
+        self.local.bscansPerBuffer = self.count
+        if pipeline_factory is None:
+            from .pipeline import OctPipeline
+            pipeline_factory = lambda base: OctPipeline(fft_mode=fft_mode, device=device, bscan_index_base=base)  # noqa: E731
+        self.pipe = pipeline_factory(self.start % 2)
+        self._fpn_shared = False
+
+    def initialize(self, h1=None, h2=None) -> bool:
+        if self.count == 0:
+            return True
+        return self.pipe.initializeCuda(h1, h2, self.local)
+
+    def local_slice(self, full_raw: np.ndarray) -> np.ndarray:
+        q = self.full
+        v = full_raw.reshape(q.bscansPerBuffer, q.ascansPerBscan, q.samplesPerLine)
+        return np.ascontiguousarray(v[self.start:self.start + self.count])
+
+    # ---- FPN line: rank 0 determines, everybody uses it ----
+    def _broadcast_fpn(self):
+        import torch
+        n = int(self.full.samplesPerLine)
+        if self.rank == 0:
+            ml = torch.from_numpy(np.ascontiguousarray(self.pipe.fpn_mean_line(), np.float32))
+        else:
+            ml = torch.zeros((n, 2), dtype=torch.float32)
+        dev = getattr(self, "_coll_device", None)
+        if dev is not None:
+            ml = ml.to(dev)
+        self.dist.broadcast(ml, 0)
+        if self.rank != 0 and self.count:
+            self.pipe.set_fpn_mean_line(ml.cpu().numpy())
+
+    def process_host(self, h_raw_local) -> None:
+        q = self.local
+        need_share = bool(q.fixedPatternNoiseRemoval) and self.world > 1 and self.dist is not None and \
+            (not self._fpn_shared or q.continuousFixedPatternNoiseDetermination or q.redetermineFixedPatternNoise)
+        if need_share:
+            # rank 0 owns the first B-scans of the buffer (cuda_code.cu:1520): it runs first, then the line is shared
+            if self.rank == 0:
+                self.pipe.octCudaPipeline(h_raw_local); self.pipe.sync()
+            self._broadcast_fpn()
+            self._fpn_shared = True
+            if self.rank != 0 and self.count:
+                self.pipe.octCudaPipeline(h_raw_local)
+        elif self.count:
+            self.pipe.octCudaPipeline(h_raw_local)
+
+    def sync(self) -> None:
+        if self.count:
+            self.pipe.sync()
+
+    # ---- en-face frame of the whole (sharded) volume ----
+    def enface(self, frame_nr: int, n_frames: int, fn: int, local_extract, device=None):
+        """local_extract(frame_nr, n_frames, fn) -> torch tensor [A*B_local] in the reference's order
+        (disp[(E-1)-i], cuda_code.cu:909).  Returns the full frame [A*B_total] on every rank."""
+        import torch
+        a, btot = int(self.full.ascansPerBscan), int(self.full.bscansPerBuffer)
+        mine = local_extract(frame_nr, n_frames, fn)
+        if self.world == 1 or self.dist is None:
+            return mine
+        maxc = max(shard_bounds(btot, self.world, r)[1] for r in range(self.world))
+        pad = torch.zeros(a * maxc, dtype=torch.float32, device=mine.device)
+        pad[: mine.numel()] = mine
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(parts, pad)
+        # the reference writes the frame reversed (index (E-1)-i): global order = shards in reverse rank order
+        out = [parts[r][: a * shard_bounds(btot, self.world, r)[1]] for r in reversed(range(self.world))]
+        return torch.cat(out)

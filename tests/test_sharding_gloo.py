@@ -1,0 +1,106 @@
+"""Host-side multi-GPU logic on CPU: two ranks over gloo, the per-rank engine replaced by an oracle-backed stand-in.
+Checks the shard bounds, the flip parity across shard boundaries (bscanIndexBase), the FPN-line broadcast and the
+en-face all_gather order against the un-sharded oracle result."""
+import copy
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from octproz_b200 import benchmark_params, synth
+from octproz_b200.sharding import ShardedPipeline, shard_bounds
+from oracle import oracle as orc
+
+
+def test_shard_bounds_cover_and_balance():
+    for total in (1, 7, 32, 256):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    assert shard_bounds(256, 8, 3) == (96, 32)
+    with pytest.raises(ValueError):
+        shard_bounds(8, 2, 2)
+
+
+class OracleEngine:
+    """stand-in for OctPipeline (TEST ONLY): same methods, arithmetic by the oracle"""
+
+    def __init__(self, base):
+        self.base, self.ml, self.q, self.out = base, None, None, None
+
+    def initializeCuda(self, h1, h2, q):
+        self.q = q
+        return True
+
+    def set_fpn_mean_line(self, ml):
+        self.ml = np.asarray(ml, np.float64)
+
+    def fpn_mean_line(self):
+        return self.ml.astype(np.float32)
+
+    def octCudaPipeline(self, raw):
+        q = copy.deepcopy(self.q)
+        flip = q.bscanFlip
+        q.bscanFlip = False
+        determine = q.fixedPatternNoiseRemoval and self.ml is None
+        out, ml, _ = orc.process(q, raw, mean_line=self.ml, determine_fpn=determine)
+        if determine:
+            self.ml = ml
+        if flip:                                  # flip B-scans whose index in the UN-SHARDED buffer is even
+            for b in range(out.shape[0]):
+                if (b + self.base) % 2 == 0:
+                    out[b] = out[b, ::-1].copy()
+        self.out = out
+
+    def sync(self):
+        pass
+
+
+def _worker(rank, world, port, raw, q, ref, ref_enface, errs):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        sp = ShardedPipeline(q, rank, world, dist=dist, pipeline_factory=lambda base: OracleEngine(base))
+        assert sp.initialize()
+        sp.process_host(sp.local_slice(raw))
+        sp.sync()
+        lo, cnt = sp.start, sp.count
+        assert np.allclose(sp.pipe.out, ref[lo:lo + cnt], rtol=0, atol=2e-6), f"rank {rank}: shard differs from the un-sharded result"
+        h = q.samplesPerLine // 2
+        extract = lambda f, nf, fn: torch.from_numpy(orc.enface_frame(sp.pipe.out, h, q.ascansPerBscan, cnt, f, nf, fn))  # noqa: E731
+        full = sp.enface(17, 1, 0, extract)
+        assert np.allclose(full.numpy(), ref_enface, rtol=0, atol=2e-6), f"rank {rank}: en-face gather order"
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        errs.put(f"rank {rank}: {e!r}")
+        raise
+
+
+@pytest.mark.parametrize("bscans", [6, 5])
+def test_two_ranks_match_unsharded(bscans):
+    n, a = 256, 10
+    q = benchmark_params(n, a, bscans)
+    q.bscanFlip = True; q.bscansForNoiseDetermination = 1
+    q.update_all_curves()
+    raw = synth.make_volume(n, a, bscans, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+    ref, _, _ = orc.process(q, raw)
+    ref_enface = orc.enface_frame(ref, n // 2, a, bscans, 17, 1, 0)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    errs = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, raw, q, ref, ref_enface, errs)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    msgs = []
+    while not errs.empty():
+        msgs.append(errs.get())
+    assert not msgs and all(p.exitcode == 0 for p in procs), msgs
