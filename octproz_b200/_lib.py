@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboctb200.so")
+LIB_PATH = os.environ.get("OCTB200_LIB", os.path.join(_HERE, "liboctb200.so"))   # override: development A/B builds only
 
 # every symbol include/octb200.h declares (tests check the list against the header)
 SYMBOLS = [

@@ -49,22 +49,66 @@ template <int K> struct W32 {
 	static constexpr float im = s[K];
 };
 
+/* ---- complex arithmetic on packed fp32 pairs ----
+ * sm_100a has two-lane fp32 instructions (PTX add/mul/fma.rn.f32x2 -> SASS FADD2/FMUL2/FFMA2) whose operands take
+ * per-half swizzles (LO_HI), per-half negation and scalar broadcast for free.  A complex value is exactly one such
+ * pair, so a butterfly with a general twiddle is 4 issue slots instead of 8.  Host builds (tests/emu) use plain floats. */
+OCT_HD float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+	return __fadd2_rn(a, b);
+#else
+	return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+OCT_HD float2 csub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+	return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a);
+#else
+	return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+/* a * (s, s) */
+OCT_HD float2 cscale(float2 a, float s) {
+#if defined(__CUDA_ARCH__)
+	return __fmul2_rn(a, make_float2(s, s));
+#else
+	return make_float2(a.x * s, a.y * s);
+#endif
+}
+/* i * a = (-a.y, a.x): a swizzle + half negation, folded into the consumer's operand modifiers */
+OCT_HD float2 cmul_i(float2 a) { return make_float2(-a.y, a.x); }
+
+/* c = a * b (complex): 2 packed instructions */
+OCT_HD float2 cmul(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+	const float2 t = __fmul2_rn(make_float2(a.x, a.x), b);
+	return __ffma2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x), t);
+#else
+	return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+#endif
+}
+
 /* d * w_32^IDX with the trivial cases folded at compile time */
 template <int IDX>
 OCT_HD float2 mul_w32(float2 d) {
 	if constexpr (IDX == 0) {
 		return d;
 	} else if constexpr (IDX == 8) {
-		return make_float2(-d.y, d.x);
+		return cmul_i(d);
 	} else if constexpr (IDX == 4) {
 		constexpr float h = 0.70710678118654752440f;
-		return make_float2((d.x - d.y) * h, (d.x + d.y) * h);
+		return cscale(cadd(d, cmul_i(d)), h);             /* (x - y, x + y) h */
 	} else if constexpr (IDX == 12) {
 		constexpr float h = 0.70710678118654752440f;
-		return make_float2((-d.x - d.y) * h, (d.x - d.y) * h);
+		return cscale(csub(cmul_i(d), d), h);             /* (-x - y, x - y) h */
 	} else {
 		constexpr float c = W32<IDX>::re, s = W32<IDX>::im;
+#if defined(__CUDA_ARCH__)
+		const float2 t = __fmul2_rn(d, make_float2(c, c));
+		return __ffma2_rn(make_float2(d.y, d.x), make_float2(-s, s), t);
+#else
 		return make_float2(d.x * c - d.y * s, d.x * s + d.y * c);
+#endif
 	}
 }
 
@@ -84,16 +128,11 @@ OCT_HD void fft32_inv_dif(float2 (&v)[32]) {
 				constexpr int i0 = g * 2 * half + k;
 				constexpr int i1 = i0 + half;
 				const float2 a = v[i0], b = v[i1];
-				v[i0] = make_float2(a.x + b.x, a.y + b.y);
-				v[i1] = mul_w32<(k << s)>(make_float2(a.x - b.x, a.y - b.y));
+				v[i0] = cadd(a, b);
+				v[i1] = mul_w32<(k << s)>(csub(a, b));
 			});
 		});
 	});
-}
-
-/* c = a * b (complex) */
-OCT_HD float2 cmul(float2 a, float2 b) {
-	return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
 }  // namespace octb200

@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(256) oct_pre_kernel(const PreArgs a) {
 		for (int m = lane; m < N; m += 32) {
 			const float4 B = __ldg(a.lutB + m);
 			float2 val;
-			if constexpr (SA == SA_TAPS4) val = sample_taps4(f, __ldg(a.lutW + m), B);
+			if constexpr (SA == SA_CUBIC) val = sample_cubic(f, B);
+			else if constexpr (SA == SA_LINEAR) val = sample_linear(f, B);
 			else if constexpr (SA == SA_NONE) val = sample_none(f, m, B);
 			else val = sample_lanczos(f, shift, B);
 			o[m] = val;
@@ -166,7 +167,8 @@ static cudaError_t launch_pre_t(const PreArgs& a, int smCount, cudaStream_t st) 
 
 template <typename RawT>
 static cudaError_t launch_pre_raw(const PreArgs& a, int sa, bool roll, int smCount, cudaStream_t st) {
-	if (sa == SA_TAPS4) return roll ? launch_pre_t<RawT, SA_TAPS4, true>(a, smCount, st) : launch_pre_t<RawT, SA_TAPS4, false>(a, smCount, st);
+	if (sa == SA_CUBIC) return roll ? launch_pre_t<RawT, SA_CUBIC, true>(a, smCount, st) : launch_pre_t<RawT, SA_CUBIC, false>(a, smCount, st);
+	if (sa == SA_LINEAR) return roll ? launch_pre_t<RawT, SA_LINEAR, true>(a, smCount, st) : launch_pre_t<RawT, SA_LINEAR, false>(a, smCount, st);
 	if (sa == SA_NONE) return roll ? launch_pre_t<RawT, SA_NONE, true>(a, smCount, st) : launch_pre_t<RawT, SA_NONE, false>(a, smCount, st);
 	return roll ? launch_pre_t<RawT, SA_LANCZOS, true>(a, smCount, st) : launch_pre_t<RawT, SA_LANCZOS, false>(a, smCount, st);
 }

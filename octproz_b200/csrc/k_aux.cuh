@@ -10,8 +10,7 @@ namespace octb200 {
 struct PreArgs {
 	const void* raw;
 	float2* out;            /* [lines][N] */
-	const float4* lutW;     /* N entries, natural order (R = 1 layout), global memory */
-	const float4* lutB;
+	const float4* lutB;     /* N entries, natural order (R = 1 layout), global memory */
 	long long totalSamples;
 	int lines;
 	int N;

@@ -1,7 +1,7 @@
 /*
  * k_fused.cuh -- the hot kernel: one launch takes raw u16 spectra to finished B-scan lines.
  *
- *   raw line --cp.async.bulk (TMA 1-D) + mbarrier, double buffered per line group--> shared memory
+ *   raw line --cp.async.bulk (TMA 1-D) + mbarrier, one prefetched slot per line group--> shared memory
  *     -> exact u16->fp32 slot conversion [+ rolling-mean background removal]          (cuda_code.cu:109-211)
  *     -> 4-tap / 16-tap resampling x window x dispersion phasor from LUTs             (cuda_code.cu:213-489)
  *     -> 32x32 four-step inverse FFT, registers + one shared-memory transpose          (cuda_code.cu:1514-1515)
@@ -21,9 +21,15 @@
 
 namespace octb200 {
 
+#ifndef OCT_R1_THREADS
+#define OCT_R1_THREADS 512
+#endif
+#ifndef OCT_R2_THREADS
+#define OCT_R2_THREADS 448
+#endif
 template <int R> struct FusedCfg {
 	static constexpr int N = 1024 * R;
-	static constexpr int MAX_THREADS = (R == 1) ? 384 : 256;
+	static constexpr int MAX_THREADS = (R == 1) ? OCT_R1_THREADS : OCT_R2_THREADS;
 };
 
 /* shared-memory layout, shared by host (sizing) and device (carving) */
@@ -38,7 +44,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll,
 	const int N = 1024 * R, H = N / 2;
 	FusedSmem L;
 	int off = 0;
-	L.offW = off;    off += (src == SRC_RAW16 && sa == SA_TAPS4) ? N * 16 : 0;
+	L.offW = off;
 	L.offB = off;    off += (src == SRC_RAW16) ? N * 16 : 0;
 	L.offTw = off;   off += 1024 * 8;
 	L.offCtw = off;  off += (R == 2) ? 1024 * 8 : 0;
@@ -54,7 +60,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll,
 		if (w2 > work) work = w2;
 	}
 	L.workBytes = align_up(work, 128);
-	L.groupBytes = 2 * L.slotBytes + L.workBytes + 128 /* mbarriers */;
+	L.groupBytes = L.slotBytes + L.workBytes + 128 /* mbarrier */;
 	L.total = L.offGroups + groups * L.groupBytes;
 	return L;
 }
@@ -93,7 +99,6 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	const int tig = p * 32 + lane;     /* thread in group */
 	const FusedSmem L = fused_smem_layout(R, SA, ROLL, SRC, a.HB, a.HA, groupsPerCta);
 
-	const float4* sW = reinterpret_cast<const float4*>(smem + L.offW);
 	const float4* sB = reinterpret_cast<const float4*>(smem + L.offB);
 	const float2* sTw = reinterpret_cast<const float2*>(smem + L.offTw);
 	const float2* sCtw = reinterpret_cast<const float2*>(smem + L.offCtw);
@@ -108,7 +113,6 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 			for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
 		};
 		if constexpr (SRC == SRC_RAW16) {
-			if constexpr (SA == SA_TAPS4) fill(L.offW, a.lutW, N * 16);
 			fill(L.offB, a.lutB, N * 16);
 		}
 		fill(L.offTw, a.tw, 1024 * 8);
@@ -118,10 +122,11 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	}
 
 	unsigned char* gbase = smem + L.offGroups + grp * L.groupBytes;
-	unsigned char* slot0 = gbase;
-	unsigned char* slot1 = gbase + L.slotBytes;
-	unsigned char* work = gbase + 2 * L.slotBytes;
-	uint64_t* bars = reinterpret_cast<uint64_t*>(work + L.workBytes);
+	/* ONE raw slot per group: it is free again as soon as the line has been converted to fp32, i.e. a full line time
+	 * (~10 us with 16 groups per SM) before its next use -- far longer than the HBM latency of the bulk copy */
+	unsigned char* slot = gbase;
+	unsigned char* work = gbase + L.slotBytes;
+	uint64_t* bar = reinterpret_cast<uint64_t*>(work + L.workBytes);
 	float2* tile = reinterpret_cast<float2*>(work) + p * XBUF_FLOAT2;
 	float2* partnerTile = reinterpret_cast<float2*>(work) + (R == 2 ? (1 - p) : 0) * XBUF_FLOAT2;
 	const int barId = 1 + grp;
@@ -134,14 +139,11 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	const int g0 = blockIdx.x * groupsPerCta + grp;
 
 	if constexpr (SRC == SRC_RAW16) {
-		if (tig == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+		if (tig == 0) { mbar_init(bar, 1); mbar_fence_init(); }
 	}
 	__syncthreads();
 	if constexpr (SRC == SRC_RAW16) {
-		if (tig == 0) {
-			if (g0 < a.lines) issue_line_load<R>(a, g0, slot0, &bars[0]);
-			if (g0 + G < a.lines) issue_line_load<R>(a, g0 + G, slot1, &bars[1]);
-		}
+		if (tig == 0 && g0 < a.lines) issue_line_load<R>(a, g0, slot, bar);
 	}
 
 	int it = 0;
@@ -149,9 +151,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 		float2 v[32];
 
 		if constexpr (SRC == SRC_RAW16) {
-			unsigned char* slot = (it & 1) ? slot1 : slot0;
-			uint64_t* bar = &bars[it & 1];
-			mbar_wait(bar, (uint32_t)((it >> 1) & 1));
+			mbar_wait(bar, (uint32_t)(it & 1));
 
 			/* ---- slot conversion: inputToCufftComplex[_and_bitshift] once per sample (cuda_code.cu:109-147) ---- */
 			{
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 				}
 			}
 			group_sync<R>(barId);
-			/* raw slot consumed: refill it with the line this group handles two iterations from now */
-			if (tig == 0 && gline + 2 * G < a.lines) issue_line_load<R>(a, gline + 2 * G, slot, bar);
+			/* raw slot consumed: refill it with the next line of this group */
+			if (tig == 0 && gline + G < a.lines) issue_line_load<R>(a, gline + G, slot, bar);
 			if constexpr (ROLL) {
 				const int W = a.W;
 				for (int q = tig; q < SE; q += 32 * R) {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 			const float* f = fslot + a.HB;
 			/* the reference clamps the Lanczos line offset to >= 8 (cuda_code.cu:313): line 0 of the buffer is read 8 samples late */
 			const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
-			stage_a<SA, R>(lane, p, f, shift, sW, sB, v);
+			stage_a<SA, R>(lane, p, f, shift, sB, v);
 			group_sync<R>(barId);          /* all gathers done before the exchange tile (aliasing the slot) is written */
 		} else {
 			const float2* in = a.cin + (size_t)gline * N;

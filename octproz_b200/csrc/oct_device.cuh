@@ -55,7 +55,6 @@ struct FusedArgs {
 	const float2* cin;       /* SRC_CPLX : [lines][N] float2 FFT input written by the pre-FFT kernel */
 	float* out;              /* [lines][N/2] processed output slab (flip folded into the line address) */
 	float2* cplxOut;         /* != NULL: write the pre-FPN complex bins [lines][N/2] instead (FPN determination pass) */
-	const float4* lutW;      /* N tap-weight entries (SA_TAPS4) */
 	const float4* lutB;      /* N entries */
 	const float2* tw;        /* 1024 inter-pass twiddles */
 	const float2* ctw;       /* 1024 combine twiddles (R == 2) */

@@ -4,9 +4,8 @@
  * The reference uploads three per-sample curves (resample, window, dispersion phase) and lets every
  * thread re-derive tap indices / interpolation polynomials / the window*phasor product for every
  * A-scan (cuda_code.cu:213-489).  All of that is identical for every A-scan, so it is folded ONCE into
- * two float4 tables per sample m:
- *   W[m] = four tap weights        (linear: cuda_code.cu:213-231, Catmull-Rom: cuda_code.cu:258-295)
- *   B[m] = { first tap index, window*cos(phi), window*sin(phi), fractional position }
+ * one float4 table entry per sample m:
+ *   B[m] = { (int)resample[m], window*cos(phi), window*sin(phi), resample[m] - (int)resample[m] }
  * plus the four-step twiddles of the 32x32 FFT and the folded scale constants of
  * postProcessTruncateLog/Lin (cuda_code.cu:699-741).
  */
@@ -20,7 +19,7 @@
 namespace octb200 {
 
 struct StageLuts {
-	std::vector<float4> W, B;
+	std::vector<float4> B;
 };
 
 inline float int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
@@ -32,53 +31,20 @@ inline size_t lut_slot(int m, int N, int R) { return (size_t)(m % R) * (size_t)(
 /*
  * N           samples per line
  * R           warps per line group (1 for N=1024, 2 for N=2048); 1 for the generic pre-FFT kernel
- * sa          SA_NONE / SA_TAPS4 / SA_LANCZOS
- * interp      OCTB200_INTERP_* (only for SA_TAPS4: 0 linear, 1 cubic)
  * resample    clamped resample curve (nullptr when resampling is off)
  * window      window LUT or nullptr (windowing off -> 1)
  * phasor      (cos phi, sin phi) pairs as produced by fill_phase on the GPU, or nullptr (dispersion off -> (1,0))
  */
-inline void build_stage_luts(int N, int R, int sa, int interp, const float* resample, const float* window,
-                             const float2* phasor, StageLuts& out) {
-	out.W.assign((size_t)N, make_float4(0, 0, 0, 0));
+inline void build_stage_luts(int N, int R, const float* resample, const float* window, const float2* phasor, StageLuts& out) {
 	out.B.assign((size_t)N, make_float4(0, 0, 0, 0));
 	for (int m = 0; m < N; ++m) {
 		const float w = window ? window[m] : 1.0f;
 		const float px = phasor ? phasor[m].x : 1.0f;
 		const float py = phasor ? phasor[m].y : 0.0f;
-		float4 W = make_float4(0, 0, 0, 0);
-		float4 B = make_float4(0, w * px, w * py, 0);
-		if (sa == SA_TAPS4 || sa == SA_LANCZOS) {
-			const float xi = resample ? resample[m] : (float)m;
-			const int n1 = (int)xi;                 /* C truncation, cuda_code.cu:223 / :283 / :315 */
-			const float tf = xi - (float)n1;        /* exact in fp32 */
-			B.w = tf;
-			if (sa == SA_LANCZOS) {
-				B.x = int_as_float(n1);
-			} else {
-				const double t = (double)tf;
-				double w0, w1, w2, w3;
-				if (interp == 1) {                   /* Catmull-Rom, cuda_code.cu:258-271 expanded per tap */
-					w0 = 0.5 * (-t * t * t + 2.0 * t * t - t);
-					w1 = 0.5 * (3.0 * t * t * t - 5.0 * t * t + 2.0);
-					w2 = 0.5 * (-3.0 * t * t * t + 4.0 * t * t + t);
-					w3 = 0.5 * (t * t * t - t * t);
-				} else {                             /* linear, cuda_code.cu:229 */
-					w0 = 0.0; w1 = 1.0 - t; w2 = t; w3 = 0.0;
-				}
-				if (n1 >= 1) {
-					B.x = int_as_float(n1 - 1);
-					W = make_float4((float)w0, (float)w1, (float)w2, (float)w3);
-				} else {
-					/* n1 == 0: the reference reads y0 at abs(n1-1) = 1 (cuda_code.cu:284) -> fold w0 onto tap 1 */
-					B.x = int_as_float(0);
-					W = make_float4((float)w1, (float)(w0 + w2), (float)w3, 0.0f);
-				}
-			}
-		}
-		const size_t slot = lut_slot(m, N, R);
-		out.W[slot] = W;
-		out.B[slot] = B;
+		const float xi = resample ? resample[m] : (float)m;
+		const int n1 = (int)xi;                 /* C truncation, cuda_code.cu:223 / :283 / :315 */
+		const float t = xi - (float)n1;         /* exact in fp32 */
+		out.B[lut_slot(m, N, R)] = make_float4(int_as_float(n1), w * px, w * py, t);
 	}
 }
 

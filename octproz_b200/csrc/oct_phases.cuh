@@ -45,7 +45,7 @@ constexpr int XBUF_FLOAT2 = 32 * XPITCH;           /* per warp */
 constexpr int XBUF_BYTES = XBUF_FLOAT2 * 8;
 
 /* stage-A selector */
-enum { SA_NONE = 0, SA_TAPS4 = 1, SA_LANCZOS = 2 };
+enum { SA_NONE = 0, SA_LINEAR = 1, SA_LANCZOS = 2, SA_CUBIC = 3 };
 
 struct EpiConsts {
 	float scaleA;      /* log: coeff*10*log10(2)/(max-min) applied to log2(p);  lin: coeff/((N/2)*(max-min)) applied to sqrt(p) */
@@ -65,20 +65,30 @@ OCT_HD int lut_int(float f) {
 }
 
 /* ---- stage A, one sample.  f points at slot element 0 of the CURRENT line (halo before it). ----
- * LUT B = { tap base (int bits), window*cos(phi), window*sin(phi), frac }  (per sample m)
- * LUT W = { w0, w1, w2, w3 }  four tap weights (linear / Catmull-Rom, cuda_code.cu:213-295) */
-OCT_HD float2 sample_taps4(const float* f, float4 W, float4 B) {
-	const int nb = lut_int(B.x);
-	float y = W.x * f[nb];
-	y = OCT_FMA(W.y, f[nb + 1], y);
-	y = OCT_FMA(W.z, f[nb + 2], y);
-	y = OCT_FMA(W.w, f[nb + 3], y);
-	return make_float2(y * B.y, y * B.z);
+ * LUT B[m] = { n1 = (int)resample[m] as int bits, window*cos(phi), window*sin(phi), t = resample[m] - n1 }.
+ * One 16-byte shared-memory read per sample: the interpolation polynomial is evaluated in registers exactly in the
+ * reference's form (shared-memory bandwidth, not the FMA pipe, bounds this kernel). */
+OCT_HD float2 sample_linear(const float* f, float4 B) {          /* cuda_code.cu:213-231 */
+	const int n = lut_int(B.x);
+	const float f0 = f[n], f1 = f[n + 1];
+	const float y = OCT_FMA(f1 - f0, B.w, f0);
+	return cscale(make_float2(B.y, B.z), y);
+}
+OCT_HD float2 sample_cubic(const float* f, float4 B) {           /* cuda_code.cu:258-295 */
+	const int n1 = lut_int(B.x);
+	const int n0 = n1 >= 1 ? n1 - 1 : 1;                          /* abs(n1 - 1), cuda_code.cu:284 */
+	const float y0 = f[n0], y1 = f[n1], y2 = f[n1 + 1], y3 = f[n1 + 2];
+	const float a = -y0 + 3.0f * (y1 - y2) + y3;
+	const float b = 2.0f * y0 - 5.0f * y1 + 4.0f * y2 - y3;
+	const float c = -y0 + y2;
+	const float pos = B.w, pos2 = pos * pos;
+	const float y = 0.5f * pos * (a * pos2 + b * pos + c) + y1;
+	return cscale(make_float2(B.y, B.z), y);
 }
 
 OCT_HD float2 sample_none(const float* f, int m, float4 B) {
 	const float y = f[m];
-	return make_float2(y * B.y, y * B.z);
+	return cscale(make_float2(B.y, B.z), y);
 }
 
 /* cuda_code.cu:297-302 + 304-326: 16 taps i=-7..8 around n0, kernel sinc(pi u) sinc(pi u / 8).
@@ -105,20 +115,20 @@ OCT_HD float2 sample_lanczos(const float* f, int shift, float4 B) {
 		const float y = f[shift + n0 + i];
 		sum += y * lanczos8(t - (float)i);
 	}
-	return make_float2(sum * B.y, sum * B.z);
+	return cscale(make_float2(B.y, B.z), sum);
 }
 
 /* ---- stage A for one lane: 32 samples s = lane + 32 j of sub-sequence p (m = R*s + p) ----
  * LUTs are stored de-interleaved: entry of sample m lives at (m % R) * (N/R) + m / R. */
 template <int SA, int R>
-OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lutW, const float4* lutB,
-                    float2 (&v)[32]) {
+OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lutB, float2 (&v)[32]) {
 	const int base = p * 1024;
 #pragma unroll
 	for (int j = 0; j < 32; ++j) {
 		const int s = lane + 32 * j;
 		const float4 B = lutB[base + s];
-		if constexpr (SA == SA_TAPS4) v[j] = sample_taps4(f, lutW[base + s], B);
+		if constexpr (SA == SA_CUBIC) v[j] = sample_cubic(f, B);
+		else if constexpr (SA == SA_LINEAR) v[j] = sample_linear(f, B);
 		else if constexpr (SA == SA_NONE) v[j] = sample_none(f, R * s + p, B);
 		else v[j] = sample_lanczos(f, shift, B);
 	}
@@ -163,9 +173,9 @@ OCT_HD void combine_load(int lane, int p, float2 (&v)[32], const float2* partner
 		constexpr int r = decltype(rc)::value;
 		constexpr int k2 = bitrev5(r);
 		if constexpr (k2 < 16) {
-			if (p == 0) { const float2 o = partnerTile[k2 * 32 + lane]; v[r].x += o.x; v[r].y += o.y; }
+			if (p == 0) v[r] = cadd(v[r], partnerTile[k2 * 32 + lane]);
 		} else {
-			if (p == 1) { const float2 o = partnerTile[(k2 - 16) * 32 + lane]; v[r].x += o.x; v[r].y += o.y; }
+			if (p == 1) v[r] = cadd(v[r], partnerTile[(k2 - 16) * 32 + lane]);
 		}
 	});
 }
@@ -193,7 +203,7 @@ OCT_HD void epilogue_scaled(int lane, const float2 (&v)[32], const EpiConsts& e,
 		if constexpr (k2 >= K2LO && k2 < K2LO + 16) {
 			const int z = lane + 32 * k2;
 			float re = v[r].x, im = v[r].y;
-			if (e.fpn) { const float2 m = meanLine[z]; re -= m.x; im -= m.y; }
+			if (e.fpn) { const float2 d = csub(v[r], meanLine[z]); re = d.x; im = d.y; }
 			float o = scale_output(re, im, e);
 			if (e.ppbg) o = saturate01(o - OCT_FMA(e.ppbgWeight, ppbg[z], e.ppbgOffset));
 			outLine[z] = o;

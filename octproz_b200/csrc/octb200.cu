@@ -81,8 +81,8 @@ struct octb200_pipeline {
 	float2* dMeanLine = nullptr;
 	float* dPpbg = nullptr;
 	float* dPhase = nullptr; float2* dPhasor = nullptr;
-	float4 *dLutW = nullptr, *dLutB = nullptr;       /* fused layout (de-interleaved by R) */
-	float4 *dLutW1 = nullptr, *dLutB1 = nullptr;     /* natural order for the generic pre kernel */
+	float4* dLutB = nullptr;       /* fused layout (de-interleaved by R) */
+	float4* dLutB1 = nullptr;      /* natural order for the generic pre kernel */
 	float2 *dTw = nullptr, *dCtw = nullptr;
 	float* dSinCurve = nullptr;
 	void* dOutConv[2] = { nullptr, nullptr };
@@ -155,7 +155,7 @@ struct Stage { int sa; bool roll; int W; int HB, HA; };
 Stage select_stage(const octb200_pipeline* p) {
 	Stage s{};
 	const octb200_params& q = p->prm;
-	s.sa = q.resampling ? (q.resamplingInterpolation == OCTB200_INTERP_LANCZOS ? SA_LANCZOS : SA_TAPS4) : SA_NONE;
+	s.sa = q.resampling ? (q.resamplingInterpolation == OCTB200_INTERP_LANCZOS ? SA_LANCZOS : (q.resamplingInterpolation == OCTB200_INTERP_CUBIC ? SA_CUBIC : SA_LINEAR)) : SA_NONE;
 	s.roll = q.backgroundRemoval != 0;
 	s.W = q.rollingAverageWindowSize < 1 ? 1 : q.rollingAverageWindowSize;
 	if (s.sa == SA_LANCZOS) { s.HB = 16 + (s.roll ? rup(s.W, 16) : 0); s.HA = s.HB; }
@@ -182,16 +182,14 @@ int rebuild_luts(octb200_pipeline* p) {
 	const float* res = q.resampling ? p->hResample.data() : nullptr;
 	const float* win = q.windowing ? p->hWindow.data() : nullptr;
 	const float2* ph = q.dispersionCompensation ? phasor.data() : nullptr;
-	const int interp = q.resamplingInterpolation == OCTB200_INTERP_CUBIC ? 1 : 0;
+	const int interp = q.resamplingInterpolation;
 	StageLuts l;
-	if (p->R >= 1 && (p->N == 1024 || p->N == 2048)) {
-		build_stage_luts(N, p->R, st.sa, interp, res, win, ph, l);
-		CK(p, cudaMemcpyAsync(p->dLutW, l.W.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
+	if (p->N == 1024 || p->N == 2048) {
+		build_stage_luts(N, p->R, res, win, ph, l);
 		CK(p, cudaMemcpyAsync(p->dLutB, l.B.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
 		CK(p, cudaStreamSynchronize(p->sCompute));
 	}
-	build_stage_luts(N, 1, st.sa, interp, res, win, ph, l);
-	CK(p, cudaMemcpyAsync(p->dLutW1, l.W.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
+	build_stage_luts(N, 1, res, win, ph, l);
 	CK(p, cudaMemcpyAsync(p->dLutB1, l.B.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
 	CK(p, cudaStreamSynchronize(p->sCompute));
 	p->lutsDirty = false;
@@ -223,7 +221,7 @@ FusedArgs fused_args(const octb200_pipeline* p, const Stage& st, const void* dRa
 	FusedArgs a{};
 	a.raw = static_cast<const uint16_t*>(dRaw);
 	a.cin = p->dFft;
-	a.lutW = p->dLutW; a.lutB = p->dLutB; a.tw = p->dTw; a.ctw = p->dCtw;
+	a.lutB = p->dLutB; a.tw = p->dTw; a.ctw = p->dCtw;
 	a.meanLine = p->dMeanLine; a.ppbg = p->dPpbg;
 	a.totalSamples = p->S; a.lines = lines; a.A = p->A;
 	a.flip = p->prm.bscanFlip; a.bscanBase = p->cfg.bscanIndexBase;
@@ -232,7 +230,7 @@ FusedArgs fused_args(const octb200_pipeline* p, const Stage& st, const void* dRa
 }
 PreArgs pre_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, int lines) {
 	PreArgs a{};
-	a.raw = dRaw; a.out = p->dFft; a.lutW = p->dLutW1; a.lutB = p->dLutB1;
+	a.raw = dRaw; a.out = p->dFft; a.lutB = p->dLutB1;
 	a.totalSamples = p->S; a.lines = lines; a.N = p->N;
 	a.shiftBits = p->prm.bitshift ? 4 : 0; a.W = st.W;
 	/* halos in elements, multiples of 16 so every container type keeps 16-byte alignment */
@@ -444,8 +442,7 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	RCC(dalloc(p, &p->dPpbg, (size_t)p->H));
 	RCC(dalloc(p, &p->dPhase, (size_t)p->N));
 	RCC(dalloc(p, &p->dPhasor, (size_t)p->N));
-	RCC(dalloc(p, &p->dLutW, (size_t)p->N)); RCC(dalloc(p, &p->dLutB, (size_t)p->N));
-	RCC(dalloc(p, &p->dLutW1, (size_t)p->N)); RCC(dalloc(p, &p->dLutB1, (size_t)p->N));
+	RCC(dalloc(p, &p->dLutB, (size_t)p->N)); RCC(dalloc(p, &p->dLutB1, (size_t)p->N));
 	RCC(dalloc(p, &p->dTw, (size_t)1024)); RCC(dalloc(p, &p->dCtw, (size_t)1024));
 	RCC(dalloc(p, &p->dSinCurve, (size_t)p->A));
 	{
@@ -483,7 +480,7 @@ int octb200_destroy(octb200_pipeline* p) {
 	if (p->evFloatCopied) cudaEventDestroy(p->evFloatCopied);
 	for (auto e : p->evConvFree) if (e) cudaEventDestroy(e);
 	dfree(p->dVolumeOwned); dfree(p->dTmp); dfree(p->dFft); dfree(p->dFpnScratch); dfree(p->dMeanLine); dfree(p->dPpbg);
-	dfree(p->dPhase); dfree(p->dPhasor); dfree(p->dLutW); dfree(p->dLutB); dfree(p->dLutW1); dfree(p->dLutB1);
+	dfree(p->dPhase); dfree(p->dPhasor); dfree(p->dLutB); dfree(p->dLutB1);
 	dfree(p->dTw); dfree(p->dCtw); dfree(p->dSinCurve);
 	for (void*& c : p->dOutConv) { if (c) cudaFree(c); c = nullptr; }
 	if (p->sCompute) cudaStreamDestroy(p->sCompute);

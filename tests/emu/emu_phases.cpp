@@ -56,7 +56,8 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 	const int R = N / 1024;
 	if (R != 1 && R != 2) return -1;
 	StageLuts luts;
-	build_stage_luts(N, R, sa, interp, resample, window, reinterpret_cast<const float2*>(phasor), luts);
+	(void)interp;
+	build_stage_luts(N, R, resample, window, reinterpret_cast<const float2*>(phasor), luts);
 	std::vector<float2> tw, ctw;
 	build_twiddles_1024(tw);
 	build_combine_twiddles_2048(ctw);
@@ -67,9 +68,11 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 	for (int p = 0; p < R; ++p) {
 		for (int lane = 0; lane < 32; ++lane) {
 			float2 (&v)[32] = regs[p][lane];
-			if (sa == SA_TAPS4) { if (R == 1) stage_a<SA_TAPS4, 1>(lane, p, fslot, shift, luts.W.data(), luts.B.data(), v); else stage_a<SA_TAPS4, 2>(lane, p, fslot, shift, luts.W.data(), luts.B.data(), v); }
-			else if (sa == SA_NONE) { if (R == 1) stage_a<SA_NONE, 1>(lane, p, fslot, shift, luts.W.data(), luts.B.data(), v); else stage_a<SA_NONE, 2>(lane, p, fslot, shift, luts.W.data(), luts.B.data(), v); }
-			else { if (R == 1) stage_a<SA_LANCZOS, 1>(lane, p, fslot, shift, luts.W.data(), luts.B.data(), v); else stage_a<SA_LANCZOS, 2>(lane, p, fslot, shift, luts.W.data(), luts.B.data(), v); }
+			const float4* B = luts.B.data();
+			if (sa == SA_CUBIC) { if (R == 1) stage_a<SA_CUBIC, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_CUBIC, 2>(lane, p, fslot, shift, B, v); }
+			else if (sa == SA_LINEAR) { if (R == 1) stage_a<SA_LINEAR, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_LINEAR, 2>(lane, p, fslot, shift, B, v); }
+			else if (sa == SA_NONE) { if (R == 1) stage_a<SA_NONE, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_NONE, 2>(lane, p, fslot, shift, B, v); }
+			else { if (R == 1) stage_a<SA_LANCZOS, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_LANCZOS, 2>(lane, p, fslot, shift, B, v); }
 			fft32_inv_dif(v);
 			exchange_store(lane, v, tile[p].data(), tw.data());
 		}

@@ -49,7 +49,7 @@ def test_four_step_1024(emu):
 @pytest.mark.parametrize("n", [1024, 2048])
 @pytest.mark.parametrize("case", ["cubic", "linear", "lanczos", "none"])
 def test_fused_line_matches_oracle(emu, n, case):
-    interp, sa = {"cubic": (1, 1), "linear": (0, 1), "lanczos": (2, 2), "none": (0, 0)}[case]
+    interp, sa = {"cubic": (1, 3), "linear": (0, 1), "lanczos": (2, 2), "none": (0, 0)}[case]     # SA_CUBIC=3, SA_LINEAR=1, SA_LANCZOS=2, SA_NONE=0
     q = benchmark_params(n, 1, 1); q.fixedPatternNoiseRemoval = False
     q.resampling = case != "none"; q.resamplingInterpolation = interp
     q.update_all_curves()

@@ -185,5 +185,38 @@ def cmd_quick():
             print("quick", n, mname, json.dumps(stats(out, ref)), flush=True)
 
 
+def cmd_perf():
+    """resident timing of the fused kernel + whole chain for both workloads (use OCTB200_LIB to pick an A/B build)"""
+    import torch
+    tag = os.environ.get("OCTB200_TAG", "default")
+    res = {}
+    for (n, a, b, bits) in ((1024, 512, 256, 12), (2048, 1024, 128, 16)):
+        q = benchmark_params(n, a, b, bits); q.update_all_curves()
+        small = synth.make_volume(n, a, 8, bits, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+        raw = np.ascontiguousarray(np.tile(small, (b // 8, 1, 1)))
+        d = [torch.from_numpy(raw.view(np.int16)).cuda(), torch.from_numpy(raw.view(np.int16).copy()).cuda()]
+        p = OctPipeline(fft_mode=_lib.FFT_FUSED)
+        assert p.initializeCuda(None, None, copy.deepcopy(q)), getattr(p, "_create_error", "")
+        p.process_device(d[0]); p.sync()
+        for i in range(5):
+            p.process_device(d[i & 1])
+        p.sync()
+        iters = 50
+        p.event_record(0)
+        for i in range(iters):
+            p.process_device(d[i & 1])
+        p.event_record(1)
+        ms = p.event_elapsed_ms(0, 1) / iters
+        kms = p.time_kernel(d[1], 30)
+        out = p.copy_output(0)
+        ref, _, _ = orc.process(copy.deepcopy(q).__class__(**{**q.__dict__, "bscansPerBuffer": 8}), small, mean_line=p.fpn_mean_line().astype(np.float64), determine_fpn=False)
+        st = stats(out[:8], ref)
+        key = f"{tag}/N{n}"
+        res[key] = {"chain_ms": ms, "kernel_ms": kms, "MHz": a * b / ms / 1e3, "alg_GBs": a * b * n * 4 / kms / 1e6, "p9999_vs_oracle": st["p9999"], "gt1e-4": st["frac_gt_1e-4"]}
+        print(key, json.dumps(res[key]), flush=True)
+        p.cleanupCuda()
+    json.dump(res, open(os.path.join(OUT, f"perf_{tag}.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"quick": cmd_quick, "parity": cmd_parity, "refcuda": cmd_refcuda, "timing": cmd_timing}[sys.argv[1]]()
+    {"perf": cmd_perf, "quick": cmd_quick, "parity": cmd_parity, "refcuda": cmd_refcuda, "timing": cmd_timing}[sys.argv[1]]()
