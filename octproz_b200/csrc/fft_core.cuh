@@ -18,6 +18,7 @@
 #endif
 
 #include <type_traits>
+#include <cmath>
 
 namespace octb200 {
 
@@ -75,6 +76,23 @@ OCT_HD float2 cscale(float2 a, float s) {
 	return make_float2(a.x * s, a.y * s);
 #endif
 }
+/* generic packed pair helpers (two independent fp32 lanes) */
+OCT_HD float2 pfma(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+	return __ffma2_rn(a, b, c);
+#else
+	return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+OCT_HD float2 pmul(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+	return __fmul2_rn(a, b);
+#else
+	return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+OCT_HD float2 pneg(float2 a) { return make_float2(-a.x, -a.y); }
+
 /* i * a = (-a.y, a.x): a swizzle + half negation, folded into the consumer's operand modifiers */
 OCT_HD float2 cmul_i(float2 a) { return make_float2(-a.y, a.x); }
 

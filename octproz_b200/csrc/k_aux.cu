@@ -45,7 +45,7 @@ __device__ __forceinline__ float convert_raw(RawT v, int shiftBits) {
 
 /* per-warp shared layout of the pre kernel */
 __host__ __device__ inline int pre_warp_bytes(int SE, int rawBytes, bool roll) {
-	return 2 * align_up(SE * rawBytes, 128) + align_up(SE * 4, 128) + (roll ? align_up((SE + 1) * 8, 128) : 0) + 128;
+	return 2 * align_up(SE * rawBytes, 128) + align_up((FSLOT_PAD + SE) * 4, 128) + (roll ? align_up((SE + 1) * 8, 128) : 0) + 128;
 }
 
 template <typename RawT, int SA, bool ROLL>
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(256) oct_pre_kernel(const PreArgs a) {
 	unsigned char* wbase = smem + warp * pre_warp_bytes(SE, RB, ROLL);
 	const int slotBytes = align_up(SE * RB, 128);
 	unsigned char* slots[2] = { wbase, wbase + slotBytes };
-	float* fslot = reinterpret_cast<float*>(wbase + 2 * slotBytes);
-	unsigned long long* prefix = reinterpret_cast<unsigned long long*>(wbase + 2 * slotBytes + align_up(SE * 4, 128));
+	float* fslot = reinterpret_cast<float*>(wbase + 2 * slotBytes) + FSLOT_PAD;
+	unsigned long long* prefix = reinterpret_cast<unsigned long long*>(wbase + 2 * slotBytes + align_up((FSLOT_PAD + SE) * 4, 128));
 	uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + pre_warp_bytes(SE, RB, ROLL) - 128);
 
 	const int G = gridDim.x * (blockDim.x >> 5);
@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(256) oct_pre_kernel(const PreArgs a) {
 				else sum = (float)d;
 				fslot[q] -= __fdividef(sum, (float)(e - ss + 1));
 			}
+			__syncwarp();
+		}
+		if constexpr (SA == SA_CUBIC) {
+			if (lane == 0) fslot[a.HB - 1] = fslot[a.HB + 1];      /* mirrored first tap of the cubic (cuda_code.cu:284) */
 			__syncwarp();
 		}
 		const float* f = fslot + a.HB;

@@ -56,7 +56,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll,
 	L.slotBytes = (src == SRC_RAW16) ? align_up(SE * 2, 128) : 0;
 	int work = R * XBUF_BYTES;
 	if (src == SRC_RAW16) {
-		int w2 = align_up(SE * 4, 16) + (roll ? align_up((SE + 1) * 4, 16) : 0);
+		int w2 = align_up((FSLOT_PAD + SE) * 4, 16) + (roll ? align_up((SE + 1) * 4, 16) : 0);
 		if (w2 > work) work = w2;
 	}
 	L.workBytes = align_up(work, 128);
@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	const int barId = 1 + grp;
 
 	const int SE = a.HB + N + a.HA;
-	float* fslot = reinterpret_cast<float*>(work);
-	unsigned* prefix = reinterpret_cast<unsigned*>(work + align_up(SE * 4, 16));
+	float* fslot = reinterpret_cast<float*>(work) + FSLOT_PAD;       /* slot element 0; FSLOT_PAD floats of head room */
+	unsigned* prefix = reinterpret_cast<unsigned*>(work + align_up((FSLOT_PAD + SE) * 4, 16));
 
 	const int G = gridDim.x * groupsPerCta;
 	const int g0 = blockIdx.x * groupsPerCta + grp;
@@ -146,6 +146,11 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 		if (tig == 0 && g0 < a.lines) issue_line_load<R>(a, g0, slot, bar);
 	}
 
+#ifdef OCT_STAGGER_NS
+	/* de-phase the line groups of a CTA so that shared-memory-heavy (stage A) and FMA-heavy (FFT) phases of different
+	 * groups overlap instead of all groups hitting the same pipe at the same time */
+	__nanosleep((unsigned)(grp * OCT_STAGGER_NS));
+#endif
 	int it = 0;
 	for (int gline = g0; gline < a.lines; gline += G, ++it) {
 		float2 v[32];
@@ -157,10 +162,17 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 			{
 				const uint2* s2 = reinterpret_cast<const uint2*>(slot);
 				float4* f4 = reinterpret_cast<float4*>(fslot);
+				const unsigned sh = (unsigned)a.shiftBits;
+				const unsigned msk = (0xFFFFu >> sh) * 0x00010001u;
+#pragma unroll 4
 				for (int q4 = tig; q4 < SE / 4; q4 += 32 * R) {
-					uint2 w = s2[q4];
-					if (a.shiftBits) { w.x = (w.x >> 4) & 0x0FFF0FFFu; w.y = (w.y >> 4) & 0x0FFF0FFFu; }
-					f4[q4] = make_float4(u16lo_to_float(w.x), u16hi_to_float(w.x), u16lo_to_float(w.y), u16hi_to_float(w.y));
+					const uint2 w = s2[q4];
+					const unsigned wx = (w.x >> sh) & msk, wy = (w.y >> sh) & msk;
+					f4[q4] = make_float4(u16lo_to_float(wx), u16hi_to_float(wx), u16lo_to_float(wy), u16hi_to_float(wy));
+				}
+				if constexpr (SA == SA_CUBIC && !ROLL) {
+					/* mirrored first tap of the cubic: f[-1] = f[1] (cuda_code.cu:284) */
+					if (tig == 0) fslot[a.HB - 1] = (float)(reinterpret_cast<const uint16_t*>(slot)[a.HB + 1] >> sh);
 				}
 			}
 			if constexpr (ROLL) {
@@ -194,6 +206,10 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 					fslot[q] -= mean;
 				}
 				group_sync<R>(barId);
+				if constexpr (SA == SA_CUBIC) {
+					if (tig == 0) fslot[a.HB - 1] = fslot[a.HB + 1];
+					group_sync<R>(barId);
+				}
 			}
 
 			const float* f = fslot + a.HB;

@@ -5,7 +5,7 @@
  * thread re-derive tap indices / interpolation polynomials / the window*phasor product for every
  * A-scan (cuda_code.cu:213-489).  All of that is identical for every A-scan, so it is folded ONCE into
  * one float4 table entry per sample m:
- *   B[m] = { (int)resample[m], window*cos(phi), window*sin(phi), resample[m] - (int)resample[m] }
+ *   B[m] = { 4*(int)resample[m] (byte offset), window*cos(phi), window*sin(phi), resample[m] - (int)resample[m] }
  * plus the four-step twiddles of the 32x32 FFT and the folded scale constants of
  * postProcessTruncateLog/Lin (cuda_code.cu:699-741).
  */
@@ -44,7 +44,7 @@ inline void build_stage_luts(int N, int R, const float* resample, const float* w
 		const float xi = resample ? resample[m] : (float)m;
 		const int n1 = (int)xi;                 /* C truncation, cuda_code.cu:223 / :283 / :315 */
 		const float t = xi - (float)n1;         /* exact in fp32 */
-		out.B[lut_slot(m, N, R)] = make_float4(int_as_float(n1), w * px, w * py, t);
+		out.B[lut_slot(m, N, R)] = make_float4(int_as_float(4 * n1), w * px, w * py, t);   /* byte offset of tap n1 */
 	}
 }
 

@@ -64,26 +64,59 @@ OCT_HD int lut_int(float f) {
 #endif
 }
 
-/* ---- stage A, one sample.  f points at slot element 0 of the CURRENT line (halo before it). ----
- * LUT B[m] = { n1 = (int)resample[m] as int bits, window*cos(phi), window*sin(phi), t = resample[m] - n1 }.
- * One 16-byte shared-memory read per sample: the interpolation polynomial is evaluated in registers exactly in the
- * reference's form (shared-memory bandwidth, not the FMA pipe, bounds this kernel). */
+/* ---- stage A.  f points at slot element 0 of the CURRENT line; the float slot has FSLOT_PAD floats in front of the
+ * line (plus the Lanczos halo), and for the cubic f[-1] is set to f[1] so that the reference's mirrored first tap
+ * abs(n1-1) (cuda_code.cu:284) is a plain n1-1.
+ * LUT B[m] = { 4*n1 as int bits (byte offset of tap n1), window*cos(phi), window*sin(phi), t = resample[m] - n1 }.
+ * One 16-byte shared-memory read per sample; the interpolation polynomial is evaluated in registers in the
+ * reference's form, two samples per packed (f32x2) instruction. */
+constexpr int FSLOT_PAD = 4;
+
+OCT_HD float ldf(const float* f, int byteOff) {
+	return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(f) + byteOff);
+}
+
 OCT_HD float2 sample_linear(const float* f, float4 B) {          /* cuda_code.cu:213-231 */
-	const int n = lut_int(B.x);
-	const float f0 = f[n], f1 = f[n + 1];
+	const int o = lut_int(B.x);
+	const float f0 = ldf(f, o), f1 = ldf(f, o + 4);
 	const float y = OCT_FMA(f1 - f0, B.w, f0);
 	return cscale(make_float2(B.y, B.z), y);
 }
+/* scalar form (generic pre kernel, odd tails); needs f[-1] == f[1] */
 OCT_HD float2 sample_cubic(const float* f, float4 B) {           /* cuda_code.cu:258-295 */
-	const int n1 = lut_int(B.x);
-	const int n0 = n1 >= 1 ? n1 - 1 : 1;                          /* abs(n1 - 1), cuda_code.cu:284 */
-	const float y0 = f[n0], y1 = f[n1], y2 = f[n1 + 1], y3 = f[n1 + 2];
+	const int o = lut_int(B.x);
+	const float y0 = ldf(f, o - 4), y1 = ldf(f, o), y2 = ldf(f, o + 4), y3 = ldf(f, o + 8);
 	const float a = -y0 + 3.0f * (y1 - y2) + y3;
 	const float b = 2.0f * y0 - 5.0f * y1 + 4.0f * y2 - y3;
 	const float c = -y0 + y2;
 	const float pos = B.w, pos2 = pos * pos;
 	const float y = 0.5f * pos * (a * pos2 + b * pos + c) + y1;
 	return cscale(make_float2(B.y, B.z), y);
+}
+/* two samples at once: every polynomial step is one packed instruction for both */
+OCT_HD void sample_cubic_x2(const float* f, float4 Ba, float4 Bb, float2& outA, float2& outB) {
+	const int oa = lut_int(Ba.x), ob = lut_int(Bb.x);
+	const float2 Y0 = make_float2(ldf(f, oa - 4), ldf(f, ob - 4));
+	const float2 Y1 = make_float2(ldf(f, oa), ldf(f, ob));
+	const float2 Y2 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4));
+	const float2 Y3 = make_float2(ldf(f, oa + 8), ldf(f, ob + 8));
+	const float2 a = pfma(csub(Y1, Y2), make_float2(3.0f, 3.0f), csub(Y3, Y0));                                /* -y0 + 3(y1-y2) + y3 */
+	const float2 b = pfma(Y0, make_float2(2.0f, 2.0f), pfma(Y1, make_float2(-5.0f, -5.0f), pfma(Y2, make_float2(4.0f, 4.0f), pneg(Y3))));
+	const float2 c = csub(Y2, Y0);
+	const float2 pos = make_float2(Ba.w, Bb.w);
+	const float2 pos2 = pmul(pos, pos);
+	const float2 inner = pfma(a, pos2, pfma(b, pos, c));
+	const float2 y = pfma(pmul(pos, make_float2(0.5f, 0.5f)), inner, Y1);
+	outA = cscale(make_float2(Ba.y, Ba.z), y.x);
+	outB = cscale(make_float2(Bb.y, Bb.z), y.y);
+}
+OCT_HD void sample_linear_x2(const float* f, float4 Ba, float4 Bb, float2& outA, float2& outB) {
+	const int oa = lut_int(Ba.x), ob = lut_int(Bb.x);
+	const float2 F0 = make_float2(ldf(f, oa), ldf(f, ob));
+	const float2 F1 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4));
+	const float2 y = pfma(csub(F1, F0), make_float2(Ba.w, Bb.w), F0);
+	outA = cscale(make_float2(Ba.y, Ba.z), y.x);
+	outB = cscale(make_float2(Bb.y, Bb.z), y.y);
 }
 
 OCT_HD float2 sample_none(const float* f, int m, float4 B) {
@@ -107,12 +140,12 @@ OCT_HD float lanczos8(float x) {
 }
 
 OCT_HD float2 sample_lanczos(const float* f, int shift, float4 B) {
-	const int n0 = lut_int(B.x);
+	const int o = lut_int(B.x) + 4 * shift;
 	const float t = B.w;
 	float sum = 0.0f;
 #pragma unroll
 	for (int i = -7; i <= 8; ++i) {
-		const float y = f[shift + n0 + i];
+		const float y = ldf(f, o + 4 * i);
 		sum += y * lanczos8(t - (float)i);
 	}
 	return cscale(make_float2(B.y, B.z), sum);
@@ -123,14 +156,22 @@ OCT_HD float2 sample_lanczos(const float* f, int shift, float4 B) {
 template <int SA, int R>
 OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lutB, float2 (&v)[32]) {
 	const int base = p * 1024;
+	if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
 #pragma unroll
-	for (int j = 0; j < 32; ++j) {
-		const int s = lane + 32 * j;
-		const float4 B = lutB[base + s];
-		if constexpr (SA == SA_CUBIC) v[j] = sample_cubic(f, B);
-		else if constexpr (SA == SA_LINEAR) v[j] = sample_linear(f, B);
-		else if constexpr (SA == SA_NONE) v[j] = sample_none(f, R * s + p, B);
-		else v[j] = sample_lanczos(f, shift, B);
+		for (int j = 0; j < 32; j += 2) {
+			const float4 Ba = lutB[base + lane + 32 * j];
+			const float4 Bb = lutB[base + lane + 32 * (j + 1)];
+			if constexpr (SA == SA_CUBIC) sample_cubic_x2(f, Ba, Bb, v[j], v[j + 1]);
+			else sample_linear_x2(f, Ba, Bb, v[j], v[j + 1]);
+		}
+	} else {
+#pragma unroll
+		for (int j = 0; j < 32; ++j) {
+			const int s = lane + 32 * j;
+			const float4 B = lutB[base + s];
+			if constexpr (SA == SA_NONE) v[j] = sample_none(f, R * s + p, B);
+			else v[j] = sample_lanczos(f, shift, B);
+		}
 	}
 }
 
@@ -182,7 +223,7 @@ OCT_HD void combine_load(int lane, int p, float2 (&v)[32], const float2* partner
 
 /* ---- epilogue for 16 outputs per lane: z = zBase + lane + 32*(k2 - K2LO), k2 in [K2LO, K2LO+16) ---- */
 OCT_HD float scale_output(float re, float im, const EpiConsts& e) {
-	const float pw = re * re + im * im;
+	const float pw = OCT_FMA(re, re, im * im);
 	return e.logMode ? OCT_FMA(OCT_LG2(pw), e.scaleA, e.scaleB) : OCT_FMA(OCT_SQRT(pw), e.scaleA, e.scaleB);
 }
 OCT_HD float saturate01(float v) {
@@ -194,21 +235,39 @@ OCT_HD float saturate01(float v) {
 #endif
 }
 
-template <int K2LO>
-OCT_HD void epilogue_scaled(int lane, const float2 (&v)[32], const EpiConsts& e, const float2* meanLine,
-                            const float* ppbg, float* outLine) {
+template <int K2LO, bool LOG, bool FPN, bool PPBG>
+OCT_HD void epilogue_scaled_t(int lane, const float2 (&v)[32], const EpiConsts& e, const float2* meanLine,
+                              const float* ppbg, float* outLine) {
+	const float sA = e.scaleA, sB = e.scaleB, bw = e.ppbgWeight, bo = e.ppbgOffset;
 	static_for<0, 32>([&](auto rc) {
 		constexpr int r = decltype(rc)::value;
 		constexpr int k2 = bitrev5(r);
 		if constexpr (k2 >= K2LO && k2 < K2LO + 16) {
 			const int z = lane + 32 * k2;
-			float re = v[r].x, im = v[r].y;
-			if (e.fpn) { const float2 d = csub(v[r], meanLine[z]); re = d.x; im = d.y; }
-			float o = scale_output(re, im, e);
-			if (e.ppbg) o = saturate01(o - OCT_FMA(e.ppbgWeight, ppbg[z], e.ppbgOffset));
+			float2 d = v[r];
+			if constexpr (FPN) d = csub(d, meanLine[z]);
+			const float pw = OCT_FMA(d.x, d.x, d.y * d.y);
+			float o = LOG ? OCT_FMA(OCT_LG2(pw), sA, sB) : OCT_FMA(OCT_SQRT(pw), sA, sB);
+			if constexpr (PPBG) o = saturate01(o - OCT_FMA(bw, ppbg[z], bo));
 			outLine[z] = o;
 		}
 	});
+}
+/* runtime flags -> one uniform branch per line instead of three per output */
+template <int K2LO>
+OCT_HD void epilogue_scaled(int lane, const float2 (&v)[32], const EpiConsts& e, const float2* meanLine,
+                            const float* ppbg, float* outLine) {
+	const int sel = (e.logMode ? 1 : 0) | (e.fpn ? 2 : 0) | (e.ppbg ? 4 : 0);
+	switch (sel) {
+	case 0: epilogue_scaled_t<K2LO, false, false, false>(lane, v, e, meanLine, ppbg, outLine); break;
+	case 1: epilogue_scaled_t<K2LO, true, false, false>(lane, v, e, meanLine, ppbg, outLine); break;
+	case 2: epilogue_scaled_t<K2LO, false, true, false>(lane, v, e, meanLine, ppbg, outLine); break;
+	case 3: epilogue_scaled_t<K2LO, true, true, false>(lane, v, e, meanLine, ppbg, outLine); break;
+	case 4: epilogue_scaled_t<K2LO, false, false, true>(lane, v, e, meanLine, ppbg, outLine); break;
+	case 5: epilogue_scaled_t<K2LO, true, false, true>(lane, v, e, meanLine, ppbg, outLine); break;
+	case 6: epilogue_scaled_t<K2LO, false, true, true>(lane, v, e, meanLine, ppbg, outLine); break;
+	default: epilogue_scaled_t<K2LO, true, true, true>(lane, v, e, meanLine, ppbg, outLine); break;
+	}
 }
 
 /* complex store of the same 16 bins (fixed-pattern-noise determination pre-pass) */

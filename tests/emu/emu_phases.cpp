@@ -63,6 +63,8 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 	build_combine_twiddles_2048(ctw);
 	EpiConsts e = make_epi_consts(N, logMode, gmin, gmax, coeff, addend);
 	e.fpn = meanLine != nullptr; e.ppbg = ppbg != nullptr; e.ppbgWeight = ppbgW; e.ppbgOffset = ppbgO;
+	/* cubic: the kernel mirrors f[-1] = f[1]; the caller's buffer has room in front of the line */
+	if (sa == SA_CUBIC) const_cast<float*>(fslot)[-1] = fslot[1];
 	static float2 regs[2][32][32];
 	std::vector<float2> tile[2] = { std::vector<float2>(XBUF_FLOAT2), std::vector<float2>(XBUF_FLOAT2) };
 	for (int p = 0; p < R; ++p) {
