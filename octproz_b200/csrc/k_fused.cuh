@@ -25,7 +25,7 @@ namespace octb200 {
 #define OCT_R1_THREADS 512
 #endif
 #ifndef OCT_R2_THREADS
-#define OCT_R2_THREADS 448
+#define OCT_R2_THREADS 384
 #endif
 template <int R> struct FusedCfg {
 	static constexpr int N = 1024 * R;

@@ -48,6 +48,24 @@ inline void build_stage_luts(int N, int R, const float* resample, const float* w
 	}
 }
 
+/* paired layout for the fused kernel (see stage_a): N float4s = [ P (N/2) | Q (N/2) ] */
+inline void build_stage_luts_paired(int N, int R, const float* resample, const float* window, const float2* phasor,
+                                    std::vector<float4>& out) {
+	StageLuts nat;
+	build_stage_luts(N, 1, resample, window, phasor, nat);      /* natural order: nat.B[m] = {off, wPx, wPy, t} */
+	out.assign((size_t)N, make_float4(0, 0, 0, 0));
+	const int half = N / 2;
+	for (int p = 0; p < R; ++p)
+		for (int jj = 0; jj < 16; ++jj)
+			for (int lane = 0; lane < 32; ++lane) {
+				const int sa = lane + 64 * jj, sb = sa + 32;               /* rows j = 2jj and 2jj+1 */
+				const float4 A = nat.B[(size_t)R * sa + p], B = nat.B[(size_t)R * sb + p];
+				const size_t idx = (size_t)p * 512 + lane + 32 * jj;
+				out[idx] = make_float4(A.y, A.z, B.y, B.z);
+				out[half + idx] = make_float4(A.x, B.x, A.w, B.w);
+			}
+}
+
 /* tw[k1*32+n2] = exp(+2 pi i k1 n2 / 1024): inter-pass twiddles of the 32x32 four-step transform */
 inline void build_twiddles_1024(std::vector<float2>& tw) {
 	tw.resize(1024);

@@ -93,9 +93,9 @@ OCT_HD float2 sample_cubic(const float* f, float4 B) {           /* cuda_code.cu
 	const float y = 0.5f * pos * (a * pos2 + b * pos + c) + y1;
 	return cscale(make_float2(B.y, B.z), y);
 }
-/* two samples at once: every polynomial step is one packed instruction for both */
-OCT_HD void sample_cubic_x2(const float* f, float4 Ba, float4 Bb, float2& outA, float2& outB) {
-	const int oa = lut_int(Ba.x), ob = lut_int(Bb.x);
+/* two samples at once: every polynomial step is one packed instruction for both.
+ * off = byte offsets of tap n1 of the two samples, pos = their fractional positions, wa/wb = window*phasor */
+OCT_HD void sample_cubic_x2(const float* f, int oa, int ob, float2 pos, float2 wa, float2 wb, float2& outA, float2& outB) {
 	const float2 Y0 = make_float2(ldf(f, oa - 4), ldf(f, ob - 4));
 	const float2 Y1 = make_float2(ldf(f, oa), ldf(f, ob));
 	const float2 Y2 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4));
@@ -103,20 +103,18 @@ OCT_HD void sample_cubic_x2(const float* f, float4 Ba, float4 Bb, float2& outA, 
 	const float2 a = pfma(csub(Y1, Y2), make_float2(3.0f, 3.0f), csub(Y3, Y0));                                /* -y0 + 3(y1-y2) + y3 */
 	const float2 b = pfma(Y0, make_float2(2.0f, 2.0f), pfma(Y1, make_float2(-5.0f, -5.0f), pfma(Y2, make_float2(4.0f, 4.0f), pneg(Y3))));
 	const float2 c = csub(Y2, Y0);
-	const float2 pos = make_float2(Ba.w, Bb.w);
 	const float2 pos2 = pmul(pos, pos);
 	const float2 inner = pfma(a, pos2, pfma(b, pos, c));
 	const float2 y = pfma(pmul(pos, make_float2(0.5f, 0.5f)), inner, Y1);
-	outA = cscale(make_float2(Ba.y, Ba.z), y.x);
-	outB = cscale(make_float2(Bb.y, Bb.z), y.y);
+	outA = cscale(wa, y.x);
+	outB = cscale(wb, y.y);
 }
-OCT_HD void sample_linear_x2(const float* f, float4 Ba, float4 Bb, float2& outA, float2& outB) {
-	const int oa = lut_int(Ba.x), ob = lut_int(Bb.x);
+OCT_HD void sample_linear_x2(const float* f, int oa, int ob, float2 pos, float2 wa, float2 wb, float2& outA, float2& outB) {
 	const float2 F0 = make_float2(ldf(f, oa), ldf(f, ob));
 	const float2 F1 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4));
-	const float2 y = pfma(csub(F1, F0), make_float2(Ba.w, Bb.w), F0);
-	outA = cscale(make_float2(Ba.y, Ba.z), y.x);
-	outB = cscale(make_float2(Bb.y, Bb.z), y.y);
+	const float2 y = pfma(csub(F1, F0), pos, F0);
+	outA = cscale(wa, y.x);
+	outB = cscale(wb, y.y);
 }
 
 OCT_HD float2 sample_none(const float* f, int m, float4 B) {
@@ -152,25 +150,29 @@ OCT_HD float2 sample_lanczos(const float* f, int shift, float4 B) {
 }
 
 /* ---- stage A for one lane: 32 samples s = lane + 32 j of sub-sequence p (m = R*s + p) ----
- * LUTs are stored de-interleaved: entry of sample m lives at (m % R) * (N/R) + m / R. */
+ * Fused-kernel LUT ("paired" layout, build_stage_luts_paired): rows j = 2jj and 2jj+1 of a lane share two float4s
+ *   P[p*512 + lane + 32 jj] = { wPx_a, wPy_a, wPx_b, wPy_b }        Q[...] = { off_a, off_b, t_a, t_b }
+ * so every packed operand (window*phasor of a sample, the two t's) is an aligned register pair straight out of LDS.128. */
 template <int SA, int R>
-OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lutB, float2 (&v)[32]) {
-	const int base = p * 1024;
-	if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
+OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lut, float2 (&v)[32]) {
+	const float4* P = lut + p * 512;
+	const float4* Q = lut + 512 * R + p * 512;
 #pragma unroll
-		for (int j = 0; j < 32; j += 2) {
-			const float4 Ba = lutB[base + lane + 32 * j];
-			const float4 Bb = lutB[base + lane + 32 * (j + 1)];
-			if constexpr (SA == SA_CUBIC) sample_cubic_x2(f, Ba, Bb, v[j], v[j + 1]);
-			else sample_linear_x2(f, Ba, Bb, v[j], v[j + 1]);
-		}
-	} else {
-#pragma unroll
-		for (int j = 0; j < 32; ++j) {
-			const int s = lane + 32 * j;
-			const float4 B = lutB[base + s];
-			if constexpr (SA == SA_NONE) v[j] = sample_none(f, R * s + p, B);
-			else v[j] = sample_lanczos(f, shift, B);
+	for (int jj = 0; jj < 16; ++jj) {
+		const float4 Pq = P[lane + 32 * jj];
+		const float4 Qq = Q[lane + 32 * jj];
+		const float2 wa = make_float2(Pq.x, Pq.y), wb = make_float2(Pq.z, Pq.w);
+		if constexpr (SA == SA_CUBIC) {
+			sample_cubic_x2(f, lut_int(Qq.x), lut_int(Qq.y), make_float2(Qq.z, Qq.w), wa, wb, v[2 * jj], v[2 * jj + 1]);
+		} else if constexpr (SA == SA_LINEAR) {
+			sample_linear_x2(f, lut_int(Qq.x), lut_int(Qq.y), make_float2(Qq.z, Qq.w), wa, wb, v[2 * jj], v[2 * jj + 1]);
+		} else if constexpr (SA == SA_NONE) {
+			const int s = lane + 64 * jj;
+			v[2 * jj] = cscale(wa, f[R * s + p]);
+			v[2 * jj + 1] = cscale(wb, f[R * (s + 32) + p]);
+		} else {
+			v[2 * jj] = sample_lanczos(f, shift, make_float4(Qq.x, Pq.x, Pq.y, Qq.z));
+			v[2 * jj + 1] = sample_lanczos(f, shift, make_float4(Qq.y, Pq.z, Pq.w, Qq.w));
 		}
 	}
 }

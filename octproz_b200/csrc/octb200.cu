@@ -185,8 +185,9 @@ int rebuild_luts(octb200_pipeline* p) {
 	const int interp = q.resamplingInterpolation;
 	StageLuts l;
 	if (p->N == 1024 || p->N == 2048) {
-		build_stage_luts(N, p->R, res, win, ph, l);
-		CK(p, cudaMemcpyAsync(p->dLutB, l.B.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
+		std::vector<float4> paired;
+		build_stage_luts_paired(N, p->R, res, win, ph, paired);
+		CK(p, cudaMemcpyAsync(p->dLutB, paired.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
 		CK(p, cudaStreamSynchronize(p->sCompute));
 	}
 	build_stage_luts(N, 1, res, win, ph, l);

@@ -55,9 +55,9 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
                               float* outLine /* N/2 */, float* cplxLine /* N/2 pairs or NULL */) {
 	const int R = N / 1024;
 	if (R != 1 && R != 2) return -1;
-	StageLuts luts;
+	std::vector<float4> lut;
 	(void)interp;
-	build_stage_luts(N, R, resample, window, reinterpret_cast<const float2*>(phasor), luts);
+	build_stage_luts_paired(N, R, resample, window, reinterpret_cast<const float2*>(phasor), lut);
 	std::vector<float2> tw, ctw;
 	build_twiddles_1024(tw);
 	build_combine_twiddles_2048(ctw);
@@ -70,7 +70,7 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 	for (int p = 0; p < R; ++p) {
 		for (int lane = 0; lane < 32; ++lane) {
 			float2 (&v)[32] = regs[p][lane];
-			const float4* B = luts.B.data();
+			const float4* B = lut.data();
 			if (sa == SA_CUBIC) { if (R == 1) stage_a<SA_CUBIC, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_CUBIC, 2>(lane, p, fslot, shift, B, v); }
 			else if (sa == SA_LINEAR) { if (R == 1) stage_a<SA_LINEAR, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_LINEAR, 2>(lane, p, fslot, shift, B, v); }
 			else if (sa == SA_NONE) { if (R == 1) stage_a<SA_NONE, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_NONE, 2>(lane, p, fslot, shift, B, v); }
