@@ -66,14 +66,21 @@ inline void build_stage_luts_paired(int N, int R, const float* resample, const f
 			}
 }
 
-/* tw[k1*32+n2] = exp(+2 pi i k1 n2 / 1024): inter-pass twiddles of the 32x32 four-step transform */
+/* inter-pass twiddles of the 32x32 four-step transform, factored (see exchange_store):
+ *   tw[a*32 + n2]       = exp(+2 pi i (4a) n2 / 1024), a = 0..7
+ *   tw[256 + b*32 + n2] = exp(+2 pi i   b  n2 / 1024), b = 0..3          (384 entries, array kept at 1024) */
 inline void build_twiddles_1024(std::vector<float2>& tw) {
-	tw.resize(1024);
-	for (int k1 = 0; k1 < 32; ++k1)
-		for (int n2 = 0; n2 < 32; ++n2) {
-			const double a = 2.0 * M_PI * (double)(k1 * n2) / 1024.0;
-			tw[k1 * 32 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
+	tw.assign(1024, make_float2(1.0f, 0.0f));
+	for (int n2 = 0; n2 < 32; ++n2) {
+		for (int a = 0; a < 8; ++a) {
+			const double ang = 2.0 * M_PI * (double)(4 * a * n2) / 1024.0;
+			tw[a * 32 + n2] = make_float2((float)std::cos(ang), (float)std::sin(ang));
 		}
+		for (int b = 0; b < 4; ++b) {
+			const double ang = 2.0 * M_PI * (double)(b * n2) / 1024.0;
+			tw[256 + b * 32 + n2] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+		}
+	}
 }
 /* ctw[k] = exp(+2 pi i k / 2048), k < 1024: radix-2 combine of the two interleaved 1024-point transforms */
 inline void build_combine_twiddles_2048(std::vector<float2>& ctw) {

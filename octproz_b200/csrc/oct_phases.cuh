@@ -178,14 +178,26 @@ OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lu
 }
 
 /* ---- four-step exchange: after pass 1, v[r] = V[k1 = bitrev5(r)] for column n2 = lane ----
- * multiply by w_1024^{k1*n2} (tw[k1*32+n2]) and store row-major [k1][n2]. */
+ * multiply by w_1024^{k1*n2} and store row-major [k1][n2].  Shared-memory bandwidth bounds this kernel, so the 31
+ * twiddles of a lane are not read one by one: k1 = 4a + b, w^{k1 n2} = A[a] * B[b] with A[a] = w^{4a n2} (a = 1..7) and
+ * B[b] = w^{b n2} (b = 1..3): 10 reads + 21 complex products.  tw layout: tw[a*32 + n2] = A[a], tw[256 + b*32 + n2] = B[b]. */
 OCT_HD void exchange_store(int lane, const float2 (&v)[32], float2* xbuf, const float2* tw) {
-	static_for<0, 32>([&](auto rc) {
-		constexpr int r = decltype(rc)::value;
-		constexpr int k1 = bitrev5(r);
-		float2 val = v[r];
-		if constexpr (k1 != 0) val = cmul(val, tw[k1 * 32 + lane]);
-		xbuf[k1 * XPITCH + lane] = val;
+	const float2 B1 = tw[256 + 32 + lane], B2 = tw[256 + 64 + lane], B3 = tw[256 + 96 + lane];
+	static_for<0, 8>([&](auto ac) {
+		constexpr int a = decltype(ac)::value;
+		float2 A = make_float2(1.0f, 0.0f);
+		if constexpr (a != 0) A = tw[a * 32 + lane];
+		static_for<0, 4>([&](auto bc) {
+			constexpr int b = decltype(bc)::value;
+			constexpr int k1 = 4 * a + b;
+			constexpr int r = bitrev5(k1);
+			float2 val = v[r];
+			if constexpr (a == 0 && b == 0) { /* w^0 */ }
+			else if constexpr (a == 0) val = cmul(val, b == 1 ? B1 : (b == 2 ? B2 : B3));
+			else if constexpr (b == 0) val = cmul(val, A);
+			else val = cmul(val, cmul(A, b == 1 ? B1 : (b == 2 ? B2 : B3)));
+			xbuf[k1 * XPITCH + lane] = val;
+		});
 	});
 }
 
