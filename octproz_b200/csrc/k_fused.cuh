@@ -18,9 +18,15 @@
  */
 #pragma once
 #include "oct_device.cuh"
+#include "oct_tmem.cuh"
 
 namespace octb200 {
 
+/* OCT_TMEM_LUT = 1: per-lane tables (stage LUT, twiddles, FPN line, background) live in tensor memory (oct_tmem.cuh)
+ * instead of shared memory; 0 keeps everything in shared memory (A/B builds, and the layout the CPU emulator models). */
+#ifndef OCT_TMEM_LUT
+#define OCT_TMEM_LUT 1
+#endif
 #ifndef OCT_R1_THREADS
 #define OCT_R1_THREADS 512
 #endif
@@ -45,11 +51,17 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll,
 	FusedSmem L;
 	int off = 0;
 	L.offW = off;
+#if OCT_TMEM_LUT
+	L.offB = off; L.offTw = off; L.offCtw = off; L.offMean = off; L.offPpbg = off;
+	off += 128;      /* TMEM base address word */
+	(void)H;
+#else
 	L.offB = off;    off += (src == SRC_RAW16) ? N * 16 : 0;
 	L.offTw = off;   off += 1024 * 8;
 	L.offCtw = off;  off += (R == 2) ? 1024 * 8 : 0;
 	L.offMean = off; off += H * 8;
 	L.offPpbg = off; off += H * 4;
+#endif
 	off = align_up(off, 128);
 	L.offGroups = off;
 	const int SE = HB + N + HA;
@@ -105,21 +117,33 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	const float2* sMean = reinterpret_cast<const float2*>(smem + L.offMean);
 	const float* sPpbg = reinterpret_cast<const float*>(smem + L.offPpbg);
 
-	/* ---- one-time table fill (all threads) ---- */
+	/* ---- one-time table fill ---- */
+#if OCT_TMEM_LUT
+	uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(smem + L.offW);
+	if (warp == 0) tmem_alloc(tmemBaseSlot, TmemMap<R>::ALLOC);
+	tmem_fence_before_sync();
+	__syncthreads();
+	tmem_fence_after_sync();
+	const uint32_t tmemBase = *tmemBaseSlot;
+	const uint32_t tq = tmemBase + ((uint32_t)(warp & 3) << 21);     /* lane quadrant of this warp: lane field = bits 31:16, 32 lanes per quadrant */
+	if (warp < 4) tmem_fill<R>(tq, lane, a, SRC == SRC_RAW16);
+	tmem_fence_before_sync();
+	__syncthreads();
+	tmem_fence_after_sync();
+#else
 	{
 		auto fill = [&](int off, const void* src, int bytes) {
 			const uint4* s = reinterpret_cast<const uint4*>(src);
 			uint4* d = reinterpret_cast<uint4*>(smem + off);
 			for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
 		};
-		if constexpr (SRC == SRC_RAW16) {
-			fill(L.offB, a.lutB, N * 16);
-		}
+		if constexpr (SRC == SRC_RAW16) fill(L.offB, a.lutB, N * 16);
 		fill(L.offTw, a.tw, 1024 * 8);
 		if constexpr (R == 2) fill(L.offCtw, a.ctw, 1024 * 8);
 		if (a.epi.fpn && a.cplxOut == nullptr) fill(L.offMean, a.meanLine, H * 8);
 		if (a.epi.ppbg) fill(L.offPpbg, a.ppbg, H * 4);
 	}
+#endif
 
 	unsigned char* gbase = smem + L.offGroups + grp * L.groupBytes;
 	/* ONE raw slot per group: it is free again as soon as the line has been converted to fp32, i.e. a full line time
@@ -215,7 +239,11 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 			const float* f = fslot + a.HB;
 			/* the reference clamps the Lanczos line offset to >= 8 (cuda_code.cu:313): line 0 of the buffer is read 8 samples late */
 			const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
+#if OCT_TMEM_LUT
+			stage_a_tmem<SA, R>(lane, p, f, shift, tq, v);
+#else
 			stage_a<SA, R>(lane, p, f, shift, sB, v);
+#endif
 			group_sync<R>(barId);          /* all gathers done before the exchange tile (aliasing the slot) is written */
 		} else {
 			const float2* in = a.cin + (size_t)gline * N;
@@ -225,14 +253,22 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 
 		/* ---- 1024-point inverse FFT of this warp's sub-sequence ---- */
 		fft32_inv_dif(v);
+#if OCT_TMEM_LUT
+		exchange_store_tmem<R>(lane, v, tile, tq);
+#else
 		exchange_store(lane, v, tile, sTw);
+#endif
 		__syncwarp();
 		exchange_load(lane, v, tile);
 		fft32_inv_dif(v);
 
 		if constexpr (R == 2) {
 			__syncwarp();                  /* own tile fully read before it is reused for the hand-over */
+#if OCT_TMEM_LUT
+			combine_store_tmem(lane, p, v, tile, tq);
+#else
 			combine_store(lane, p, v, tile, sCtw);
+#endif
 			group_sync<R>(barId);
 			combine_load(lane, p, v, partnerTile);
 		}
@@ -245,10 +281,19 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 			int b = gline / a.A, al = gline - b * a.A;
 			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u) al = a.A - 1 - al;
 			float* o = a.out + ((size_t)b * a.A + al) * H;
+#if OCT_TMEM_LUT
+			if (R == 1 || p == 0) epilogue_tmem<R, 0>(lane, v, a.epi, tq, o); else epilogue_tmem<R, 16>(lane, v, a.epi, tq, o);
+#else
 			if (R == 1 || p == 0) epilogue_scaled<0>(lane, v, a.epi, sMean, sPpbg, o); else epilogue_scaled<16>(lane, v, a.epi, sMean, sPpbg, o);
+#endif
 		}
 		group_sync<R>(barId);              /* tile / slot reads finished before the next line's conversion overwrites them */
 	}
+#if OCT_TMEM_LUT
+	tmem_fence_before_sync();
+	__syncthreads();
+	if (warp == 0) tmem_dealloc(tmemBase, TmemMap<R>::ALLOC);
+#endif
 }
 
 }  // namespace octb200
