@@ -56,7 +56,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll,
 	off += 128;      /* TMEM base address word */
 	(void)H;
 #else
-	L.offB = off;    off += (src == SRC_RAW16) ? N * 16 : 0;
+	L.offB = off;    off += (src == SRC_RAW16) ? 2 * N * 16 : 0;
 	L.offTw = off;   off += 1024 * 8;
 	L.offCtw = off;  off += (R == 2) ? 1024 * 8 : 0;
 	L.offMean = off; off += H * 8;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	tmem_fence_after_sync();
 	const uint32_t tmemBase = *tmemBaseSlot;
 	const uint32_t tq = tmemBase + ((uint32_t)(warp & 3) << 21);     /* lane quadrant of this warp: lane field = bits 31:16, 32 lanes per quadrant */
-	if (warp < 4) tmem_fill<R>(tq, lane, a, SRC == SRC_RAW16);
+	if (warp < 4) tmem_fill<R>(tq, warp, lane, a, SRC == SRC_RAW16);
 	tmem_fence_before_sync();
 	__syncthreads();
 	tmem_fence_after_sync();
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 			uint4* d = reinterpret_cast<uint4*>(smem + off);
 			for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
 		};
-		if constexpr (SRC == SRC_RAW16) fill(L.offB, a.lutB, N * 16);
+		if constexpr (SRC == SRC_RAW16) fill(L.offB, a.lutB, 2 * N * 16);
 		fill(L.offTw, a.tw, 1024 * 8);
 		if constexpr (R == 2) fill(L.offCtw, a.ctw, 1024 * 8);
 		if (a.epi.fpn && a.cplxOut == nullptr) fill(L.offMean, a.meanLine, H * 8);

@@ -15,6 +15,7 @@ cudaError_t launch_fused(int R, int sa, bool roll, int src, const FusedArgs& a, 
 
 void fused_launch_shape(int R, int sa, bool roll, int src, int HB, int HA, int smCount, int lines, int* grid, int* threads, int* smem) {
 	if (src == SRC_CPLX) { sa = SA_NONE; roll = false; }
+	if (sa == SA_LINEAR) sa = SA_CUBIC;
 	const int groups = fused_pick_groups(R, sa, roll, src, HB, HA);
 	const FusedSmem L = fused_smem_layout(R, sa, roll, src, HB, HA, groups > 0 ? groups : 1);
 	int g = smCount; const int mg = groups > 0 ? (lines + groups - 1) / groups : 1;

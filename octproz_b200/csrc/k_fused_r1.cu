@@ -2,8 +2,7 @@
 #include "k_fused_launch.cuh"
 namespace octb200 {
 cudaError_t launch_fused_raw_r1(int sa, bool roll, const FusedArgs& a, int smCount, cudaStream_t st) {
-	if (sa == SA_CUBIC) return roll ? launch_fused_t<1, SA_CUBIC, true, SRC_RAW16>(a, smCount, st) : launch_fused_t<1, SA_CUBIC, false, SRC_RAW16>(a, smCount, st);
-	if (sa == SA_LINEAR) return roll ? launch_fused_t<1, SA_LINEAR, true, SRC_RAW16>(a, smCount, st) : launch_fused_t<1, SA_LINEAR, false, SRC_RAW16>(a, smCount, st);
+	if (sa == SA_CUBIC || sa == SA_LINEAR) return   /* linear = the same 4-tap kernel with weights (0, 1-t, t, 0) */ roll ? launch_fused_t<1, SA_CUBIC, true, SRC_RAW16>(a, smCount, st) : launch_fused_t<1, SA_CUBIC, false, SRC_RAW16>(a, smCount, st);
 	if (sa == SA_NONE) return roll ? launch_fused_t<1, SA_NONE, true, SRC_RAW16>(a, smCount, st) : launch_fused_t<1, SA_NONE, false, SRC_RAW16>(a, smCount, st);
 	return roll ? launch_fused_t<1, SA_LANCZOS, true, SRC_RAW16>(a, smCount, st) : launch_fused_t<1, SA_LANCZOS, false, SRC_RAW16>(a, smCount, st);
 }

@@ -48,39 +48,50 @@ inline void build_stage_luts(int N, int R, const float* resample, const float* w
 	}
 }
 
-/* paired layout for the fused kernel (see stage_a): N float4s = [ P (N/2) | Q (N/2) ] */
-inline void build_stage_luts_paired(int N, int R, const float* resample, const float* window, const float2* phasor,
+/* tap weights of the 4-tap interpolators for fractional position t (double precision, rounded once):
+ * interp 1 = Catmull-Rom, the per-tap expansion of cuda_code.cu:263-270; otherwise linear (cuda_code.cu:229) */
+inline void tap_weights(int interp, float tf, float (&w)[4]) {
+	const double t = (double)tf;
+	if (interp == 1) {
+		w[0] = (float)(0.5 * (-t * t * t + 2.0 * t * t - t));
+		w[1] = (float)(0.5 * (3.0 * t * t * t - 5.0 * t * t + 2.0));
+		w[2] = (float)(0.5 * (-3.0 * t * t * t + 4.0 * t * t + t));
+		w[3] = (float)(0.5 * (t * t * t - t * t));
+	} else {
+		w[0] = 0.0f; w[1] = (float)(1.0 - t); w[2] = (float)t; w[3] = 0.0f;
+	}
+}
+
+/* paired layout for the fused kernel (see stage_a): 2N float4s = four planes [ P | Q | W01 | W23 ] of N/2 entries */
+inline void build_stage_luts_paired(int N, int R, int interp, const float* resample, const float* window, const float2* phasor,
                                     std::vector<float4>& out) {
 	StageLuts nat;
 	build_stage_luts(N, 1, resample, window, phasor, nat);      /* natural order: nat.B[m] = {off, wPx, wPy, t} */
-	out.assign((size_t)N, make_float4(0, 0, 0, 0));
+	out.assign((size_t)2 * N, make_float4(0, 0, 0, 0));
 	const int half = N / 2;
 	for (int p = 0; p < R; ++p)
 		for (int jj = 0; jj < 16; ++jj)
 			for (int lane = 0; lane < 32; ++lane) {
 				const int sa = lane + 64 * jj, sb = sa + 32;               /* rows j = 2jj and 2jj+1 */
 				const float4 A = nat.B[(size_t)R * sa + p], B = nat.B[(size_t)R * sb + p];
+				float wa[4], wb[4];
+				tap_weights(interp, A.w, wa); tap_weights(interp, B.w, wb);
 				const size_t idx = (size_t)p * 512 + lane + 32 * jj;
 				out[idx] = make_float4(A.y, A.z, B.y, B.z);
 				out[half + idx] = make_float4(A.x, B.x, A.w, B.w);
+				out[2 * half + idx] = make_float4(wa[0], wb[0], wa[1], wb[1]);
+				out[3 * half + idx] = make_float4(wa[2], wb[2], wa[3], wb[3]);
 			}
 }
 
-/* inter-pass twiddles of the 32x32 four-step transform, factored (see exchange_store):
- *   tw[a*32 + n2]       = exp(+2 pi i (4a) n2 / 1024), a = 0..7
- *   tw[256 + b*32 + n2] = exp(+2 pi i   b  n2 / 1024), b = 0..3          (384 entries, array kept at 1024) */
+/* tw[k1*32+n2] = exp(+2 pi i k1 n2 / 1024): inter-pass twiddles of the 32x32 four-step transform */
 inline void build_twiddles_1024(std::vector<float2>& tw) {
-	tw.assign(1024, make_float2(1.0f, 0.0f));
-	for (int n2 = 0; n2 < 32; ++n2) {
-		for (int a = 0; a < 8; ++a) {
-			const double ang = 2.0 * M_PI * (double)(4 * a * n2) / 1024.0;
-			tw[a * 32 + n2] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+	tw.resize(1024);
+	for (int k1 = 0; k1 < 32; ++k1)
+		for (int n2 = 0; n2 < 32; ++n2) {
+			const double a = 2.0 * M_PI * (double)(k1 * n2) / 1024.0;
+			tw[k1 * 32 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
 		}
-		for (int b = 0; b < 4; ++b) {
-			const double ang = 2.0 * M_PI * (double)(b * n2) / 1024.0;
-			tw[256 + b * 32 + n2] = make_float2((float)std::cos(ang), (float)std::sin(ang));
-		}
-	}
 }
 /* ctw[k] = exp(+2 pi i k / 2048), k < 1024: radix-2 combine of the two interleaved 1024-point transforms */
 inline void build_combine_twiddles_2048(std::vector<float2>& ctw) {

@@ -93,26 +93,17 @@ OCT_HD float2 sample_cubic(const float* f, float4 B) {           /* cuda_code.cu
 	const float y = 0.5f * pos * (a * pos2 + b * pos + c) + y1;
 	return cscale(make_float2(B.y, B.z), y);
 }
-/* two samples at once: every polynomial step is one packed instruction for both.
- * off = byte offsets of tap n1 of the two samples, pos = their fractional positions, wa/wb = window*phasor */
-OCT_HD void sample_cubic_x2(const float* f, int oa, int ob, float2 pos, float2 wa, float2 wb, float2& outA, float2& outB) {
+/* two samples at once, tap-weight form: y = sum_k w_k x[n1-1+k] with the four weights of BOTH samples precomputed per lane
+ * (they are the same for every A-scan): linear (cuda_code.cu:229: 0, 1-t, t, 0) or Catmull-Rom (cuda_code.cu:258-271 expanded per
+ * tap).  4 packed instructions for two samples instead of 12 for the Horner form -- the fp32 pipe bounds this kernel.
+ * oa/ob = byte offsets of tap n1 of the two samples, W[k] = (w_k of sample a, w_k of sample b), wa/wb = window*phasor. */
+OCT_HD void sample_taps4_x2(const float* f, int oa, int ob, float2 W0, float2 W1, float2 W2, float2 W3, float2 wa, float2 wb,
+                            float2& outA, float2& outB) {
 	const float2 Y0 = make_float2(ldf(f, oa - 4), ldf(f, ob - 4));
 	const float2 Y1 = make_float2(ldf(f, oa), ldf(f, ob));
 	const float2 Y2 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4));
 	const float2 Y3 = make_float2(ldf(f, oa + 8), ldf(f, ob + 8));
-	const float2 a = pfma(csub(Y1, Y2), make_float2(3.0f, 3.0f), csub(Y3, Y0));                                /* -y0 + 3(y1-y2) + y3 */
-	const float2 b = pfma(Y0, make_float2(2.0f, 2.0f), pfma(Y1, make_float2(-5.0f, -5.0f), pfma(Y2, make_float2(4.0f, 4.0f), pneg(Y3))));
-	const float2 c = csub(Y2, Y0);
-	const float2 pos2 = pmul(pos, pos);
-	const float2 inner = pfma(a, pos2, pfma(b, pos, c));
-	const float2 y = pfma(pmul(pos, make_float2(0.5f, 0.5f)), inner, Y1);
-	outA = cscale(wa, y.x);
-	outB = cscale(wb, y.y);
-}
-OCT_HD void sample_linear_x2(const float* f, int oa, int ob, float2 pos, float2 wa, float2 wb, float2& outA, float2& outB) {
-	const float2 F0 = make_float2(ldf(f, oa), ldf(f, ob));
-	const float2 F1 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4));
-	const float2 y = pfma(csub(F1, F0), pos, F0);
+	const float2 y = pfma(W3, Y3, pfma(W2, Y2, pfma(W1, Y1, pmul(W0, Y0))));
 	outA = cscale(wa, y.x);
 	outB = cscale(wb, y.y);
 }
@@ -150,22 +141,26 @@ OCT_HD float2 sample_lanczos(const float* f, int shift, float4 B) {
 }
 
 /* ---- stage A for one lane: 32 samples s = lane + 32 j of sub-sequence p (m = R*s + p) ----
- * Fused-kernel LUT ("paired" layout, build_stage_luts_paired): rows j = 2jj and 2jj+1 of a lane share two float4s
- *   P[p*512 + lane + 32 jj] = { wPx_a, wPy_a, wPx_b, wPy_b }        Q[...] = { off_a, off_b, t_a, t_b }
- * so every packed operand (window*phasor of a sample, the two t's) is an aligned register pair straight out of LDS.128. */
+ * LUT ("paired" layout, build_stage_luts_paired): rows j = 2jj and 2jj+1 of a lane share four float4s, stored as four planes
+ * of N/2 entries, entry e = p*512 + lane + 32 jj:
+ *   P[e] = { wPx_a, wPy_a, wPx_b, wPy_b }   Q[e] = { off_a, off_b, t_a, t_b }   W01[e] = { w0a, w0b, w1a, w1b }   W23[e] = { w2a, w2b, w3a, w3b }
+ * so every packed operand is an aligned register pair straight out of a 128-bit read. */
 template <int SA, int R>
 OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lut, float2 (&v)[32]) {
+	constexpr int HN = 512 * R;
 	const float4* P = lut + p * 512;
-	const float4* Q = lut + 512 * R + p * 512;
+	const float4* Q = lut + HN + p * 512;
+	const float4* W01 = lut + 2 * HN + p * 512;
+	const float4* W23 = lut + 3 * HN + p * 512;
 #pragma unroll
 	for (int jj = 0; jj < 16; ++jj) {
 		const float4 Pq = P[lane + 32 * jj];
 		const float4 Qq = Q[lane + 32 * jj];
 		const float2 wa = make_float2(Pq.x, Pq.y), wb = make_float2(Pq.z, Pq.w);
-		if constexpr (SA == SA_CUBIC) {
-			sample_cubic_x2(f, lut_int(Qq.x), lut_int(Qq.y), make_float2(Qq.z, Qq.w), wa, wb, v[2 * jj], v[2 * jj + 1]);
-		} else if constexpr (SA == SA_LINEAR) {
-			sample_linear_x2(f, lut_int(Qq.x), lut_int(Qq.y), make_float2(Qq.z, Qq.w), wa, wb, v[2 * jj], v[2 * jj + 1]);
+		if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
+			const float4 Wa = W01[lane + 32 * jj], Wb = W23[lane + 32 * jj];
+			sample_taps4_x2(f, lut_int(Qq.x), lut_int(Qq.y), make_float2(Wa.x, Wa.y), make_float2(Wa.z, Wa.w),
+			                make_float2(Wb.x, Wb.y), make_float2(Wb.z, Wb.w), wa, wb, v[2 * jj], v[2 * jj + 1]);
 		} else if constexpr (SA == SA_NONE) {
 			const int s = lane + 64 * jj;
 			v[2 * jj] = cscale(wa, f[R * s + p]);
@@ -178,26 +173,14 @@ OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lu
 }
 
 /* ---- four-step exchange: after pass 1, v[r] = V[k1 = bitrev5(r)] for column n2 = lane ----
- * multiply by w_1024^{k1*n2} and store row-major [k1][n2].  Shared-memory bandwidth bounds this kernel, so the 31
- * twiddles of a lane are not read one by one: k1 = 4a + b, w^{k1 n2} = A[a] * B[b] with A[a] = w^{4a n2} (a = 1..7) and
- * B[b] = w^{b n2} (b = 1..3): 10 reads + 21 complex products.  tw layout: tw[a*32 + n2] = A[a], tw[256 + b*32 + n2] = B[b]. */
+ * multiply by w_1024^{k1*n2} (tw[k1*32+n2]) and store row-major [k1][n2]. */
 OCT_HD void exchange_store(int lane, const float2 (&v)[32], float2* xbuf, const float2* tw) {
-	const float2 B1 = tw[256 + 32 + lane], B2 = tw[256 + 64 + lane], B3 = tw[256 + 96 + lane];
-	static_for<0, 8>([&](auto ac) {
-		constexpr int a = decltype(ac)::value;
-		float2 A = make_float2(1.0f, 0.0f);
-		if constexpr (a != 0) A = tw[a * 32 + lane];
-		static_for<0, 4>([&](auto bc) {
-			constexpr int b = decltype(bc)::value;
-			constexpr int k1 = 4 * a + b;
-			constexpr int r = bitrev5(k1);
-			float2 val = v[r];
-			if constexpr (a == 0 && b == 0) { /* w^0 */ }
-			else if constexpr (a == 0) val = cmul(val, b == 1 ? B1 : (b == 2 ? B2 : B3));
-			else if constexpr (b == 0) val = cmul(val, A);
-			else val = cmul(val, cmul(A, b == 1 ? B1 : (b == 2 ? B2 : B3)));
-			xbuf[k1 * XPITCH + lane] = val;
-		});
+	static_for<0, 32>([&](auto rc) {
+		constexpr int r = decltype(rc)::value;
+		constexpr int k1 = bitrev5(r);
+		float2 val = v[r];
+		if constexpr (k1 != 0) val = cmul(val, tw[k1 * 32 + lane]);
+		xbuf[k1 * XPITCH + lane] = val;
 	});
 }
 

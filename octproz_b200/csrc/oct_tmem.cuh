@@ -9,11 +9,12 @@
  * image into each of the four lane quadrants, warp w reads quadrant w % 4), read per line with tcgen05.ld.
  * No tensor-core MMA is involved -- TMEM is used as what it physically is, a big lane-private register-file extension.
  *
- * Column map (R = N/1024 warps per line):
- *   R = 1: [0,128) stage LUT (16 row pairs x {P quad, Q quad})  [128,148) twiddles [A1 B1][A2 A3][A4 A5][A6 A7][B2 B3]  [148,180) FPN mean (16 cplx)
- *          [180,196) background (16 floats)                                               -> 256 columns allocated
- *   R = 2: [0,256) stage LUT of p=0,1  [256,276) twiddles  [276,340) combine twiddles (32 cplx)  [340,404) mean (2 x 16 cplx)
- *          [404,436) background (2 x 16)                                                   -> 512 columns allocated
+ * Column map of one lane quadrant (512 columns allocated):
+ *   [0,256)   stage LUT: 16 row pairs x 16 words { off_a off_b w0a w0b w1a w1b t_a t_b | w2a w2b w3a w3b wP_a wP_b }
+ *   [256,320) inter-pass twiddles w^{k1 lane}, k1 = 0..31 (32 complex)
+ *   [320,384) R = 2 only: combine twiddles w_2048^{lane + 32 k2}, k2 = 0..31
+ *   MEAN      FPN mean line, 16 complex of the bins this warp finalises     PPBG  background, 16 floats
+ * For R = 2 (two warps per line, p = warp % 2) a quadrant holds only the tables of its own p (quadrant = warp % 4 -> p = quadrant & 1).
  */
 #pragma once
 #include "oct_device.cuh"
@@ -21,8 +22,9 @@
 namespace octb200 {
 
 template <int R> struct TmemMap;
-template <> struct TmemMap<1> { static constexpr int LUT = 0, TW = 128, CTW = 148, MEAN = 148, PPBG = 180, ALLOC = 256; };
-template <> struct TmemMap<2> { static constexpr int LUT = 0, TW = 256, CTW = 276, MEAN = 340, PPBG = 404, ALLOC = 512; };
+/* per lane quadrant; for R = 2 a quadrant only holds the tables of ITS sub-sequence p = quadrant & 1 (warp w: p = w % 2, quadrant w % 4) */
+template <> struct TmemMap<1> { static constexpr int LUT = 0, TW = 256, CTW = 320, MEAN = 320, PPBG = 352, ALLOC = 512; };
+template <> struct TmemMap<2> { static constexpr int LUT = 0, TW = 256, CTW = 320, MEAN = 384, PPBG = 416, ALLOC = 512; };
 
 /* ---- raw tcgen05 wrappers (SASS: LDTM / STTM / UTCALLOC) ---- */
 __device__ __forceinline__ void tmem_alloc(uint32_t* smemResult, int cols) {
@@ -53,6 +55,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
 	asm volatile("tcgen05.wait::ld.sync.aligned;"
 	             : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]) :: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+	             : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+	               "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]) : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+	             : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+	               "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]) :: "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&r)[4]) {
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(taddr));
 	asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]) :: "memory");
@@ -63,111 +73,109 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, float (&r)[2]) {
 }
 
 /* ---- fill: warp q (< 4) writes the image of lane `lane` into quadrant q ---- */
+__device__ __forceinline__ void tmem_st_f4(uint32_t taddr, float4 a) {
+	const uint32_t r[4] = { __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w) };
+	tmem_st4(taddr, r);
+}
 template <int R>
-__device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int lane, const FusedArgs& a, bool haveLut) {
+__device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int quadrant, int lane, const FusedArgs& a, bool haveLut) {
 	using M = TmemMap<R>;
-	constexpr int N = 1024 * R, H = N / 2;
+	constexpr int HN = 512 * R;
+	const int p = (R == 2) ? (quadrant & 1) : 0;         /* the sub-sequence whose warps read this quadrant */
 	if (haveLut) {
-		const float4* P = a.lutB;
-		const float4* Q = a.lutB + H;
-		for (int p = 0; p < R; ++p)
-			for (int jj = 0; jj < 16; ++jj) {
-				const float4 Pq = __ldg(P + p * 512 + lane + 32 * jj), Qq = __ldg(Q + p * 512 + lane + 32 * jj);
-				const uint32_t r[8] = { __float_as_uint(Pq.x), __float_as_uint(Pq.y), __float_as_uint(Pq.z), __float_as_uint(Pq.w),
-				                        __float_as_uint(Qq.x), __float_as_uint(Qq.y), __float_as_uint(Qq.z), __float_as_uint(Qq.w) };
-				tmem_st8(tq + M::LUT + p * 128 + 8 * jj, r);
-			}
-	}
-	{   /* twiddles (oct_luts.hpp build_twiddles_1024) in the order [A1 B1][A2 A3][A4 A5][A6 A7][B2 B3]: 20 columns, 5 x4 stores */
-		float2 t[10];
-		t[0] = __ldg(a.tw + 1 * 32 + lane); t[1] = __ldg(a.tw + 256 + 1 * 32 + lane);
-		for (int i = 2; i < 8; ++i) t[i] = __ldg(a.tw + i * 32 + lane);
-		t[8] = __ldg(a.tw + 256 + 2 * 32 + lane); t[9] = __ldg(a.tw + 256 + 3 * 32 + lane);
-		for (int c = 0; c < 5; ++c) {
-			const uint32_t r[4] = { __float_as_uint(t[2 * c].x), __float_as_uint(t[2 * c].y), __float_as_uint(t[2 * c + 1].x), __float_as_uint(t[2 * c + 1].y) };
-			tmem_st4(tq + M::TW + 4 * c, r);
+		for (int jj = 0; jj < 16; ++jj) {
+			const int e = p * 512 + lane + 32 * jj;
+			const float4 Pq = __ldg(a.lutB + e), Qq = __ldg(a.lutB + HN + e), W01 = __ldg(a.lutB + 2 * HN + e), W23 = __ldg(a.lutB + 3 * HN + e);
+			/* row = [ off_a off_b w0a w0b | w1a w1b t_a t_b || w2a w2b w3a w3b | wPa wPb ]: two x8 reads, the second one late */
+			tmem_st_f4(tq + M::LUT + 16 * jj + 0, make_float4(Qq.x, Qq.y, W01.x, W01.y));
+			tmem_st_f4(tq + M::LUT + 16 * jj + 4, make_float4(W01.z, W01.w, Qq.z, Qq.w));
+			tmem_st_f4(tq + M::LUT + 16 * jj + 8, W23);
+			tmem_st_f4(tq + M::LUT + 16 * jj + 12, Pq);
 		}
+	}
+	for (int k1 = 0; k1 < 32; k1 += 2) {
+		const float2 t0 = __ldg(a.tw + k1 * 32 + lane), t1 = __ldg(a.tw + (k1 + 1) * 32 + lane);
+		tmem_st_f4(tq + M::TW + 2 * k1, make_float4(t0.x, t0.y, t1.x, t1.y));
 	}
 	if constexpr (R == 2) {
 		for (int k2 = 0; k2 < 32; k2 += 2) {
 			const float2 c0 = __ldg(a.ctw + lane + 32 * k2), c1 = __ldg(a.ctw + lane + 32 * (k2 + 1));
-			const uint32_t r[4] = { __float_as_uint(c0.x), __float_as_uint(c0.y), __float_as_uint(c1.x), __float_as_uint(c1.y) };
-			tmem_st4(tq + M::CTW + 2 * k2, r);
+			tmem_st_f4(tq + M::CTW + 2 * k2, make_float4(c0.x, c0.y, c1.x, c1.y));
 		}
 	}
+	const int k2lo = 16 * p;                              /* bins lane + 32 k2, k2 in [16p, 16p+16) are finalised by the warps of p */
 	if (a.epi.fpn && a.cplxOut == nullptr) {
-		for (int k2 = 0; k2 < 16 * R; k2 += 2) {
-			const float2 m0 = __ldg(a.meanLine + lane + 32 * k2), m1 = __ldg(a.meanLine + lane + 32 * (k2 + 1));
-			const uint32_t r[4] = { __float_as_uint(m0.x), __float_as_uint(m0.y), __float_as_uint(m1.x), __float_as_uint(m1.y) };
-			tmem_st4(tq + M::MEAN + 2 * k2, r);
+		for (int i = 0; i < 16; i += 2) {
+			const float2 m0 = __ldg(a.meanLine + lane + 32 * (k2lo + i)), m1 = __ldg(a.meanLine + lane + 32 * (k2lo + i + 1));
+			tmem_st_f4(tq + M::MEAN + 2 * i, make_float4(m0.x, m0.y, m1.x, m1.y));
 		}
 	}
 	if (a.epi.ppbg) {
-		for (int k2 = 0; k2 < 16 * R; k2 += 4) {
-			uint32_t r[4];
-			for (int i = 0; i < 4; ++i) r[i] = __float_as_uint(__ldg(a.ppbg + lane + 32 * (k2 + i)));
-			tmem_st4(tq + M::PPBG + k2, r);
-		}
+		for (int i = 0; i < 16; i += 4)
+			tmem_st_f4(tq + M::PPBG + i, make_float4(__ldg(a.ppbg + lane + 32 * (k2lo + i)), __ldg(a.ppbg + lane + 32 * (k2lo + i + 1)),
+			                                         __ldg(a.ppbg + lane + 32 * (k2lo + i + 2)), __ldg(a.ppbg + lane + 32 * (k2lo + i + 3))));
 	}
 	tmem_wait_st();
 }
 
-/* ---- stage A from TMEM (same arithmetic as stage_a in oct_phases.cuh) ---- */
+/* ---- stage A from TMEM (same arithmetic as stage_a in oct_phases.cuh): two x8 reads per row pair ---- */
 template <int SA, int R>
 __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, int shift, uint32_t tq, float2 (&v)[32]) {
 	using M = TmemMap<R>;
-	const uint32_t base = tq + M::LUT + p * 128;
 #pragma unroll
 	for (int jj = 0; jj < 16; ++jj) {
+		if constexpr ((SA == SA_CUBIC || SA == SA_LINEAR) && R == 2) {
+			/* 168 registers per thread are available at R = 2 (6 line groups): one wide read */
+			float q[16];
+			tmem_ld16(tq + M::LUT + 16 * jj, q);
+			sample_taps4_x2(f, __float_as_int(q[0]), __float_as_int(q[1]), make_float2(q[2], q[3]), make_float2(q[4], q[5]),
+			                make_float2(q[8], q[9]), make_float2(q[10], q[11]), make_float2(q[12], q[13]), make_float2(q[14], q[15]),
+			                v[2 * jj], v[2 * jj + 1]);
+			continue;
+		}
 		float q[8];
-		tmem_ld8(base + 8 * jj, q);
-		const float2 wa = make_float2(q[0], q[1]), wb = make_float2(q[2], q[3]);
-		if constexpr (SA == SA_CUBIC) {
-			sample_cubic_x2(f, __float_as_int(q[4]), __float_as_int(q[5]), make_float2(q[6], q[7]), wa, wb, v[2 * jj], v[2 * jj + 1]);
-		} else if constexpr (SA == SA_LINEAR) {
-			sample_linear_x2(f, __float_as_int(q[4]), __float_as_int(q[5]), make_float2(q[6], q[7]), wa, wb, v[2 * jj], v[2 * jj + 1]);
-		} else if constexpr (SA == SA_NONE) {
-			const int s = lane + 64 * jj;
-			v[2 * jj] = cscale(wa, f[R * s + p]);
-			v[2 * jj + 1] = cscale(wb, f[R * (s + 32) + p]);
+		tmem_ld8(tq + M::LUT + 16 * jj, q);                 /* off_a off_b w0a w0b w1a w1b t_a t_b */
+		if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
+			const int oa = __float_as_int(q[0]), ob = __float_as_int(q[1]);
+			float2 y = pmul(make_float2(q[2], q[3]), make_float2(ldf(f, oa - 4), ldf(f, ob - 4)));
+			y = pfma(make_float2(q[4], q[5]), make_float2(ldf(f, oa), ldf(f, ob)), y);
+			const float2 Y2 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4)), Y3 = make_float2(ldf(f, oa + 8), ldf(f, ob + 8));
+			float w[8];
+			tmem_ld8(tq + M::LUT + 16 * jj + 8, w);         /* w2a w2b w3a w3b wPa.x wPa.y wPb.x wPb.y */
+			y = pfma(make_float2(w[2], w[3]), Y3, pfma(make_float2(w[0], w[1]), Y2, y));
+			v[2 * jj] = cscale(make_float2(w[4], w[5]), y.x);
+			v[2 * jj + 1] = cscale(make_float2(w[6], w[7]), y.y);
 		} else {
-			v[2 * jj] = sample_lanczos(f, shift, make_float4(q[4], q[0], q[1], q[6]));
-			v[2 * jj + 1] = sample_lanczos(f, shift, make_float4(q[5], q[2], q[3], q[7]));
+			float w[8];
+			tmem_ld8(tq + M::LUT + 16 * jj + 8, w);
+			const float2 wa = make_float2(w[4], w[5]), wb = make_float2(w[6], w[7]);
+			if constexpr (SA == SA_NONE) {
+				const int s = lane + 64 * jj;
+				v[2 * jj] = cscale(wa, f[R * s + p]);
+				v[2 * jj + 1] = cscale(wb, f[R * (s + 32) + p]);
+			} else {
+				v[2 * jj] = sample_lanczos(f, shift, make_float4(q[0], wa.x, wa.y, q[6]));
+				v[2 * jj + 1] = sample_lanczos(f, shift, make_float4(q[1], wb.x, wb.y, q[7]));
+			}
 		}
 	}
 }
 
-/* ---- inter-pass twiddle + transpose store, twiddles from TMEM (cf. exchange_store) ----
- * TMEM twiddle columns (pairs of complex per x4 read): [A1 B1] [A2 A3] [A4 A5] [A6 A7] [B2 B3] */
+/* ---- inter-pass twiddle + transpose store, twiddles from TMEM (cf. exchange_store): w^{k1 lane} at columns TW + 2 k1 ---- */
 template <int R>
 __device__ __forceinline__ void exchange_store_tmem(int lane, const float2 (&v)[32], float2* xbuf, uint32_t tq) {
 	using M = TmemMap<R>;
-	float cb[4];
-	tmem_ld4(tq + M::TW + 16, cb);
-	const float2 B2 = make_float2(cb[0], cb[1]), B3 = make_float2(cb[2], cb[3]);
-	float2 B1 = make_float2(1.0f, 0.0f);
-	static_for<0, 4>([&](auto hc) {
-		constexpr int h = decltype(hc)::value;          /* a = 2h, 2h+1 */
-		float c[4];
-		tmem_ld4(tq + M::TW + 4 * h, c);
-		float2 Aeven, Aodd;
-		if constexpr (h == 0) { Aeven = make_float2(1.0f, 0.0f); Aodd = make_float2(c[0], c[1]); B1 = make_float2(c[2], c[3]); }
-		else { Aeven = make_float2(c[0], c[1]); Aodd = make_float2(c[2], c[3]); }
-		static_for<0, 2>([&](auto ec) {
-			constexpr int e = decltype(ec)::value;
-			constexpr int aIdx = 2 * h + e;
-			const float2 A = e == 0 ? Aeven : Aodd;
-			static_for<0, 4>([&](auto bc) {
-				constexpr int b = decltype(bc)::value;
-				constexpr int k1 = 4 * aIdx + b;
-				constexpr int r = bitrev5(k1);
-				float2 val = v[r];
-				if constexpr (aIdx == 0 && b == 0) { }
-				else if constexpr (aIdx == 0) val = cmul(val, b == 1 ? B1 : (b == 2 ? B2 : B3));
-				else if constexpr (b == 0) val = cmul(val, A);
-				else val = cmul(val, cmul(A, b == 1 ? B1 : (b == 2 ? B2 : B3)));
-				xbuf[k1 * XPITCH + lane] = val;
-			});
+	static_for<0, 8>([&](auto cc) {
+		constexpr int c = decltype(cc)::value;            /* k1 = 4c .. 4c+3 */
+		float t[8];
+		tmem_ld8(tq + M::TW + 8 * c, t);
+		static_for<0, 4>([&](auto ic) {
+			constexpr int i = decltype(ic)::value;
+			constexpr int k1 = 4 * c + i;
+			constexpr int r = bitrev5(k1);
+			float2 val = v[r];
+			if constexpr (k1 != 0) val = cmul(val, make_float2(t[2 * i], t[2 * i + 1]));
+			xbuf[k1 * XPITCH + lane] = val;
 		});
 	});
 }
@@ -197,8 +205,8 @@ __device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32],
 	static_for<0, 4>([&](auto gc) {
 		constexpr int g = decltype(gc)::value;           /* four bins per TMEM read: k2 = K2LO + 4g .. +3 */
 		float m[8], bgv[4];
-		if constexpr (FPN) tmem_ld8(tq + M::MEAN + 2 * (K2LO + 4 * g), m);
-		if constexpr (PPBG) tmem_ld4(tq + M::PPBG + (K2LO + 4 * g), bgv);
+		if constexpr (FPN) tmem_ld8(tq + M::MEAN + 8 * g, m);
+		if constexpr (PPBG) tmem_ld4(tq + M::PPBG + 4 * g, bgv);
 		static_for<0, 4>([&](auto ic) {
 			constexpr int i = decltype(ic)::value;
 			constexpr int k2 = K2LO + 4 * g + i;

@@ -186,8 +186,8 @@ int rebuild_luts(octb200_pipeline* p) {
 	StageLuts l;
 	if (p->N == 1024 || p->N == 2048) {
 		std::vector<float4> paired;
-		build_stage_luts_paired(N, p->R, res, win, ph, paired);
-		CK(p, cudaMemcpyAsync(p->dLutB, paired.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
+		build_stage_luts_paired(N, p->R, interp == OCTB200_INTERP_CUBIC ? 1 : 0, res, win, ph, paired);
+		CK(p, cudaMemcpyAsync(p->dLutB, paired.data(), sizeof(float4) * 2 * N, cudaMemcpyHostToDevice, p->sCompute));
 		CK(p, cudaStreamSynchronize(p->sCompute));
 	}
 	build_stage_luts(N, 1, res, win, ph, l);
@@ -443,7 +443,7 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	RCC(dalloc(p, &p->dPpbg, (size_t)p->H));
 	RCC(dalloc(p, &p->dPhase, (size_t)p->N));
 	RCC(dalloc(p, &p->dPhasor, (size_t)p->N));
-	RCC(dalloc(p, &p->dLutB, (size_t)p->N)); RCC(dalloc(p, &p->dLutB1, (size_t)p->N));
+	RCC(dalloc(p, &p->dLutB, (size_t)2 * p->N)); RCC(dalloc(p, &p->dLutB1, (size_t)p->N));
 	RCC(dalloc(p, &p->dTw, (size_t)1024)); RCC(dalloc(p, &p->dCtw, (size_t)1024));
 	RCC(dalloc(p, &p->dSinCurve, (size_t)p->A));
 	{

@@ -56,8 +56,7 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 	const int R = N / 1024;
 	if (R != 1 && R != 2) return -1;
 	std::vector<float4> lut;
-	(void)interp;
-	build_stage_luts_paired(N, R, resample, window, reinterpret_cast<const float2*>(phasor), lut);
+	build_stage_luts_paired(N, R, interp, resample, window, reinterpret_cast<const float2*>(phasor), lut);
 	std::vector<float2> tw, ctw;
 	build_twiddles_1024(tw);
 	build_combine_twiddles_2048(ctw);
