@@ -259,7 +259,9 @@ def main():
 
     # ---- dominant kernel alone (roofline): events around back-to-back launches of the fused kernel ----
     kern_ms = p.time_kernel(d_raw[1], 20)
-    alg_bytes = ascans_per_step * n * 4                  # 2 B in + 2 B out per raw sample
+    # algorithmic bytes of the timed kernel per raw sample: fused = 2 B in + 2 B out; the split path's FFT kernel reads
+    # the float2 FFT input (8 B) and writes 2 B; the cuFFT path's pre kernel reads 2 B and writes 8 B
+    alg_bytes = ascans_per_step * n * {"fused": 4, "split": 10, "cufft": 10}[args.mode]
     peak, peak_src = hbm_peak()
     traffic = None
     try:
