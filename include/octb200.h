@@ -192,6 +192,27 @@ OCTB200_API int octb200_volume_u8(octb200_pipeline* p, uint32_t bufferNrInVolume
 /* replaces floatToOutput (cuda_code.cu:943-967): saturate * (2^bits-1) into a device container array */
 OCTB200_API int octb200_float_to_output(octb200_pipeline* p, uint32_t bufferNrInVolume, void* d_out);
 
+/* ---------- multi-GPU: en-face frame of a B-scan-sharded volume, gathered over peer memory ----------
+   The en-face view is the one product that needs every shard.  The reference has no multi-GPU path; what
+   this replaces is "updateDisplayedEnFaceFrame per rank (cuda_code.cu:884-912) + one ncclAllGather": ONE kernel extracts
+   each A-scan's en-face value and stores it directly into the frame window of every rank (P2P stores over NVLink), then
+   publishes a per-rank sequence flag.  One process per GPU; the 64-byte handles are exchanged by the host
+   (torch.distributed all_gather in octproz_b200/sharding.py).
+     init    : allocate this rank's window for a volume of `globalLines` A-scans, this shard starting at line `lineOffset`
+               (= first B-scan of the shard * ascansPerBscan); returns the window's IPC handle in handleOut[64]
+     connect : handles = world * 64 bytes, rank-major; opens every peer window
+     gather  : enqueue extraction + peer stores + flag publication on the compute stream (double-buffered by sequence number:
+               a frame stays valid until the second-next gather)
+     wait    : enqueue, on the compute stream, the wait for the latest sequence number of ALL ranks; *dFrame = device pointer
+               of the assembled frame [globalLines] floats, reference order disp[(E-1)-i]
+     close   : release (collective in spirit: call after a barrier, peers must have stopped gathering) */
+#define OCTB200_IPC_HANDLE_BYTES 64
+OCTB200_API int octb200_enface_gather_init(octb200_pipeline* p, int rank, int world, uint32_t globalLines, uint32_t lineOffset, void* handleOut);
+OCTB200_API int octb200_enface_gather_connect(octb200_pipeline* p, const void* handles);
+OCTB200_API int octb200_enface_gather(octb200_pipeline* p, uint32_t frameNr, uint32_t displayFunctionFrames, int displayFunction);
+OCTB200_API int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame);
+OCTB200_API int octb200_enface_gather_close(octb200_pipeline* p);
+
 /* ---------- timing helpers (CUDA events on the pipeline's compute stream) ---------- */
 OCTB200_API void* octb200_compute_stream(octb200_pipeline* p);           /* cudaStream_t as void* */
 OCTB200_API int octb200_event_record(octb200_pipeline* p, int slot);     /* slot 0..7 */

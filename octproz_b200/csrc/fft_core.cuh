@@ -153,4 +153,83 @@ OCT_HD void fft32_inv_dif(float2 (&v)[32]) {
 	});
 }
 
+/* tan(2 pi k / 32), k = 0..15 (k = 8 is never used: w = i is handled as a swizzle) */
+template <int K> struct T32 {
+	static constexpr float t[16] = {
+		0.0f, 0.19891236737965800691f, 0.41421356237309504880f, 0.66817863791929891999f,
+		1.0f, 1.49660576266548901380f, 2.41421356237309504880f, 5.02733949212584810451f,
+		0.0f, -5.02733949212584810451f, -2.41421356237309504880f, -1.49660576266548901380f,
+		-1.0f, -0.66817863791929891999f, -0.41421356237309504880f, -0.19891236737965800691f };
+	static constexpr float v = t[K];
+};
+
+/*
+ * Decimation-in-time butterfly with the twiddle folded into fused multiply-adds (Linzer-Feig form):
+ *   w b = cos * (b + tan * i b),   a' = a + w b,   b' = a - w b
+ * is 3 packed FFMA2 (6 scalar FMAs) instead of the 4 packed instructions of "multiply, then add/subtract".
+ * The rounding error of the scaled form is bounded by eps |b| because cos * tan = sin <= 1.
+ */
+template <int IDX>
+OCT_HD void bf_dit(float2& a, float2& b) {
+	if constexpr (IDX == 0) {
+		const float2 x = a, y = b;
+		a = cadd(x, y);
+		b = csub(x, y);
+	} else if constexpr (IDX == 8) {
+		const float2 x = a, y = cmul_i(b);
+		a = cadd(x, y);
+		b = csub(x, y);
+	} else if constexpr (IDX == 4 || IDX == 12) {
+		constexpr float h = 0.70710678118654752440f;
+		const float2 x = a;
+		const float2 u = (IDX == 4) ? cadd(b, cmul_i(b)) : csub(cmul_i(b), b);     /* (1 + i) b  or  (-1 + i) b */
+		a = pfma(u, make_float2(h, h), x);
+		b = pfma(u, make_float2(-h, -h), x);
+	} else {
+		constexpr float c = W32<IDX>::re, t = T32<IDX>::v;
+		const float2 x = a;
+		const float2 u = pfma(make_float2(t, t), cmul_i(b), b);
+		a = pfma(u, make_float2(c, c), x);
+		b = pfma(u, make_float2(-c, -c), x);
+	}
+}
+
+constexpr int bitrev_n(int g, int bits) {
+	int r = 0;
+	for (int i = 0; i < bits; ++i) r |= ((g >> i) & 1) << (bits - 1 - i);
+	return r;
+}
+
+/*
+ * In-place radix-2 decimation-in-time inverse DFT of 32 complex registers, natural-order input:
+ * stage s pairs the registers that differ in index bit 4 - s; the twiddle w_32^{(16 >> s) rev_s(g)} depends only on the
+ * already transformed top s index bits g and multiplies the upper-index element before the butterfly.
+ * Input  v[j] = x[j],  output v[r] = X[bitrev5(r)]  (same maps as fft32_inv_dif).
+ * Unused outputs (the pruned upper half of the spectrum) are removed by dead-code elimination.
+ */
+OCT_HD void fft32_inv_dit(float2 (&v)[32]) {
+	static_for<0, 5>([&](auto sc) {
+		constexpr int s = decltype(sc)::value;
+		constexpr int half = 16 >> s;
+		static_for<0, (1 << s)>([&](auto gc) {
+			constexpr int g = decltype(gc)::value;
+			constexpr int idx = (16 >> s) * bitrev_n(g, s);
+			static_for<0, half>([&](auto kc) {
+				constexpr int k = decltype(kc)::value;
+				constexpr int i0 = g * 2 * half + k;
+				bf_dit<idx>(v[i0], v[i0 + half]);
+			});
+		});
+	});
+}
+
+/* the network the kernels use (OCT_FFT_DIF selects the plain multiply-then-butterfly form for A/B builds) */
+OCT_HD void fft32_inv(float2 (&v)[32]) {
+#ifdef OCT_FFT_DIF
+	fft32_inv_dif(v);
+#else
+	fft32_inv_dit(v);
+#endif
+}
+
 }  // namespace octb200

@@ -347,6 +347,60 @@ cudaError_t launch_enface_frame(float* disp, const float* vol, unsigned W, unsig
 	return cudaGetLastError();
 }
 
+/* ---- en-face extraction fused with its all-gather over peer memory (multi-GPU shards) ----
+ * Same per-line arithmetic as enface_frame_kernel (cuda_code.cu:884-912); instead of a local frame + ncclAllGather every
+ * value is stored straight into the frame window of EVERY rank (P2P stores over NVLink / NVSwitch; the own rank is a plain
+ * store).  The last CTA to finish publishes `seq` in each rank's flag word for this rank (release, system scope); readers
+ * wait with enface_wait_kernel (acquire, system scope). */
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+__global__ void __launch_bounds__(256) enface_gather_kernel(const EnfaceGatherArgs a) {
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < a.E) {
+		float val;
+		if (a.nFrames > 1) {
+			if (a.fn == 0) {
+				int cnt = 0; float sum = 0.f;
+				for (unsigned j = 0; j < a.nFrames; ++j) { const unsigned f = a.frameNr + j; if (f < a.W) { sum += a.vol[f + (size_t)i * a.W]; ++cnt; } }
+				val = __fdividef(sum, (float)cnt);
+			} else {
+				float mx = 0.f;
+				for (unsigned j = 0; j < a.nFrames; ++j) { const unsigned f = a.frameNr + j; if (f < a.W) { const float v = a.vol[f + (size_t)i * a.W]; if (mx < v) mx = v; } }
+				val = mx;
+			}
+		} else {
+			val = a.vol[a.frameNr + (size_t)i * a.W];
+		}
+		const unsigned dst = (a.Eglobal - 1u) - (a.offset + i);         /* the reference writes the frame reversed (cuda_code.cu:909) */
+#pragma unroll 1
+		for (int r = 0; r < a.world; ++r) a.frames[r][dst] = val;
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned done = atomicAdd(a.counter, 1u);
+		if (done == gridDim.x - 1) {
+			*a.counter = 0;                                             /* next launch is stream ordered behind this one */
+			__threadfence_system();
+			for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, a.seq);
+		}
+	}
+}
+__global__ void enface_wait_kernel(const unsigned* flags, int world, unsigned seq) {
+	if ((int)threadIdx.x < world) {
+		while ((int)(ld_acquire_sys(flags + threadIdx.x) - seq) < 0) __nanosleep(200);
+	}
+}
+cudaError_t launch_enface_gather(const EnfaceGatherArgs& a, cudaStream_t st) {
+	enface_gather_kernel<<<(a.E + 255) / 256, 256, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_enface_wait(const unsigned* flags, int world, unsigned seq, cudaStream_t st) {
+	enface_wait_kernel<<<1, 32, 0, st>>>(flags, world, seq);
+	return cudaGetLastError();
+}
+
 /* u8 voxels in the layout of the GL_R8 3-D texture (x = A-scan, y = B-scan in volume, z flipped depth), cuda_code.cu:928-940 */
 __global__ void __launch_bounds__(256) volume_u8_kernel(uint8_t* __restrict__ tex, const float* __restrict__ buf, long long samples,
                                                          unsigned bufferNr, unsigned B, unsigned A, unsigned Btot, unsigned depth) {

@@ -32,6 +32,22 @@ struct PostArgs {
 	unsigned bscanBase;
 };
 
+/* en-face extraction + all-gather over peer memory */
+constexpr int OCT_MAX_PEERS = 16;
+struct EnfaceGatherArgs {
+	float* frames[OCT_MAX_PEERS];      /* this sequence number's frame window of every rank (peer-mapped device pointers) */
+	unsigned* flags[OCT_MAX_PEERS];    /* flag words of every rank; word [rank] is written by this rank */
+	const float* vol;
+	unsigned* counter;                 /* local CTA completion counter (zero between launches) */
+	unsigned W, E;                     /* depth bins per line, local lines */
+	unsigned frameNr, nFrames; int fn;
+	unsigned Eglobal, offset;          /* lines of the whole (sharded) volume, first line of this shard */
+	int world, rank;
+	unsigned seq;
+};
+cudaError_t launch_enface_gather(const EnfaceGatherArgs& a, cudaStream_t st);
+cudaError_t launch_enface_wait(const unsigned* flags, int world, unsigned seq, cudaStream_t st);
+
 void launch_fill_phase(float2* ph, const float* phase, int n, cudaStream_t st);
 cudaError_t launch_pre(const PreArgs& a, int rawBytes, int sa, bool roll, int smCount, cudaStream_t st);
 cudaError_t launch_post(const PostArgs& a, int smCount, cudaStream_t st);

@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	constexpr int H = N / 2;
 	extern __shared__ __align__(128) unsigned char smem[];
 
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	/* the warp index through a shuffle: tells the compiler it is warp-uniform, so the line bookkeeping (group, line number,
+	 * slot / barrier addresses, loop counter) lives in uniform registers instead of competing with the 64 FFT registers */
+	const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 	const int groupsPerCta = (blockDim.x >> 5) / R;
 	const int grp = warp / R;          /* line group within the CTA */
 	const int p = warp % R;            /* warp within the group = sub-sequence parity */
@@ -188,12 +190,18 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 				float4* f4 = reinterpret_cast<float4*>(fslot);
 				const unsigned sh = (unsigned)a.shiftBits;
 				const unsigned msk = (0xFFFFu >> sh) * 0x00010001u;
-#pragma unroll 4
-				for (int q4 = tig; q4 < SE / 4; q4 += 32 * R) {
-					const uint2 w = s2[q4];
+				auto cvt = [&](uint2 w) {
 					const unsigned wx = (w.x >> sh) & msk, wy = (w.y >> sh) & msk;
-					f4[q4] = make_float4(u16lo_to_float(wx), u16hi_to_float(wx), u16lo_to_float(wy), u16hi_to_float(wy));
-				}
+					return make_float4(u16lo_to_float(wx), u16hi_to_float(wx), u16lo_to_float(wy), u16hi_to_float(wy));
+				};
+				/* first N samples of the slot: 8 quads per thread, all loads in flight before the first conversion */
+				uint2 w8[8];
+#pragma unroll
+				for (int i = 0; i < 8; ++i) w8[i] = s2[tig + 32 * R * i];
+#pragma unroll
+				for (int i = 0; i < 8; ++i) f4[tig + 32 * R * i] = cvt(w8[i]);
+				/* the remaining HB + HA halo samples (Lanczos only) */
+				for (int q4 = N / 4 + tig; q4 < SE / 4; q4 += 32 * R) f4[q4] = cvt(s2[q4]);
 				if constexpr (SA == SA_CUBIC && !ROLL) {
 					/* mirrored first tap of the cubic: f[-1] = f[1] (cuda_code.cu:284) */
 					if (tig == 0) fslot[a.HB - 1] = (float)(reinterpret_cast<const uint16_t*>(slot)[a.HB + 1] >> sh);
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 		}
 
 		/* ---- 1024-point inverse FFT of this warp's sub-sequence ---- */
-		fft32_inv_dif(v);
+		fft32_inv(v);
 #if OCT_TMEM_LUT
 		exchange_store_tmem<R>(lane, v, tile, tq);
 #else
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 #endif
 		__syncwarp();
 		exchange_load(lane, v, tile);
-		fft32_inv_dif(v);
+		fft32_inv(v);
 
 		if constexpr (R == 2) {
 			__syncwarp();                  /* own tile fully read before it is reused for the hand-over */

@@ -63,6 +63,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
 	             : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
 	               "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]) :: "memory");
 }
+/* split issue / wait: the read of the NEXT table row is in flight while the current row is being used.  The wait names the
+ * destination registers as read-write operands, so every consumer is ordered behind it; nothing may touch them in between. */
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&r)[16]) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+	             : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+	               "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_wait(float (&r)[16]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+	             : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+	               "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]) :: "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&r)[4]) {
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(taddr));
 	asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]) :: "memory");
@@ -122,6 +134,24 @@ __device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int q
 template <int SA, int R>
 __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, int shift, uint32_t tq, float2 (&v)[32]) {
 	using M = TmemMap<R>;
+#ifndef OCT_STAGEA_UNPIPELINED
+	if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
+		/* software pipelined: row pair jj+1 is being read from tensor memory while row pair jj is gathered and evaluated */
+		float q[2][16];
+		tmem_ld16_issue(tq + M::LUT, q[0]);
+		tmem_ld16_wait(q[0]);
+		static_for<0, 16>([&](auto jc) {
+			constexpr int jj = decltype(jc)::value;
+			constexpr int c = jj & 1;
+			if constexpr (jj < 15) tmem_ld16_issue(tq + M::LUT + 16 * (jj + 1), q[c ^ 1]);
+			sample_taps4_x2(f, __float_as_int(q[c][0]), __float_as_int(q[c][1]), make_float2(q[c][2], q[c][3]), make_float2(q[c][4], q[c][5]),
+			                make_float2(q[c][8], q[c][9]), make_float2(q[c][10], q[c][11]), make_float2(q[c][12], q[c][13]),
+			                make_float2(q[c][14], q[c][15]), v[2 * jj], v[2 * jj + 1]);
+			if constexpr (jj < 15) tmem_ld16_wait(q[c ^ 1]);
+		});
+		return;
+	}
+#endif
 #pragma unroll
 	for (int jj = 0; jj < 16; ++jj) {
 		if constexpr ((SA == SA_CUBIC || SA == SA_LINEAR) && R == 2) {

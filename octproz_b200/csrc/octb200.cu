@@ -100,6 +100,18 @@ struct octb200_pipeline {
 	void *hostFloat[2] = { nullptr, nullptr }; size_t hostFloatBytes = 0; bool hostFloatRegistered = false; bool hostFloatMine[2] = { false, false };
 	octb200_host_callback cbStreaming = nullptr, cbFloat = nullptr, cbBackground = nullptr;
 	unsigned long long launches = 0;
+
+	/* en-face gather over peer memory (multi-GPU shards): local window = [64 flag words][frame 0][frame 1] */
+	struct EnfaceGather {
+		int world = 0, rank = 0;
+		unsigned Eglobal = 0, offset = 0, seq = 0;
+		unsigned char* window = nullptr;
+		size_t frameStride = 0;
+		unsigned char* peerBase[OCT_MAX_PEERS] = {};
+		bool opened[OCT_MAX_PEERS] = {};
+		bool connected = false;
+		unsigned* counter = nullptr;
+	} eg;
 };
 
 namespace {
@@ -484,6 +496,7 @@ int octb200_destroy(octb200_pipeline* p) {
 	dfree(p->dPhase); dfree(p->dPhasor); dfree(p->dLutB); dfree(p->dLutB1);
 	dfree(p->dTw); dfree(p->dCtw); dfree(p->dSinCurve);
 	for (void*& c : p->dOutConv) { if (c) cudaFree(c); c = nullptr; }
+	octb200_enface_gather_close(p);
 	if (p->sCompute) cudaStreamDestroy(p->sCompute);
 	if (p->sH2D) cudaStreamDestroy(p->sH2D);
 	if (p->sD2H) cudaStreamDestroy(p->sD2H);
@@ -723,6 +736,81 @@ int octb200_float_to_output(octb200_pipeline* p, uint32_t nr, void* dOut) {
 	if (!p || !dOut || nr >= (uint32_t)p->V) return fail(p, OCTB200_ERR_INVALID, "bad argument");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	CK(p, launch_float_to_output(dOut, p->dVolume + (size_t)(p->S / 2) * nr, (int)p->cfg.bitDepth, p->S / 2, p->smCount, p->sCompute)); p->launches++;
+	return OCTB200_OK;
+}
+
+/* ---------- en-face gather over peer memory ---------- */
+int octb200_enface_gather_init(octb200_pipeline* p, int rank, int world, uint32_t globalLines, uint32_t lineOffset, void* handleOut) {
+	if (!p || !handleOut || world < 1 || world > OCT_MAX_PEERS || rank < 0 || rank >= world) return fail(p, OCTB200_ERR_INVALID, "bad rank/world (at most %d ranks)", OCT_MAX_PEERS);
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	const unsigned E = (unsigned)(p->A * p->B * p->V);
+	if ((unsigned long long)lineOffset + E > globalLines) return fail(p, OCTB200_ERR_INVALID, "shard [%u, %u) exceeds the %u lines of the volume", lineOffset, lineOffset + E, globalLines);
+	octb200_enface_gather_close(p);
+	auto& g = p->eg;
+	g.world = world; g.rank = rank; g.Eglobal = globalLines; g.offset = lineOffset; g.seq = 0;
+	g.frameStride = ((size_t)globalLines * sizeof(float) + 255) / 256 * 256;
+	{ int rc = dalloc(p, &g.window, 256 + 2 * g.frameStride); if (rc) return rc; }
+	{ int rc = dalloc(p, &g.counter, 1); if (rc) return rc; }
+	cudaIpcMemHandle_t h;
+	CK(p, cudaIpcGetMemHandle(&h, g.window));
+	static_assert(sizeof(h) == OCTB200_IPC_HANDLE_BYTES, "ipc handle size");
+	std::memcpy(handleOut, &h, sizeof(h));
+	g.peerBase[rank] = g.window;
+	return OCTB200_OK;
+}
+int octb200_enface_gather_connect(octb200_pipeline* p, const void* handles) {
+	if (!p || !handles || !p->eg.window) return fail(p, OCTB200_ERR_INVALID, "enface_gather_init first");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	auto& g = p->eg;
+	for (int r = 0; r < g.world; ++r) {
+		if (r == g.rank || g.opened[r]) continue;
+		cudaIpcMemHandle_t h;
+		std::memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * OCTB200_IPC_HANDLE_BYTES, sizeof(h));
+		void* base = nullptr;
+		CK(p, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+		g.peerBase[r] = static_cast<unsigned char*>(base); g.opened[r] = true;
+	}
+	g.connected = true;
+	return OCTB200_OK;
+}
+int octb200_enface_gather(octb200_pipeline* p, uint32_t frameNr, uint32_t nFrames, int fn) {
+	if (!p || !p->eg.connected) return fail(p, OCTB200_ERR_NOT_READY, "en-face gather is not connected");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	auto& g = p->eg;
+	if (frameNr >= (unsigned)p->H) frameNr = 0;                      /* cuda_code.cu:1302 */
+	EnfaceGatherArgs a{};
+	g.seq++;
+	for (int r = 0; r < g.world; ++r) {
+		a.frames[r] = reinterpret_cast<float*>(g.peerBase[r] + 256 + (size_t)(g.seq & 1u) * g.frameStride);
+		a.flags[r] = reinterpret_cast<unsigned*>(g.peerBase[r]);
+	}
+	a.vol = p->dVolume; a.counter = g.counter;
+	a.W = (unsigned)p->H; a.E = (unsigned)(p->A * p->B * p->V);
+	a.frameNr = frameNr; a.nFrames = nFrames; a.fn = fn;
+	a.Eglobal = g.Eglobal; a.offset = g.offset; a.world = g.world; a.rank = g.rank; a.seq = g.seq;
+	CK(p, launch_enface_gather(a, p->sCompute)); p->launches++;
+	return OCTB200_OK;
+}
+int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame) {
+	if (!p || !p->eg.connected || p->eg.seq == 0) return fail(p, OCTB200_ERR_NOT_READY, "no en-face gather issued");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	auto& g = p->eg;
+	CK(p, launch_enface_wait(reinterpret_cast<const unsigned*>(g.window), g.world, g.seq, p->sCompute)); p->launches++;
+	if (dFrame) *dFrame = reinterpret_cast<float*>(g.window + 256 + (size_t)(g.seq & 1u) * g.frameStride);
+	return OCTB200_OK;
+}
+int octb200_enface_gather_close(octb200_pipeline* p) {
+	if (!p) return OCTB200_ERR_INVALID;
+	auto& g = p->eg;
+	if (!g.window && !g.counter) return OCTB200_OK;
+	cudaSetDevice(p->device);
+	if (p->sCompute) cudaStreamSynchronize(p->sCompute);
+	for (int r = 0; r < OCT_MAX_PEERS; ++r) {
+		if (g.opened[r] && g.peerBase[r]) cudaIpcCloseMemHandle(g.peerBase[r]);
+		g.opened[r] = false; g.peerBase[r] = nullptr;
+	}
+	dfree(g.window); dfree(g.counter);
+	g.connected = false; g.world = 0; g.seq = 0;
 	return OCTB200_OK;
 }
 

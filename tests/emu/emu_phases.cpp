@@ -12,7 +12,7 @@ using namespace octb200;
 extern "C" int emu_fft32(const float* in, float* out) {
 	float2 v[32];
 	for (int i = 0; i < 32; ++i) v[i] = make_float2(in[2 * i], in[2 * i + 1]);
-	fft32_inv_dif(v);
+	fft32_inv(v);
 	for (int r = 0; r < 32; ++r) { out[2 * bitrev5(r)] = v[r].x; out[2 * bitrev5(r) + 1] = v[r].y; }
 	return 0;
 }
@@ -23,13 +23,13 @@ static void sub_fft_1024(const std::vector<float2>& x, std::vector<float2>& tile
 	for (int lane = 0; lane < 32; ++lane) {
 		float2 (&v)[32] = regs[lane];
 		for (int j = 0; j < 32; ++j) v[j] = x[lane + 32 * j];
-		fft32_inv_dif(v);
+		fft32_inv(v);
 		exchange_store(lane, v, tile.data(), tw.data());
 	}
 	for (int lane = 0; lane < 32; ++lane) {
 		float2 (&v)[32] = regs[lane];
 		exchange_load(lane, v, tile.data());
-		fft32_inv_dif(v);
+		fft32_inv(v);
 	}
 }
 
@@ -74,13 +74,13 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 			else if (sa == SA_LINEAR) { if (R == 1) stage_a<SA_LINEAR, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_LINEAR, 2>(lane, p, fslot, shift, B, v); }
 			else if (sa == SA_NONE) { if (R == 1) stage_a<SA_NONE, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_NONE, 2>(lane, p, fslot, shift, B, v); }
 			else { if (R == 1) stage_a<SA_LANCZOS, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_LANCZOS, 2>(lane, p, fslot, shift, B, v); }
-			fft32_inv_dif(v);
+			fft32_inv(v);
 			exchange_store(lane, v, tile[p].data(), tw.data());
 		}
 		for (int lane = 0; lane < 32; ++lane) {
 			float2 (&v)[32] = regs[p][lane];
 			exchange_load(lane, v, tile[p].data());
-			fft32_inv_dif(v);
+			fft32_inv(v);
 		}
 	}
 	const float2* mean = reinterpret_cast<const float2*>(meanLine);
