@@ -26,7 +26,10 @@ SYMBOLS = [
     "octb200_copy_output", "octb200_bind_output", "octb200_bscan_frame", "octb200_enface_frame",
     "octb200_volume_u8", "octb200_float_to_output", "octb200_compute_stream", "octb200_event_record",
     "octb200_event_elapsed_ms", "octb200_launch_count", "octb200_time_kernel",
+    "octb200_enface_gather_init", "octb200_enface_gather_connect", "octb200_enface_gather", "octb200_enface_gather_wait",
+    "octb200_enface_gather_close",
 ]
+IPC_HANDLE_BYTES = 64
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NOT_READY = 0, -1, -2, -3, -4
 FFT_AUTO, FFT_FUSED, FFT_SPLIT, FFT_CUFFT = 0, 1, 2, 3
@@ -114,5 +117,10 @@ def load() -> C.CDLL:
     lib.octb200_event_elapsed_ms.argtypes = [P, C.c_int, C.c_int, fp]
     lib.octb200_launch_count.argtypes = [P]; lib.octb200_launch_count.restype = C.c_uint64
     lib.octb200_time_kernel.argtypes = [P, C.c_void_p, C.c_int, fp]
+    lib.octb200_enface_gather_init.argtypes = [P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.octb200_enface_gather_connect.argtypes = [P, C.c_void_p]
+    lib.octb200_enface_gather.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int]
+    lib.octb200_enface_gather_wait.argtypes = [P, C.POINTER(C.c_void_p)]
+    lib.octb200_enface_gather_close.argtypes = [P]
     _lib = lib
     return lib

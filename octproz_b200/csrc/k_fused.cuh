@@ -27,6 +27,9 @@ namespace octb200 {
 #ifndef OCT_TMEM_LUT
 #define OCT_TMEM_LUT 1
 #endif
+#ifndef OCT_RT_HALO
+#define OCT_RT_HALO 0
+#endif
 #ifndef OCT_R1_THREADS
 #define OCT_R1_THREADS 512
 #endif
@@ -84,9 +87,15 @@ __device__ __forceinline__ void group_sync(int barId) {
 }
 
 /* one lane: start the asynchronous load of raw line `gline` (with halos) into `slot` */
-template <int R>
+template <int R, bool HALO>
 __device__ __forceinline__ void issue_line_load(const FusedArgs& a, int gline, unsigned char* slot, uint64_t* bar) {
 	constexpr int N = 1024 * R;
+	if constexpr (!HALO) {
+		/* no halo (every stage but Lanczos): one aligned copy of exactly the line, nothing to clip */
+		mbar_arrive_expect_tx(bar, (uint32_t)(N * 2));
+		bulk_g2s(slot, a.raw + (size_t)gline * N, (uint32_t)(N * 2), bar);
+		return;
+	}
 	const long long lo = (long long)gline * N - a.HB;
 	const long long hi = (long long)gline * N + N + a.HA;
 	const long long clo = lo < 0 ? 0 : lo;
@@ -102,6 +111,8 @@ template <int R, int SA, bool ROLL, int SRC>
 __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(const FusedArgs a) {
 	constexpr int N = 1024 * R;
 	constexpr int H = N / 2;
+	/* halos exist only for the 16-tap Lanczos stage: compile-time zero otherwise */
+	const int HBv = (SA == SA_LANCZOS || OCT_RT_HALO) ? a.HB : 0, HAv = (SA == SA_LANCZOS || OCT_RT_HALO) ? a.HA : 0;
 	extern __shared__ __align__(128) unsigned char smem[];
 
 	/* the warp index through a shuffle: tells the compiler it is warp-uniform, so the line bookkeeping (group, line number,
@@ -111,7 +122,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	const int grp = warp / R;          /* line group within the CTA */
 	const int p = warp % R;            /* warp within the group = sub-sequence parity */
 	const int tig = p * 32 + lane;     /* thread in group */
-	const FusedSmem L = fused_smem_layout(R, SA, ROLL, SRC, a.HB, a.HA, groupsPerCta);
+	const FusedSmem L = fused_smem_layout(R, SA, ROLL, SRC, HBv, HAv, groupsPerCta);
 
 	const float4* sB = reinterpret_cast<const float4*>(smem + L.offB);
 	const float2* sTw = reinterpret_cast<const float2*>(smem + L.offTw);
@@ -157,7 +168,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	float2* partnerTile = reinterpret_cast<float2*>(work) + (R == 2 ? (1 - p) : 0) * XBUF_FLOAT2;
 	const int barId = 1 + grp;
 
-	const int SE = a.HB + N + a.HA;
+	const int SE = HBv + N + HAv;
 	float* fslot = reinterpret_cast<float*>(work) + FSLOT_PAD;       /* slot element 0; FSLOT_PAD floats of head room */
 	unsigned* prefix = reinterpret_cast<unsigned*>(work + align_up((FSLOT_PAD + SE) * 4, 16));
 
@@ -169,7 +180,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	}
 	__syncthreads();
 	if constexpr (SRC == SRC_RAW16) {
-		if (tig == 0 && g0 < a.lines) issue_line_load<R>(a, g0, slot, bar);
+		if (tig == 0 && g0 < a.lines) issue_line_load<R, SA == SA_LANCZOS>(a, g0, slot, bar);
 	}
 
 #ifdef OCT_STAGGER_NS
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 				for (int q4 = N / 4 + tig; q4 < SE / 4; q4 += 32 * R) f4[q4] = cvt(s2[q4]);
 				if constexpr (SA == SA_CUBIC && !ROLL) {
 					/* mirrored first tap of the cubic: f[-1] = f[1] (cuda_code.cu:284) */
-					if (tig == 0) fslot[a.HB - 1] = (float)(reinterpret_cast<const uint16_t*>(slot)[a.HB + 1] >> sh);
+					if (tig == 0) fslot[HBv - 1] = (float)(reinterpret_cast<const uint16_t*>(slot)[HBv + 1] >> sh);
 				}
 			}
 			if constexpr (ROLL) {
@@ -225,26 +236,26 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 			}
 			group_sync<R>(barId);
 			/* raw slot consumed: refill it with the next line of this group */
-			if (tig == 0 && gline + G < a.lines) issue_line_load<R>(a, gline + G, slot, bar);
+			if (tig == 0 && gline + G < a.lines) issue_line_load<R, SA == SA_LANCZOS>(a, gline + G, slot, bar);
 			if constexpr (ROLL) {
 				const int W = a.W;
 				for (int q = tig; q < SE; q += 32 * R) {
 					int lo, hi;
-					if (q < a.HB) { lo = 0; hi = a.HB - 1; }
-					else if (q >= a.HB + N) { lo = a.HB + N; hi = SE - 1; }
-					else { lo = a.HB; hi = a.HB + N - 1; }
+					if (q < HBv) { lo = 0; hi = HBv - 1; }
+					else if (q >= HBv + N) { lo = HBv + N; hi = SE - 1; }
+					else { lo = HBv; hi = HBv + N - 1; }
 					const int s = max(lo, q - W + 1), e = min(hi, q + W);
 					const float mean = __fdividef((float)(prefix[e + 1] - prefix[s]), (float)(e - s + 1));
 					fslot[q] -= mean;
 				}
 				group_sync<R>(barId);
 				if constexpr (SA == SA_CUBIC) {
-					if (tig == 0) fslot[a.HB - 1] = fslot[a.HB + 1];
+					if (tig == 0) fslot[HBv - 1] = fslot[HBv + 1];
 					group_sync<R>(barId);
 				}
 			}
 
-			const float* f = fslot + a.HB;
+			const float* f = fslot + HBv;
 			/* the reference clamps the Lanczos line offset to >= 8 (cuda_code.cu:313): line 0 of the buffer is read 8 samples late */
 			const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
 #if OCT_TMEM_LUT

@@ -21,7 +21,9 @@ namespace octb200 {
 /* transcendental forms the reference gets from --use_fast_math (octproz/pri/cuda.pri:54): MUFU approximations */
 OCT_HD float oct_lg2(float x) {
 #if defined(__CUDA_ARCH__)
-	return __log2f(x);
+	/* lg2.approx.ftz: what the reference's log10f becomes under --use_fast_math (flush-to-zero included); the non-ftz
+	 * form costs three more instructions per output for a denormal rescale the reference does not do */
+	float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 #else
 	return log2f(x);
 #endif

@@ -75,6 +75,19 @@ __device__ __forceinline__ void tmem_ld16_wait(float (&r)[16]) {
 	             : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
 	               "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]) :: "memory");
 }
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, float (&r)[8]) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_wait(float (&r)[8]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+	             : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld8_wait2(float (&r)[8], float (&s)[8]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+	             : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+	               "+f"(s[0]), "+f"(s[1]), "+f"(s[2]), "+f"(s[3]), "+f"(s[4]), "+f"(s[5]), "+f"(s[6]), "+f"(s[7]) :: "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&r)[4]) {
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(taddr));
 	asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]) :: "memory");
@@ -134,8 +147,16 @@ __device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int q
 template <int SA, int R>
 __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, int shift, uint32_t tq, float2 (&v)[32]) {
 	using M = TmemMap<R>;
-#ifndef OCT_STAGEA_UNPIPELINED
-	if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
+	/* table-read schedule: R = 2 has 168 registers per thread (one x16 read per row pair, next row pair prefetched); R = 1 has 128
+	 * (two x8 reads per row pair, only the first half prefetched) -- x16 prefetch at 128 registers spills (ptxas), measured slower */
+#ifndef OCT_STAGEA_MODE_R1
+#define OCT_STAGEA_MODE_R1 3
+#endif
+#ifndef OCT_STAGEA_MODE_R2
+#define OCT_STAGEA_MODE_R2 2
+#endif
+	constexpr int MODE = (R == 1) ? OCT_STAGEA_MODE_R1 : OCT_STAGEA_MODE_R2;
+	if constexpr (MODE == 2 && (SA == SA_CUBIC || SA == SA_LINEAR)) {
 		/* software pipelined: row pair jj+1 is being read from tensor memory while row pair jj is gathered and evaluated */
 		float q[2][16];
 		tmem_ld16_issue(tq + M::LUT, q[0]);
@@ -151,7 +172,29 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 		});
 		return;
 	}
-#endif
+	if constexpr (MODE == 3 && (SA == SA_CUBIC || SA == SA_LINEAR)) {
+		/* two x8 reads per row pair; the first half of the NEXT row pair (tap offsets, first weights) is prefetched while the
+		 * current one is gathered; the second half (late weights, window x phasor) is read while the gathers are in flight */
+		float qa[2][8];
+		tmem_ld8_issue(tq + M::LUT, qa[0]);
+		tmem_ld8_wait(qa[0]);
+		static_for<0, 16>([&](auto jc) {
+			constexpr int jj = decltype(jc)::value;
+			constexpr int c = jj & 1;
+			const int oa = __float_as_int(qa[c][0]), ob = __float_as_int(qa[c][1]);
+			const float2 Y0 = make_float2(ldf(f, oa - 4), ldf(f, ob - 4)), Y1 = make_float2(ldf(f, oa), ldf(f, ob));
+			const float2 Y2 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4)), Y3 = make_float2(ldf(f, oa + 8), ldf(f, ob + 8));
+			float w[8];
+			tmem_ld8_issue(tq + M::LUT + 16 * jj + 8, w);
+			if constexpr (jj < 15) tmem_ld8_issue(tq + M::LUT + 16 * (jj + 1), qa[c ^ 1]);
+			float2 y = pfma(make_float2(qa[c][4], qa[c][5]), Y1, pmul(make_float2(qa[c][2], qa[c][3]), Y0));
+			if constexpr (jj < 15) tmem_ld8_wait2(w, qa[c ^ 1]); else tmem_ld8_wait(w);
+			y = pfma(make_float2(w[2], w[3]), Y3, pfma(make_float2(w[0], w[1]), Y2, y));
+			v[2 * jj] = cscale(make_float2(w[4], w[5]), y.x);
+			v[2 * jj + 1] = cscale(make_float2(w[6], w[7]), y.y);
+		});
+		return;
+	}
 #pragma unroll
 	for (int jj = 0; jj < 16; ++jj) {
 		if constexpr ((SA == SA_CUBIC || SA == SA_LINEAR) && R == 2) {
@@ -195,18 +238,23 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 template <int R>
 __device__ __forceinline__ void exchange_store_tmem(int lane, const float2 (&v)[32], float2* xbuf, uint32_t tq) {
 	using M = TmemMap<R>;
+	/* the twiddles of chunk c+1 are read from tensor memory while chunk c is multiplied and stored */
+	float t[2][8];
+	tmem_ld8_issue(tq + M::TW, t[0]);
+	tmem_ld8_wait(t[0]);
 	static_for<0, 8>([&](auto cc) {
 		constexpr int c = decltype(cc)::value;            /* k1 = 4c .. 4c+3 */
-		float t[8];
-		tmem_ld8(tq + M::TW + 8 * c, t);
+		constexpr int b = c & 1;
+		if constexpr (c < 7) tmem_ld8_issue(tq + M::TW + 8 * (c + 1), t[b ^ 1]);
 		static_for<0, 4>([&](auto ic) {
 			constexpr int i = decltype(ic)::value;
 			constexpr int k1 = 4 * c + i;
 			constexpr int r = bitrev5(k1);
 			float2 val = v[r];
-			if constexpr (k1 != 0) val = cmul(val, make_float2(t[2 * i], t[2 * i + 1]));
+			if constexpr (k1 != 0) val = cmul(val, make_float2(t[b][2 * i], t[b][2 * i + 1]));
 			xbuf[k1 * XPITCH + lane] = val;
 		});
+		if constexpr (c < 7) tmem_ld8_wait(t[b ^ 1]);
 	});
 }
 

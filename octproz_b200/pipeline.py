@@ -140,6 +140,30 @@ class OctPipeline:
     def changeDisplayedEnFaceFrame(self, frameNr: int, displayFunctionFrames: int, displayFunction: int, d_out) -> None:
         self._ck(self._lib.octb200_enface_frame(self._h, frameNr, displayFunctionFrames, displayFunction, _ptr(d_out)), "enface_frame")
 
+    # ------------------------------------------------------------------ multi-GPU en-face gather over peer memory (include/octb200.h)
+    def enface_gather_init(self, rank: int, world: int, global_lines: int, line_offset: int) -> bytes:
+        """allocate this rank's frame window; returns its 64-byte IPC handle (exchange with torch.distributed, then connect)"""
+        h = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        self._ck(self._lib.octb200_enface_gather_init(self._h, rank, world, global_lines, line_offset, h), "enface_gather_init")
+        return bytes(h)
+
+    def enface_gather_connect(self, handles: bytes) -> None:
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        self._ck(self._lib.octb200_enface_gather_connect(self._h, buf), "enface_gather_connect")
+
+    def enface_gather(self, frameNr: int, displayFunctionFrames: int, displayFunction: int) -> None:
+        """changeDisplayedEnFaceFrame of the whole sharded volume: extraction + P2P stores into every rank's frame, one kernel"""
+        self._ck(self._lib.octb200_enface_gather(self._h, frameNr, displayFunctionFrames, displayFunction), "enface_gather")
+
+    def enface_gather_wait(self) -> int:
+        """enqueue the wait for all ranks' slabs of the latest gather; returns the device address of the assembled frame"""
+        out = C.c_void_p()
+        self._ck(self._lib.octb200_enface_gather_wait(self._h, C.byref(out)), "enface_gather_wait")
+        return int(out.value or 0)
+
+    def enface_gather_close(self) -> None:
+        self._ck(self._lib.octb200_enface_gather_close(self._h), "enface_gather_close")
+
     # ------------------------------------------------------------------ results
     def output_ptr(self, buffer_nr: int = 0) -> int:
         return int(self._lib.octb200_output_device_ptr(self._h, buffer_nr) or 0)
