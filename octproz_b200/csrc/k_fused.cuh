@@ -139,7 +139,10 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	tmem_fence_after_sync();
 	const uint32_t tmemBase = *tmemBaseSlot;
 	const uint32_t tq = tmemBase + ((uint32_t)(warp & 3) << 21);     /* lane quadrant of this warp: lane field = bits 31:16, 32 lanes per quadrant */
-	if (warp < 4) tmem_fill<R>(tq, warp, lane, a, SRC == SRC_RAW16);
+	{
+		const int nWarps = blockDim.x >> 5, quadrant = warp & 3;
+		tmem_fill<R>(tq, quadrant, warp >> 2, (nWarps - quadrant + 3) >> 2, lane, a, SRC == SRC_RAW16);
+	}
 	tmem_fence_before_sync();
 	__syncthreads();
 	tmem_fence_after_sync();

@@ -102,43 +102,72 @@ __device__ __forceinline__ void tmem_st_f4(uint32_t taddr, float4 a) {
 	const uint32_t r[4] = { __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w) };
 	tmem_st4(taddr, r);
 }
+/* Every warp takes part: warp w writes rows part, part + parts, ... of quadrant w % 4 (part = w / 4, parts = warps of that quadrant).
+ * All global loads of a phase are issued before the first tensor-memory store, so the fill costs two memory latencies instead of
+ * one per row (it used to be ~7 % of the kernel: 50 dependent L2 round trips by 4 warps while 12 waited at the barrier). */
 template <int R>
-__device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int quadrant, int lane, const FusedArgs& a, bool haveLut) {
+__device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int quadrant, int part, int parts, int lane, const FusedArgs& a, bool haveLut) {
 	using M = TmemMap<R>;
 	constexpr int HN = 512 * R;
 	const int p = (R == 2) ? (quadrant & 1) : 0;         /* the sub-sequence whose warps read this quadrant */
 	if (haveLut) {
-		for (int jj = 0; jj < 16; ++jj) {
-			const int e = p * 512 + lane + 32 * jj;
-			const float4 Pq = __ldg(a.lutB + e), Qq = __ldg(a.lutB + HN + e), W01 = __ldg(a.lutB + 2 * HN + e), W23 = __ldg(a.lutB + 3 * HN + e);
-			/* row = [ off_a off_b w0a w0b | w1a w1b t_a t_b || w2a w2b w3a w3b | wPa wPb ]: two x8 reads, the second one late */
-			tmem_st_f4(tq + M::LUT + 16 * jj + 0, make_float4(Qq.x, Qq.y, W01.x, W01.y));
-			tmem_st_f4(tq + M::LUT + 16 * jj + 4, make_float4(W01.z, W01.w, Qq.z, Qq.w));
-			tmem_st_f4(tq + M::LUT + 16 * jj + 8, W23);
-			tmem_st_f4(tq + M::LUT + 16 * jj + 12, Pq);
-		}
-	}
-	for (int k1 = 0; k1 < 32; k1 += 2) {
-		const float2 t0 = __ldg(a.tw + k1 * 32 + lane), t1 = __ldg(a.tw + (k1 + 1) * 32 + lane);
-		tmem_st_f4(tq + M::TW + 2 * k1, make_float4(t0.x, t0.y, t1.x, t1.y));
-	}
-	if constexpr (R == 2) {
-		for (int k2 = 0; k2 < 32; k2 += 2) {
-			const float2 c0 = __ldg(a.ctw + lane + 32 * k2), c1 = __ldg(a.ctw + lane + 32 * (k2 + 1));
-			tmem_st_f4(tq + M::CTW + 2 * k2, make_float4(c0.x, c0.y, c1.x, c1.y));
+		for (int base = part; base < 16; base += 4 * parts) {
+			float4 b[4][4];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				const int jj = base + u * parts;
+				if (jj < 16) {
+					const int e = p * 512 + lane + 32 * jj;
+					b[u][0] = __ldg(a.lutB + e); b[u][1] = __ldg(a.lutB + HN + e); b[u][2] = __ldg(a.lutB + 2 * HN + e); b[u][3] = __ldg(a.lutB + 3 * HN + e);
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				const int jj = base + u * parts;
+				if (jj < 16) {
+					const float4 Pq = b[u][0], Qq = b[u][1], W01 = b[u][2], W23 = b[u][3];
+					/* row = [ off_a off_b w0a w0b | w1a w1b t_a t_b || w2a w2b w3a w3b | wPa wPb ]: two x8 reads, the second one late */
+					tmem_st_f4(tq + M::LUT + 16 * jj + 0, make_float4(Qq.x, Qq.y, W01.x, W01.y));
+					tmem_st_f4(tq + M::LUT + 16 * jj + 4, make_float4(W01.z, W01.w, Qq.z, Qq.w));
+					tmem_st_f4(tq + M::LUT + 16 * jj + 8, W23);
+					tmem_st_f4(tq + M::LUT + 16 * jj + 12, Pq);
+				}
+			}
 		}
 	}
 	const int k2lo = 16 * p;                              /* bins lane + 32 k2, k2 in [16p, 16p+16) are finalised by the warps of p */
-	if (a.epi.fpn && a.cplxOut == nullptr) {
-		for (int i = 0; i < 16; i += 2) {
-			const float2 m0 = __ldg(a.meanLine + lane + 32 * (k2lo + i)), m1 = __ldg(a.meanLine + lane + 32 * (k2lo + i + 1));
-			tmem_st_f4(tq + M::MEAN + 2 * i, make_float4(m0.x, m0.y, m1.x, m1.y));
+	const bool fpn = a.epi.fpn && a.cplxOut == nullptr;
+	for (int base = part; base < 16; base += 4 * parts) {
+		float4 t[4], c[4], m[4], g[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const int i = base + u * parts;                 /* pair index: twiddles k1 = 2i, 2i+1; mean bins 2i, 2i+1 (i < 8); background bins 4i..4i+3 (i < 4) */
+			if (i < 16) {
+				const float2 t0 = __ldg(a.tw + (2 * i) * 32 + lane), t1 = __ldg(a.tw + (2 * i + 1) * 32 + lane);
+				t[u] = make_float4(t0.x, t0.y, t1.x, t1.y);
+				if constexpr (R == 2) {
+					const float2 c0 = __ldg(a.ctw + lane + 32 * (2 * i)), c1 = __ldg(a.ctw + lane + 32 * (2 * i + 1));
+					c[u] = make_float4(c0.x, c0.y, c1.x, c1.y);
+				}
+				if (fpn && i < 8) {
+					const float2 m0 = __ldg(a.meanLine + lane + 32 * (k2lo + 2 * i)), m1 = __ldg(a.meanLine + lane + 32 * (k2lo + 2 * i + 1));
+					m[u] = make_float4(m0.x, m0.y, m1.x, m1.y);
+				}
+				if (a.epi.ppbg && i < 4)
+					g[u] = make_float4(__ldg(a.ppbg + lane + 32 * (k2lo + 4 * i)), __ldg(a.ppbg + lane + 32 * (k2lo + 4 * i + 1)),
+					                   __ldg(a.ppbg + lane + 32 * (k2lo + 4 * i + 2)), __ldg(a.ppbg + lane + 32 * (k2lo + 4 * i + 3)));
+			}
 		}
-	}
-	if (a.epi.ppbg) {
-		for (int i = 0; i < 16; i += 4)
-			tmem_st_f4(tq + M::PPBG + i, make_float4(__ldg(a.ppbg + lane + 32 * (k2lo + i)), __ldg(a.ppbg + lane + 32 * (k2lo + i + 1)),
-			                                         __ldg(a.ppbg + lane + 32 * (k2lo + i + 2)), __ldg(a.ppbg + lane + 32 * (k2lo + i + 3))));
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const int i = base + u * parts;
+			if (i < 16) {
+				tmem_st_f4(tq + M::TW + 4 * i, t[u]);
+				if constexpr (R == 2) tmem_st_f4(tq + M::CTW + 4 * i, c[u]);
+				if (fpn && i < 8) tmem_st_f4(tq + M::MEAN + 4 * i, m[u]);
+				if (a.epi.ppbg && i < 4) tmem_st_f4(tq + M::PPBG + 4 * i, g[u]);
+			}
+		}
 	}
 	tmem_wait_st();
 }

@@ -5,6 +5,9 @@ Every stage of the path is per A-scan or per B-scan, so the shards never exchang
     (cuda_code.cu:1520-1522) and broadcast once (or per buffer in continuous mode);
   * the displayed en-face slice: each rank extracts its A x B_local floats, one all_gather assembles the frame
     (the only collective on the display path; the volume itself stays sharded in HBM).
+The en-face gather has two implementations: `enface` (local extraction + one all_gather: NCCL / gloo) and
+`connect_enface_peers` + `enface_p2p` (the library's own kernel stores every value straight into all ranks' frame windows
+over NVLink peer memory and publishes a sequence flag: one kernel, no NCCL call on the display path).
 `dist` is a torch.distributed-like module (NCCL on GPUs, gloo in the CPU tests); `pipeline_factory` builds the
 per-rank engine (OctPipeline on a B200; the tests inject an oracle-backed stand-in to check the host logic).
 """
@@ -100,3 +103,45 @@ class ShardedPipeline:
         # the reference writes the frame reversed (index (E-1)-i): global order = shards in reverse rank order
         out = [parts[r][: a * shard_bounds(btot, self.world, r)[1]] for r in reversed(range(self.world))]
         return torch.cat(out)
+
+    # ---- en-face frame gathered by the library's own kernel over peer memory (include/octb200.h: octb200_enface_gather_*) ----
+    def connect_enface_peers(self, device=None) -> None:
+        """collective: every rank allocates its frame window, the 64-byte IPC handles are exchanged rank-major with one
+        all_gather, every rank opens the windows of its peers.  `device`: where the handle tensor lives for the collective
+        (a CUDA device for NCCL, None/cpu for gloo)."""
+        import torch
+        if self.count == 0:
+            raise ValueError("a rank without B-scans cannot take part in the peer gather")
+        a, btot = int(self.full.ascansPerBscan), int(self.full.bscansPerBuffer)
+        mine = self.pipe.enface_gather_init(self.rank, self.world, a * btot, a * self.start)
+        if len(mine) != 64:
+            raise ValueError("IPC handle must be 64 bytes")
+        if self.world == 1 or self.dist is None:
+            handles = mine
+        else:
+            t = torch.tensor(list(mine), dtype=torch.uint8)
+            if device is not None:
+                t = t.to(device)
+            parts = [torch.empty_like(t) for _ in range(self.world)]
+            self.dist.all_gather(parts, t)
+            handles = b"".join(bytes(x.cpu().numpy().tobytes()) for x in parts)
+        self.pipe.enface_gather_connect(handles)
+        self._p2p = True
+        if self.world > 1 and self.dist is not None:
+            self.dist.barrier()           # nobody gathers into a window that is not open yet
+
+    def enface_p2p(self, frame_nr: int, n_frames: int, fn: int, wait: bool = True) -> int:
+        """extraction + peer stores + flag (one kernel on the compute stream).  With wait=True also enqueues the wait for every
+        rank's slab and returns the device address of the assembled frame [A*B_total] floats in the reference's order."""
+        if not getattr(self, "_p2p", False):
+            raise RuntimeError("connect_enface_peers() first")
+        self.pipe.enface_gather(frame_nr, n_frames, fn)
+        return self.pipe.enface_gather_wait() if wait else 0
+
+    def close_enface_peers(self) -> None:
+        if getattr(self, "_p2p", False):
+            self.sync()
+            if self.world > 1 and self.dist is not None:
+                self.dist.barrier()       # peers have stopped writing into this rank's window
+            self.pipe.enface_gather_close()
+            self._p2p = False

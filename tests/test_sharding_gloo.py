@@ -61,6 +61,20 @@ class OracleEngine:
     def sync(self):
         pass
 
+    # peer-gather protocol stand-ins: the "handle" encodes who made it, connect checks the rank-major exchange
+    def enface_gather_init(self, rank, world, global_lines, line_offset):
+        self.gather = dict(rank=rank, world=world, global_lines=global_lines, line_offset=line_offset)
+        return bytes([rank]) * 64
+
+    def enface_gather_connect(self, handles):
+        w = self.gather["world"]
+        assert len(handles) == 64 * w
+        assert all(handles[64 * r:64 * (r + 1)] == bytes([r]) * 64 for r in range(w)), "handles must arrive rank-major"
+        self.gather["connected"] = True
+
+    def enface_gather_close(self):
+        self.gather["connected"] = False
+
 
 def _worker(rank, world, port, raw, q, ref, ref_enface, errs):
     try:
@@ -76,6 +90,12 @@ def _worker(rank, world, port, raw, q, ref, ref_enface, errs):
         extract = lambda f, nf, fn: torch.from_numpy(orc.enface_frame(sp.pipe.out, h, q.ascansPerBscan, cnt, f, nf, fn))  # noqa: E731
         full = sp.enface(17, 1, 0, extract)
         assert np.allclose(full.numpy(), ref_enface, rtol=0, atol=2e-6), f"rank {rank}: en-face gather order"
+        # peer-memory gather: handle exchange + window geometry (the kernel itself is covered by the GPU tests)
+        sp.connect_enface_peers()
+        g = sp.pipe.gather
+        assert g["connected"] and g["global_lines"] == q.ascansPerBscan * q.bscansPerBuffer and g["line_offset"] == q.ascansPerBscan * lo
+        sp.close_enface_peers()
+        assert not g["connected"]
         dist.barrier()
         dist.destroy_process_group()
     except Exception as e:  # noqa: BLE001
