@@ -13,8 +13,9 @@ A "step" = one pass of the hot path over one raw buffer (one volume = 131072 A-s
 One JSON line on stdout (rank 0).  `value` = device-resident rate (raw already in HBM), `e2e` = through the
 reference-facing call octCudaPipeline(host buffer) with the pinned H2D copy and the D2H of the converted
 output (the reference's stream-to-host path) inside the timed region.  Multi-GPU: weak scaling, every rank
-processes its own buffer (slab of a G-times larger volume) and the en-face slice is all-gathered over NCCL
-inside the timed region.
+processes its own buffer (slab of a G-times larger volume) and the en-face slice is gathered inside the timed
+region, every step, by the library's own kernel over NVLink peer memory (octb200_enface_gather; `--enface nccl` = the
+extraction kernel + ncclAllGather baseline).
 """
 from __future__ import annotations
 
@@ -152,6 +153,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--mode", default="fused", choices=["fused", "split", "cufft"])
+    ap.add_argument("--enface", default="p2p", choices=["p2p", "nccl"], help="multi-GPU en-face gather: own peer-memory kernel or NCCL")
     ap.add_argument("--cpu-bscans", type=int, default=0, help="B-scans in the cpu_baseline sample (0 = auto)")
     args = ap.parse_args()
 
@@ -228,12 +230,44 @@ def main():
         dist.broadcast(ml, 0)
         p.set_fpn_mean_line(ml.cpu().numpy())
 
-    def step_resident(i):
-        p.process_device(d_raw[i & 1])
-        if dist is not None:
+    # en-face slice of the G-times larger volume, every step: the library's own kernel stores each rank's slab straight into every
+    # rank's frame window over NVLink peer memory (octb200_enface_gather); extraction + ncclAllGather only if IPC is unavailable
+    gather_impl = None
+    if dist is not None and args.enface != "nccl":
+        try:
+            mine = p.enface_gather_init(rank, world, world * a * b, rank * a * b)
+            t = torch.tensor(list(mine), dtype=torch.uint8, device="cuda")
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            p.enface_gather_connect(b"".join(x.cpu().numpy().tobytes() for x in parts))
+            ok = torch.ones(1, device="cuda")
+        except Exception as e:  # noqa: BLE001
+            print(f"rank {rank}: peer-memory en-face gather unavailable ({e}); using NCCL", file=sys.stderr, flush=True)
+            ok = torch.zeros(1, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_impl = "p2p" if float(ok.item()) > 0 else "nccl"
+        dist.barrier()
+    elif dist is not None:
+        gather_impl = "nccl"
+
+    if gather_impl == "p2p":
+        p.enface_gather_auto(True, 100, 1, 0)      # every process call gathers depth 100: fused into the main kernel's epilogue
+
+    def enface_step():
+        if gather_impl == "p2p":
+            pass
+        elif gather_impl == "nccl":
             p.changeDisplayedEnFaceFrame(100, 1, 0, enface)
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gathered, enface)
+
+    def enface_finish():
+        if gather_impl == "p2p":
+            p.enface_gather_wait()         # every rank's slab of the last frame has arrived (flags, system-scope acquire)
+
+    def step_resident(i):
+        p.process_device(d_raw[i & 1])
+        enface_step()
 
     # warm-up (includes LUT build, FPN determination, cuFFT plan if any)
     p.process_device(d_raw[0]); p.sync(); fpn_share()
@@ -248,6 +282,7 @@ def main():
     p.event_record(0)
     for i in range(args.steps):
         step_resident(i)
+    enface_finish()
     p.event_record(1)
     ms_total = p.event_elapsed_ms(0, 1)
     sync_all()
@@ -283,10 +318,8 @@ def main():
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         p.octCudaPipeline(h_raw[i & 1].numpy())
-        if dist is not None:
-            p.changeDisplayedEnFaceFrame(100, 1, 0, enface)
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, enface)
+        enface_step()
+    enface_finish()
     p.sync(); torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -303,6 +336,10 @@ def main():
         c = cpu_reference_run(q, ncores, bscans, repeats=4)
         cpu = {"value": c["mhz"], "unit": "MHz (1e6 A-scans/s)", "cores": c["threads"], "kind": c["kind"], "sample": c["sample"]}
 
+    if dist is not None:
+        p.sync(); torch.cuda.synchronize(); dist.barrier()       # peers have stopped writing into this rank's window
+        if gather_impl == "p2p":
+            p.enface_gather_close()
     p.cleanupCuda()
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
@@ -313,7 +350,8 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours",
             "config": dict(config, mode=args.mode, l2="two alternating 256 MiB inputs and 256 MiB outputs per GPU: larger than the 126 MB L2",
-                           parallelism=f"b-scan sharding x{world}" + (", NCCL all-gather of the en-face slice every step" if world > 1 else "")),
+                           parallelism=f"b-scan sharding x{world}" + ((", en-face slice gathered every step inside the fused kernel's epilogue over NVLink peer memory"
+                                                                       if gather_impl == "p2p" else ", NCCL all-gather of the en-face slice every step") if world > 1 else "")),
             "e2e": {"value": e2e_mhz, "unit": "MHz (1e6 A-scans/s)", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": conv_bytes,
                     "ms_per_step": e2e_s * 1e3 / e2e_steps, "steps": e2e_steps, "timer": "host wall clock between device synchronisations, max over ranks",
                     "checksum": checksum},

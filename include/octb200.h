@@ -203,6 +203,10 @@ OCTB200_API int octb200_float_to_output(octb200_pipeline* p, uint32_t bufferNrIn
      connect : handles = world * 64 bytes, rank-major; opens every peer window
      gather  : enqueue extraction + peer stores + flag publication on the compute stream (double-buffered by sequence number:
                a frame stays valid until the second-next gather)
+     auto    : from now on EVERY octb200_process_* call also gathers frame (frameNr, frames, function) of the buffer it produced.
+               When one depth frame is displayed and the slab is final after the fused kernel (single-slab volume, no sinusoidal
+               correction, no background recording) the extraction and the peer stores happen inside that kernel's epilogue -- compute and collective
+               in one launch; otherwise the stand-alone gather kernel is appended to the chain
      wait    : enqueue, on the compute stream, the wait for the latest sequence number of ALL ranks; *dFrame = device pointer
                of the assembled frame [globalLines] floats, reference order disp[(E-1)-i]
      close   : release (collective in spirit: call after a barrier, peers must have stopped gathering) */
@@ -210,6 +214,7 @@ OCTB200_API int octb200_float_to_output(octb200_pipeline* p, uint32_t bufferNrIn
 OCTB200_API int octb200_enface_gather_init(octb200_pipeline* p, int rank, int world, uint32_t globalLines, uint32_t lineOffset, void* handleOut);
 OCTB200_API int octb200_enface_gather_connect(octb200_pipeline* p, const void* handles);
 OCTB200_API int octb200_enface_gather(octb200_pipeline* p, uint32_t frameNr, uint32_t displayFunctionFrames, int displayFunction);
+OCTB200_API int octb200_enface_gather_auto(octb200_pipeline* p, int enable, uint32_t frameNr, uint32_t displayFunctionFrames, int displayFunction);
 OCTB200_API int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame);
 OCTB200_API int octb200_enface_gather_close(octb200_pipeline* p);
 

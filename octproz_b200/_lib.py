@@ -27,7 +27,7 @@ SYMBOLS = [
     "octb200_volume_u8", "octb200_float_to_output", "octb200_compute_stream", "octb200_event_record",
     "octb200_event_elapsed_ms", "octb200_launch_count", "octb200_time_kernel",
     "octb200_enface_gather_init", "octb200_enface_gather_connect", "octb200_enface_gather", "octb200_enface_gather_wait",
-    "octb200_enface_gather_close",
+    "octb200_enface_gather_close", "octb200_enface_gather_auto",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
     lib.octb200_enface_gather_init.argtypes = [P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.octb200_enface_gather_connect.argtypes = [P, C.c_void_p]
     lib.octb200_enface_gather.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int]
+    lib.octb200_enface_gather_auto.argtypes = [P, C.c_int, C.c_uint32, C.c_uint32, C.c_int]
     lib.octb200_enface_gather_wait.argtypes = [P, C.POINTER(C.c_void_p)]
     lib.octb200_enface_gather_close.argtypes = [P]
     _lib = lib

@@ -352,8 +352,6 @@ cudaError_t launch_enface_frame(float* disp, const float* vol, unsigned W, unsig
  * value is stored straight into the frame window of EVERY rank (P2P stores over NVLink / NVSwitch; the own rank is a plain
  * store).  The last CTA to finish publishes `seq` in each rank's flag word for this rank (release, system scope); readers
  * wait with enface_wait_kernel (acquire, system scope). */
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 __global__ void __launch_bounds__(256) enface_gather_kernel(const EnfaceGatherArgs a) {
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,13 +381,13 @@ __global__ void __launch_bounds__(256) enface_gather_kernel(const EnfaceGatherAr
 		if (done == gridDim.x - 1) {
 			*a.counter = 0;                                             /* next launch is stream ordered behind this one */
 			__threadfence_system();
-			for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, a.seq);
+			for (int r = 0; r < a.world; ++r) st_release_sys_u32(a.flags[r] + a.rank, a.seq);
 		}
 	}
 }
 __global__ void enface_wait_kernel(const unsigned* flags, int world, unsigned seq) {
 	if ((int)threadIdx.x < world) {
-		while ((int)(ld_acquire_sys(flags + threadIdx.x) - seq) < 0) __nanosleep(200);
+		while ((int)(ld_acquire_sys_u32(flags + threadIdx.x) - seq) < 0) __nanosleep(200);
 	}
 }
 cudaError_t launch_enface_gather(const EnfaceGatherArgs& a, cudaStream_t st) {

@@ -33,7 +33,6 @@ struct PostArgs {
 };
 
 /* en-face extraction + all-gather over peer memory */
-constexpr int OCT_MAX_PEERS = 16;
 struct EnfaceGatherArgs {
 	float* frames[OCT_MAX_PEERS];      /* this sequence number's frame window of every rank (peer-mapped device pointers) */
 	unsigned* flags[OCT_MAX_PEERS];    /* flag words of every rank; word [rank] is written by this rank */

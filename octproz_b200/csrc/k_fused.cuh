@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	 * groups overlap instead of all groups hitting the same pipe at the same time */
 	__nanosleep((unsigned)(grp * OCT_STAGGER_NS));
 #endif
+	/* en-face gather fused into the epilogue: k2 index of the displayed depth bin (bin = lane + 32 k2), -1 = off */
+	const int egK2 = (a.eg.world > 0) ? (int)(a.eg.frameNr >> 5) : -1;
 	int it = 0;
 	for (int gline = g0; gline < a.lines; gline += G, ++it) {
 		float2 v[32];
@@ -304,7 +306,9 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u) al = a.A - 1 - al;
 			float* o = a.out + ((size_t)b * a.A + al) * H;
 #if OCT_TMEM_LUT
-			if (R == 1 || p == 0) epilogue_tmem<R, 0>(lane, v, a.epi, tq, o); else epilogue_tmem<R, 16>(lane, v, a.epi, tq, o);
+			float egVal = 0.f;
+			if (R == 1 || p == 0) epilogue_tmem<R, 0>(lane, v, a.epi, tq, o, egK2, egVal); else epilogue_tmem<R, 16>(lane, v, a.epi, tq, o, egK2, egVal);
+			if (egK2 >= 0 && (R == 1 || p == (egK2 >> 4)) && lane == (int)(a.eg.frameNr & 31u)) gather_store(a.eg, (unsigned)(b * a.A + al), egVal);
 #else
 			if (R == 1 || p == 0) epilogue_scaled<0>(lane, v, a.epi, sMean, sPpbg, o); else epilogue_scaled<16>(lane, v, a.epi, sMean, sPpbg, o);
 #endif
@@ -315,7 +319,21 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	tmem_fence_before_sync();
 	__syncthreads();
 	if (warp == 0) tmem_dealloc(tmemBase, TmemMap<R>::ALLOC);
+#else
+	__syncthreads();
 #endif
+	if (a.eg.world > 0 && threadIdx.x == 0) {
+		/* the last CTA to arrive publishes this rank's sequence number in every rank's flag word.  One system-scope fence by
+		 * this thread after the CTA barrier orders the peer stores of ALL its threads before the arrival (fence cumulativity:
+		 * the pattern of a grid-wide barrier) -- a fence per storing thread cost 4 % of the kernel */
+		__threadfence_system();
+		const unsigned done = atomicAdd(a.eg.counter, 1u);
+		if (done == gridDim.x - 1) {
+			*a.eg.counter = 0;
+			__threadfence_system();
+			for (int r = 0; r < a.eg.world; ++r) st_release_sys_u32(a.eg.flags[r] + a.eg.rank, a.eg.seq);
+		}
+	}
 }
 
 }  // namespace octb200

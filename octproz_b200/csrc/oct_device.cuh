@@ -49,6 +49,32 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 __device__ __forceinline__ float u16lo_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.0f; }
 __device__ __forceinline__ float u16hi_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f; }
 
+/* ---------------- en-face gather over peer memory, fused into the epilogue (multi-GPU shards) ----------------
+ * world > 0: the lane that finalises depth bin frameNr of a line (updateDisplayedEnFaceFrame with one frame, cuda_code.cu:909)
+ * keeps that output value in a register and writes it straight into the frame window of EVERY rank (P2P stores over NVLink);
+ * the last CTA publishes `seq` in every rank's flag word (release, system scope).  See k_aux.cu enface_gather_kernel for the
+ * stand-alone form used for multi-frame averages / MIP and when later passes (sinusoidal correction, background recording)
+ * still change the slab. */
+constexpr int OCT_MAX_PEERS = 16;
+struct GatherDev {
+	float* frames[OCT_MAX_PEERS];
+	unsigned* flags[OCT_MAX_PEERS];
+	unsigned* counter;
+	unsigned Eglobal, offset, seq;
+	unsigned frameNr, nFrames;
+	int fn;
+	int world, rank;
+};
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+/* store the en-face value of output line `line` into every rank's frame (called by the one lane that holds the depth bin) */
+__device__ __forceinline__ void gather_store(const GatherDev& g, unsigned line, float val) {
+	const unsigned dst = (g.Eglobal - 1u) - (g.offset + line);
+#pragma unroll 1
+	for (int r = 0; r < g.world; ++r) g.frames[r][dst] = val;
+}
+
 /* ---------------- argument block of the fused / own-FFT kernels ---------------- */
 struct FusedArgs {
 	const uint16_t* raw;     /* SRC_RAW16: [lines][N] u16 (whole raw buffer, halo reads clip to [0,totalSamples)) */
@@ -69,6 +95,7 @@ struct FusedArgs {
 	int shiftBits;
 	int W;
 	int HB, HA;
+	GatherDev eg;            /* eg.world == 0: no en-face gather in this launch */
 };
 
 enum { SRC_RAW16 = 0, SRC_CPLX = 1 };

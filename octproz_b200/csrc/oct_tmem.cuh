@@ -306,7 +306,7 @@ __device__ __forceinline__ void combine_store_tmem(int lane, int p, float2 (&v)[
 
 /* ---- epilogue with the FPN line / background from TMEM (cf. epilogue_scaled_t) ---- */
 template <int R, int K2LO, bool LOG, bool FPN, bool PPBG>
-__device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine) {
+__device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, int egK2, float& egVal) {
 	using M = TmemMap<R>;
 	const float sA = e.scaleA, sB = e.scaleB, bw = e.ppbgWeight, bo = e.ppbgOffset;
 	static_for<0, 4>([&](auto gc) {
@@ -325,21 +325,22 @@ __device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32],
 			float o = LOG ? fmaf(oct_lg2(pw), sA, sB) : fmaf(oct_sqrt(pw), sA, sB);
 			if constexpr (PPBG) o = saturate01(o - fmaf(bw, bgv[i], bo));
 			outLine[z] = o;
+			if (k2 == egK2) egVal = o;                   /* uniform compare: the displayed en-face bin stays in a register */
 		});
 	});
 }
 template <int R, int K2LO>
-__device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine) {
+__device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, int egK2, float& egVal) {
 	const int sel = (e.logMode ? 1 : 0) | (e.fpn ? 2 : 0) | (e.ppbg ? 4 : 0);
 	switch (sel) {
-	case 0: epilogue_tmem_t<R, K2LO, false, false, false>(lane, v, e, tq, outLine); break;
-	case 1: epilogue_tmem_t<R, K2LO, true, false, false>(lane, v, e, tq, outLine); break;
-	case 2: epilogue_tmem_t<R, K2LO, false, true, false>(lane, v, e, tq, outLine); break;
-	case 3: epilogue_tmem_t<R, K2LO, true, true, false>(lane, v, e, tq, outLine); break;
-	case 4: epilogue_tmem_t<R, K2LO, false, false, true>(lane, v, e, tq, outLine); break;
-	case 5: epilogue_tmem_t<R, K2LO, true, false, true>(lane, v, e, tq, outLine); break;
-	case 6: epilogue_tmem_t<R, K2LO, false, true, true>(lane, v, e, tq, outLine); break;
-	default: epilogue_tmem_t<R, K2LO, true, true, true>(lane, v, e, tq, outLine); break;
+	case 0: epilogue_tmem_t<R, K2LO, false, false, false>(lane, v, e, tq, outLine, egK2, egVal); break;
+	case 1: epilogue_tmem_t<R, K2LO, true, false, false>(lane, v, e, tq, outLine, egK2, egVal); break;
+	case 2: epilogue_tmem_t<R, K2LO, false, true, false>(lane, v, e, tq, outLine, egK2, egVal); break;
+	case 3: epilogue_tmem_t<R, K2LO, true, true, false>(lane, v, e, tq, outLine, egK2, egVal); break;
+	case 4: epilogue_tmem_t<R, K2LO, false, false, true>(lane, v, e, tq, outLine, egK2, egVal); break;
+	case 5: epilogue_tmem_t<R, K2LO, true, false, true>(lane, v, e, tq, outLine, egK2, egVal); break;
+	case 6: epilogue_tmem_t<R, K2LO, false, true, true>(lane, v, e, tq, outLine, egK2, egVal); break;
+	default: epilogue_tmem_t<R, K2LO, true, true, true>(lane, v, e, tq, outLine, egK2, egVal); break;
 	}
 }
 

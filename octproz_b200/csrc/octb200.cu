@@ -111,6 +111,8 @@ struct octb200_pipeline {
 		bool opened[OCT_MAX_PEERS] = {};
 		bool connected = false;
 		unsigned* counter = nullptr;
+		bool autoOn = false;               /* every process call also gathers the en-face frame */
+		unsigned autoFrame = 0, autoFrames = 1; int autoFn = 0;
 	} eg;
 };
 
@@ -253,6 +255,30 @@ PreArgs pre_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, i
 	return a;
 }
 
+/* next en-face gather of this handle: sequence number, frame window of that parity on every rank, flag words */
+GatherDev next_gather(octb200_pipeline* p, unsigned frameNr, unsigned nFrames, int fn) {
+	auto& g = p->eg;
+	GatherDev d{};
+	g.seq++;
+	for (int r = 0; r < g.world; ++r) {
+		d.frames[r] = reinterpret_cast<float*>(g.peerBase[r] + 256 + (size_t)(g.seq & 1u) * g.frameStride);
+		d.flags[r] = reinterpret_cast<unsigned*>(g.peerBase[r]);
+	}
+	d.counter = g.counter; d.Eglobal = g.Eglobal; d.offset = g.offset; d.seq = g.seq;
+	d.frameNr = (frameNr >= (unsigned)p->H) ? 0u : frameNr;          /* cuda_code.cu:1302 */
+	d.nFrames = nFrames < 1 ? 1u : nFrames; d.fn = fn; d.world = g.world; d.rank = g.rank;
+	return d;
+}
+cudaError_t launch_gather_standalone(octb200_pipeline* p, const GatherDev& d) {
+	EnfaceGatherArgs a{};
+	for (int r = 0; r < d.world; ++r) { a.frames[r] = d.frames[r]; a.flags[r] = d.flags[r]; }
+	a.vol = p->dVolume; a.counter = d.counter;
+	a.W = (unsigned)p->H; a.E = (unsigned)(p->A * p->B * p->V);
+	a.frameNr = d.frameNr; a.nFrames = d.nFrames; a.fn = d.fn;
+	a.Eglobal = d.Eglobal; a.offset = d.offset; a.world = d.world; a.rank = d.rank; a.seq = d.seq;
+	return launch_enface_gather(a, p->sCompute);
+}
+
 /* the whole per-buffer chain on the compute stream; dRaw is device memory */
 int run_chain(octb200_pipeline* p, const void* dRaw) {
 	octb200_params& q = p->prm;
@@ -291,6 +317,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 	int fpnHeight = (int)q.bscansForNoiseDetermination * p->A;
 	if (fpnHeight > p->lines) fpnHeight = p->lines;
 
+	bool gatherDone = false;
 	if (mode == OCTB200_FFT_CUFFT) {
 		PreArgs pa = pre_args(p, st, dRaw, p->lines);
 		CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++;
@@ -326,6 +353,11 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		if (src == SRC_CPLX) { PreArgs pa = pre_args(p, st, dRaw, p->lines); CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++; }
 		FusedArgs fa = fused_args(p, st, dRaw, p->lines);
 		fa.out = mainOut; fa.epi = epi_for(p, fpn, ppbgFoldMain);
+		/* automatic en-face gather: fused into this kernel's epilogue when the slab is final after it */
+		if (p->eg.autoOn && p->eg.connected && !sinus && !ppbgRecord && p->V == 1 && p->eg.autoFrames <= 1) {
+			fa.eg = next_gather(p, p->eg.autoFrame, p->eg.autoFrames, p->eg.autoFn);
+			gatherDone = true;
+		}
 		CK(p, launch_fused(p->R, st.sa, st.roll, src, fa, p->smCount, p->sCompute)); p->launches++;
 	}
 
@@ -341,6 +373,12 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		int rc = enqueue_callback(p, p->sCompute, p->cbBackground, p->hPpbg.data()); if (rc) return rc;
 		q.postProcessBackgroundRecordingRequested = 0;
 		CK(p, launch_ppbg_remove(slab, p->dPpbg, q.postProcessBackgroundWeight, q.postProcessBackgroundOffset, p->H, p->S / 2, p->smCount, p->sCompute)); p->launches++;
+	}
+
+	if (p->eg.autoOn && p->eg.connected && !gatherDone) {
+		/* later passes changed the slab (or the volume has several slabs): stand-alone extraction + peer stores */
+		const GatherDev d = next_gather(p, p->eg.autoFrame, p->eg.autoFrames, p->eg.autoFn);
+		CK(p, launch_gather_standalone(p, d)); p->launches++;
 	}
 
 	/* ---- streaming to the host (cuda_code.cu:1357-1386,1595-1604) ---- */
@@ -776,19 +814,14 @@ int octb200_enface_gather_connect(octb200_pipeline* p, const void* handles) {
 int octb200_enface_gather(octb200_pipeline* p, uint32_t frameNr, uint32_t nFrames, int fn) {
 	if (!p || !p->eg.connected) return fail(p, OCTB200_ERR_NOT_READY, "en-face gather is not connected");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
-	auto& g = p->eg;
-	if (frameNr >= (unsigned)p->H) frameNr = 0;                      /* cuda_code.cu:1302 */
-	EnfaceGatherArgs a{};
-	g.seq++;
-	for (int r = 0; r < g.world; ++r) {
-		a.frames[r] = reinterpret_cast<float*>(g.peerBase[r] + 256 + (size_t)(g.seq & 1u) * g.frameStride);
-		a.flags[r] = reinterpret_cast<unsigned*>(g.peerBase[r]);
-	}
-	a.vol = p->dVolume; a.counter = g.counter;
-	a.W = (unsigned)p->H; a.E = (unsigned)(p->A * p->B * p->V);
-	a.frameNr = frameNr; a.nFrames = nFrames; a.fn = fn;
-	a.Eglobal = g.Eglobal; a.offset = g.offset; a.world = g.world; a.rank = g.rank; a.seq = g.seq;
-	CK(p, launch_enface_gather(a, p->sCompute)); p->launches++;
+	const GatherDev d = next_gather(p, frameNr, nFrames, fn);
+	CK(p, launch_gather_standalone(p, d)); p->launches++;
+	return OCTB200_OK;
+}
+int octb200_enface_gather_auto(octb200_pipeline* p, int enable, uint32_t frameNr, uint32_t nFrames, int fn) {
+	if (!p) return OCTB200_ERR_INVALID;
+	if (enable && !p->eg.connected) return fail(p, OCTB200_ERR_NOT_READY, "en-face gather is not connected");
+	p->eg.autoOn = enable != 0; p->eg.autoFrame = frameNr; p->eg.autoFrames = nFrames; p->eg.autoFn = fn;
 	return OCTB200_OK;
 }
 int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame) {
@@ -810,7 +843,7 @@ int octb200_enface_gather_close(octb200_pipeline* p) {
 		g.opened[r] = false; g.peerBase[r] = nullptr;
 	}
 	dfree(g.window); dfree(g.counter);
-	g.connected = false; g.world = 0; g.seq = 0;
+	g.connected = false; g.world = 0; g.seq = 0; g.autoOn = false;
 	return OCTB200_OK;
 }
 

@@ -155,6 +155,10 @@ class OctPipeline:
         """changeDisplayedEnFaceFrame of the whole sharded volume: extraction + P2P stores into every rank's frame, one kernel"""
         self._ck(self._lib.octb200_enface_gather(self._h, frameNr, displayFunctionFrames, displayFunction), "enface_gather")
 
+    def enface_gather_auto(self, enable: bool, frameNr: int = 0, displayFunctionFrames: int = 1, displayFunction: int = 0) -> None:
+        """every octCudaPipeline / process_device call also gathers this frame (inside the fused kernel's epilogue when possible)"""
+        self._ck(self._lib.octb200_enface_gather_auto(self._h, int(enable), frameNr, displayFunctionFrames, displayFunction), "enface_gather_auto")
+
     def enface_gather_wait(self) -> int:
         """enqueue the wait for all ranks' slabs of the latest gather; returns the device address of the assembled frame"""
         out = C.c_void_p()

@@ -58,6 +58,19 @@ def main():
         assert same, f"rank {rank}: peer gather differs from all_gather for frame {(frame, nf, fn)}"
         assert e_p2p < 1e-3, f"rank {rank}: en-face differs from the oracle by {e_p2p}"
         dist.barrier()
+    # ---- automatic gather inside the fused kernel's epilogue: process + gather in ONE launch, every rank's frame complete ----
+    sp.pipe.enface_gather_auto(True, 17, 1, 0)
+    sp.pipe.octCudaPipeline(sp.local_slice(raw))
+    ptr = sp.pipe.enface_gather_wait(); sp.sync()
+
+    class _W2:  # noqa: N801
+        __cuda_array_interface__ = {"shape": (a * btot,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    got = torch.as_tensor(_W2(), device=dev).clone().cpu().numpy()
+    e_auto = float(np.abs(got - orc.enface_frame(ref, n // 2, a, btot, 17, 1, 0)).max())
+    assert e_auto < 1e-3, f"rank {rank}: fused en-face gather differs from the oracle by {e_auto}"
+    out["fused_gather_max_abs_err_vs_oracle"] = e_auto
+    sp.pipe.enface_gather_auto(False)
+    dist.barrier()
     # ---- timing of the two gathers (device events, max over ranks) ----
     stream = torch.cuda.ExternalStream(int(sp.pipe._lib.octb200_compute_stream(sp.pipe.handle)), device=dev)
     loc = torch.empty(a * sp.count, dtype=torch.float32, device=dev)

@@ -55,6 +55,48 @@ def test_single_rank_gather_equals_enface_frame():
     p.cleanupCuda()
 
 
+@pytest.mark.parametrize("n,kw", [(1024, {}), (1024, dict(bscanFlip=True)), (2048, dict(bscanFlip=True)),
+                                  (1024, dict(bscanFlip=True, sinusoidalScanCorrection=True)),
+                                  (1024, dict(fixedPatternNoiseRemoval=True)), (1024, dict(resamplingInterpolation=2))])
+def test_automatic_gather_fused_into_the_epilogue(n, kw):
+    """octb200_enface_gather_auto: every process call gathers the frame -- inside the fused kernel when the slab is final
+    after it, by the appended stand-alone kernel otherwise (sinusoidal correction); both must equal octb200_enface_frame."""
+    import torch
+    a, b = 48, 5
+    q = benchmark_params(n, a, b); q.fixedPatternNoiseRemoval = False
+    for k, v in kw.items():
+        setattr(q, k, v)
+    q.update_all_curves()
+    raw = np.ascontiguousarray(synth.make_volume(n, a, b, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve))
+    p = OctPipeline(fft_mode=_lib.FFT_FUSED)
+    assert p.initializeCuda(None, None, copy.deepcopy(q)), getattr(p, "_create_error", "")
+    dev = torch.device("cuda", 0)
+    p.enface_gather_connect(p.enface_gather_init(0, 1, a * b, 0))
+    launches, cases = [], []
+    for (frame, nf, fn) in ((17, 1, 0), (n // 2 - 1, 1, 0), (40, 5, 0), (n // 2 - 3, 9, 0), (100, 40, 0), (60, 6, 1), (0, 70, 1)):
+        p.enface_gather_auto(True, frame, nf, fn)
+        l0 = p.launch_count()
+        p.octCudaPipeline(raw)
+        launches.append(p.launch_count() - l0); cases.append(nf)
+        ptr = p.enface_gather_wait(); p.sync()
+        got = _window_tensor(ptr, a * b, torch, dev).clone()
+        want = torch.empty(a * b, dtype=torch.float32, device=dev)
+        p.changeDisplayedEnFaceFrame(frame, nf, fn, want); p.sync()
+        if nf == 1 or fn == 1:
+            assert torch.equal(got, want), (frame, nf, fn)
+        else:       # averaging: tree sum in the kernel vs sequential sum in the frame kernel
+            assert torch.allclose(got, want, rtol=2e-6, atol=1e-6), (frame, nf, fn, float((got - want).abs().max()))
+    p.enface_gather_auto(False)
+    l0 = p.launch_count(); p.octCudaPipeline(raw); p.sync()
+    base = p.launch_count() - l0
+    sinus = bool(kw.get("sinusoidalScanCorrection"))
+    # one displayed depth frame: fused, no extra launch for the gather; multi-frame average / MIP or a later pass over the slab
+    # (sinusoidal correction): the stand-alone gather kernel is appended to the chain
+    assert all(l == base + (1 if (sinus or nf > 1) else 0) for l, nf in list(zip(launches, cases))[1:]), (launches, cases, base)
+    p.enface_gather_close()
+    p.cleanupCuda()
+
+
 def test_two_ranks_peer_gather_matches_nccl_and_oracle():
     import torch
     ngpu = torch.cuda.device_count()

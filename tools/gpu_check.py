@@ -197,6 +197,9 @@ def cmd_perf():
         d = [torch.from_numpy(raw.view(np.int16)).cuda(), torch.from_numpy(raw.view(np.int16).copy()).cuda()]
         p = OctPipeline(fft_mode=_lib.FFT_FUSED)
         assert p.initializeCuda(None, None, copy.deepcopy(q)), getattr(p, "_create_error", "")
+        if os.environ.get("OCTB200_AUTOGATHER"):
+            p.enface_gather_connect(p.enface_gather_init(0, 1, a * b, 0))
+            p.enface_gather_auto(True, 100, int(os.environ["OCTB200_AUTOGATHER"]), 0)
         p.process_device(d[0]); p.sync()
         for i in range(5):
             p.process_device(d[i & 1])
