@@ -218,6 +218,32 @@ OCTB200_API int octb200_enface_gather_auto(octb200_pipeline* p, int enable, uint
 OCTB200_API int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame);
 OCTB200_API int octb200_enface_gather_close(octb200_pipeline* p);
 
+/* ---------- dispersion-estimator sweep (octproz-dispersion-estimator-extension) ----------
+   Replaces the loop of DispersionEstimationEngine::processDispersionMetric (src/dispersionestimationengine.cpp:78-90,118-158),
+   which re-runs the CPU path (octprocessor/processor.tpp:241-321) once per trial coefficient, and
+   AscanMetricCalculator::calculateMetric (src/ascanmetriccalculator.cpp:22-128): ALL trials are processed by ONE launch of the
+   fused kernel (gridDim.y = trials, every trial reads the same center A-scans through its own window x phasor table) and one
+   metric kernel.  Stage settings (resampling + interpolation, windowing, rolling background removal, bitshift) and the resample /
+   window curves are the handle's; dispersion compensation is on with the trial coefficients; fixed-pattern-noise removal, flip,
+   sinusoidal correction and background removal do not exist in the CPU path and are not applied.  The A-scans are scaled in the
+   CPU path's units (processor.tpp:424-470), so thresholds mean what they mean in the reference.
+   raw: `lines` A-scans (host or device memory, u16 containers).  coeffs: trials x {d0, d1, d2, d3} (octalgorithmparameters.cpp:
+   dispersion polynomial).  metricsOut: host, `trials` floats.  ascansOut: NULL or host [trials][lines][samplesPerLine/2]. */
+enum { OCTB200_METRIC_SUM_ABOVE_THRESHOLD = 0, OCTB200_METRIC_SAMPLES_ABOVE_THRESHOLD = 1, OCTB200_METRIC_PEAK_VALUE = 2,
+       OCTB200_METRIC_MEAN_SOBEL = 3 };                /* ASCAN_SHARPNESS_METRIC, dispersionestimatorparameters.h:51-56 */
+typedef struct {
+	uint32_t lines;            /* numberOfCenterAscans */
+	uint32_t trials;           /* numberOfDispersionSamples (<= 65535) */
+	int32_t  metric;           /* OCTB200_METRIC_* */
+	float    metricThreshold;
+	int32_t  samplesToIgnore;  /* numberOfAscanSamplesToIgnore */
+	int32_t  logScale;         /* !useLinearAscans (dispersionestimationengine.cpp:29-33) */
+	float    logMin, logMax, logCoeff, logAddend;      /* processorcontroller.cpp:85-89 */
+	uint32_t reserved[4];
+} octb200_sweep_config;
+OCTB200_API int octb200_dispersion_sweep(octb200_pipeline* p, const void* raw, const octb200_sweep_config* cfg, const float* coeffs,
+                                         float* metricsOut, float* ascansOut);
+
 /* ---------- timing helpers (CUDA events on the pipeline's compute stream) ---------- */
 OCTB200_API void* octb200_compute_stream(octb200_pipeline* p);           /* cudaStream_t as void* */
 OCTB200_API int octb200_event_record(octb200_pipeline* p, int slot);     /* slot 0..7 */

@@ -27,7 +27,7 @@ SYMBOLS = [
     "octb200_volume_u8", "octb200_float_to_output", "octb200_compute_stream", "octb200_event_record",
     "octb200_event_elapsed_ms", "octb200_launch_count", "octb200_time_kernel",
     "octb200_enface_gather_init", "octb200_enface_gather_connect", "octb200_enface_gather", "octb200_enface_gather_wait",
-    "octb200_enface_gather_close", "octb200_enface_gather_auto",
+    "octb200_enface_gather_close", "octb200_enface_gather_auto", "octb200_dispersion_sweep",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -57,6 +57,13 @@ class Params(C.Structure):
                 ("reserved", C.c_uint32 * 3)]
 
 
+class SweepConfig(C.Structure):
+    _fields_ = [("lines", C.c_uint32), ("trials", C.c_uint32), ("metric", C.c_int32), ("metricThreshold", C.c_float),
+                ("samplesToIgnore", C.c_int32), ("logScale", C.c_int32), ("logMin", C.c_float), ("logMax", C.c_float),
+                ("logCoeff", C.c_float), ("logAddend", C.c_float), ("reserved", C.c_uint32 * 4)]
+
+
+METRIC_SUM_ABOVE_THRESHOLD, METRIC_SAMPLES_ABOVE_THRESHOLD, METRIC_PEAK_VALUE, METRIC_MEAN_SOBEL = 0, 1, 2, 3
 HOST_CALLBACK = C.CFUNCTYPE(None, C.c_void_p)
 
 _lib = None
@@ -123,5 +130,6 @@ def load() -> C.CDLL:
     lib.octb200_enface_gather_auto.argtypes = [P, C.c_int, C.c_uint32, C.c_uint32, C.c_int]
     lib.octb200_enface_gather_wait.argtypes = [P, C.POINTER(C.c_void_p)]
     lib.octb200_enface_gather_close.argtypes = [P]
+    lib.octb200_dispersion_sweep.argtypes = [P, C.c_void_p, C.POINTER(SweepConfig), C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib

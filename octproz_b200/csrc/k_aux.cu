@@ -399,6 +399,43 @@ cudaError_t launch_enface_wait(const unsigned* flags, int world, unsigned seq, c
 	return cudaGetLastError();
 }
 
+/* ------------------------------------------------------------------ dispersion sweep: A-scan sharpness metric per trial
+ * AscanMetricCalculator::calculateMetric (octproz-dispersion-estimator-extension/src/ascanmetriccalculator.cpp:22-128) on the
+ * [trials][lines][H] outputs of one sweep launch.  One block per trial, one thread per line; every sum runs in the reference's
+ * order (samples ascending inside a line, then lines ascending), so the value is the reference's for the same processed data. */
+__global__ void __launch_bounds__(128) sweep_metric_kernel(float* __restrict__ metrics, const float* __restrict__ data, int lines, int H,
+                                                          int metric, float thr, int ignore) {
+	extern __shared__ float lineMetric[];
+	const float* trial = data + (size_t)blockIdx.x * lines * H;
+	int ig = ignore;
+	if (ig > 0) ig = ig < H ? ig : H;                      /* clamp, ascanmetriccalculator.cpp:39-41 */
+	const int valid = H - ig;
+	for (int l = threadIdx.x; l < lines; l += blockDim.x) {
+		const float* d = trial + (size_t)l * H + ig;
+		float m = 0.0f;
+		if (valid > 0) {
+			if (metric == 0) { for (int i = 0; i < valid; ++i) { const float v = d[i]; if (v > thr) m += v; } }
+			else if (metric == 1) { int c = 0; for (int i = 0; i < valid; ++i) if (d[i] > thr) ++c; m = (float)c; }
+			else if (metric == 2) { for (int i = 0; i < valid; ++i) m = fmaxf(m, d[i]); }
+			else if (metric == 3 && valid >= 3) {
+				float s = 0.0f; int c = 0;
+				for (int i = 1; i < valid - 1; ++i) { s += fabsf((d[i + 1] - d[i - 1]) * 0.5f); ++c; }
+				m = c > 0 ? s / (float)c : 0.0f;
+			}
+		}
+		lineMetric[l] = (valid > 0) ? m : 0.0f;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		float total = 0.0f;
+		for (int l = 0; l < lines; ++l) total += lineMetric[l];
+		metrics[blockIdx.x] = total;
+	}
+}
+cudaError_t launch_sweep_metric(float* metrics, const float* data, int trials, int lines, int H, int metric, float thr, int ignore, cudaStream_t st) {
+	sweep_metric_kernel<<<trials, 128, (size_t)lines * sizeof(float), st>>>(metrics, data, lines, H, metric, thr, ignore);
+	return cudaGetLastError();
+}
 /* u8 voxels in the layout of the GL_R8 3-D texture (x = A-scan, y = B-scan in volume, z flipped depth), cuda_code.cu:928-940 */
 __global__ void __launch_bounds__(256) volume_u8_kernel(uint8_t* __restrict__ tex, const float* __restrict__ buf, long long samples,
                                                          unsigned bufferNr, unsigned B, unsigned A, unsigned Btot, unsigned depth) {

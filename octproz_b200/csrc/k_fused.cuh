@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 	const uint32_t tq = tmemBase + ((uint32_t)(warp & 3) << 21);     /* lane quadrant of this warp: lane field = bits 31:16, 32 lanes per quadrant */
 	{
 		const int nWarps = blockDim.x >> 5, quadrant = warp & 3;
-		tmem_fill<R>(tq, quadrant, warp >> 2, (nWarps - quadrant + 3) >> 2, lane, a, SRC == SRC_RAW16);
+		tmem_fill<R>(tq, quadrant, warp >> 2, (nWarps - quadrant + 3) >> 2, lane, a, a.lutB + (size_t)blockIdx.y * a.trialLutStride, SRC == SRC_RAW16);
 	}
 	tmem_fence_before_sync();
 	__syncthreads();
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 			uint4* d = reinterpret_cast<uint4*>(smem + off);
 			for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
 		};
-		if constexpr (SRC == SRC_RAW16) fill(L.offB, a.lutB, 2 * N * 16);
+		if constexpr (SRC == SRC_RAW16) fill(L.offB, a.lutB + (size_t)blockIdx.y * a.trialLutStride, 2 * N * 16);
 		fill(L.offTw, a.tw, 1024 * 8);
 		if constexpr (R == 2) fill(L.offCtw, a.ctw, 1024 * 8);
 		if (a.epi.fpn && a.cplxOut == nullptr) fill(L.offMean, a.meanLine, H * 8);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(
 		} else {
 			int b = gline / a.A, al = gline - b * a.A;
 			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u) al = a.A - 1 - al;
-			float* o = a.out + ((size_t)b * a.A + al) * H;
+			float* o = a.out + (size_t)blockIdx.y * a.trialOutStride + ((size_t)b * a.A + al) * H;
 #if OCT_TMEM_LUT
 			float egVal = 0.f;
 			if (R == 1 || p == 0) epilogue_tmem<R, 0>(lane, v, a.epi, tq, o, egK2, egVal); else epilogue_tmem<R, 16>(lane, v, a.epi, tq, o, egK2, egVal);

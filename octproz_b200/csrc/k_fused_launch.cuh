@@ -24,7 +24,7 @@ cudaError_t launch_fused_t(const FusedArgs& a, int smCount, cudaStream_t st) {
 	const int maxGrid = (a.lines + groups - 1) / groups;
 	if (grid > maxGrid) grid = maxGrid;
 	if (grid < 1) grid = 1;
-	k<<<grid, groups * R * 32, L.total, st>>>(a);
+	k<<<dim3(grid, a.trials > 1 ? a.trials : 1), groups * R * 32, L.total, st>>>(a);
 	return cudaGetLastError();
 }
 

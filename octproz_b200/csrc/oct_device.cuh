@@ -96,6 +96,10 @@ struct FusedArgs {
 	int W;
 	int HB, HA;
 	GatherDev eg;            /* eg.world == 0: no en-face gather in this launch */
+	/* dispersion sweep (gridDim.y = trials): trial t = blockIdx.y processes the SAME lines with its own stage LUT and writes its own output slab */
+	int trials;              /* 0 / 1: plain launch */
+	int trialLutStride;      /* float4 elements between the LUT images of consecutive trials */
+	long long trialOutStride;/* floats between the output slabs of consecutive trials */
 };
 
 enum { SRC_RAW16 = 0, SRC_CPLX = 1 };

@@ -106,7 +106,7 @@ __device__ __forceinline__ void tmem_st_f4(uint32_t taddr, float4 a) {
  * All global loads of a phase are issued before the first tensor-memory store, so the fill costs two memory latencies instead of
  * one per row (it used to be ~7 % of the kernel: 50 dependent L2 round trips by 4 warps while 12 waited at the barrier). */
 template <int R>
-__device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int quadrant, int part, int parts, int lane, const FusedArgs& a, bool haveLut) {
+__device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int quadrant, int part, int parts, int lane, const FusedArgs& a, const float4* lutB, bool haveLut) {
 	using M = TmemMap<R>;
 	constexpr int HN = 512 * R;
 	const int p = (R == 2) ? (quadrant & 1) : 0;         /* the sub-sequence whose warps read this quadrant */
@@ -118,7 +118,7 @@ __device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int q
 				const int jj = base + u * parts;
 				if (jj < 16) {
 					const int e = p * 512 + lane + 32 * jj;
-					b[u][0] = __ldg(a.lutB + e); b[u][1] = __ldg(a.lutB + HN + e); b[u][2] = __ldg(a.lutB + 2 * HN + e); b[u][3] = __ldg(a.lutB + 3 * HN + e);
+					b[u][0] = __ldg(lutB + e); b[u][1] = __ldg(lutB + HN + e); b[u][2] = __ldg(lutB + 2 * HN + e); b[u][3] = __ldg(lutB + 3 * HN + e);
 				}
 			}
 #pragma unroll

@@ -101,6 +101,13 @@ struct octb200_pipeline {
 	octb200_host_callback cbStreaming = nullptr, cbFloat = nullptr, cbBackground = nullptr;
 	unsigned long long launches = 0;
 
+	/* dispersion sweep scratch (grown on demand) */
+	unsigned char* dSweepRaw = nullptr; size_t sweepRawBytes = 0;
+	float4* dSweepLut = nullptr; size_t sweepLutElems = 0;
+	float* dSweepOut = nullptr; size_t sweepOutElems = 0;
+	float* dSweepPhase = nullptr; float2* dSweepPhasor = nullptr; size_t sweepPhaseElems = 0;
+	float* dSweepMetric = nullptr; size_t sweepMetricElems = 0;
+
 	/* en-face gather over peer memory (multi-GPU shards): local window = [64 flag words][frame 0][frame 1] */
 	struct EnfaceGather {
 		int world = 0, rank = 0;
@@ -138,6 +145,14 @@ template <typename T> int dalloc(octb200_pipeline* p, T** ptr, size_t count) {
 	return OCTB200_OK;
 }
 template <typename T> void dfree(T*& ptr) { if (ptr) { cudaFree(ptr); ptr = nullptr; } }
+/* scratch that only ever grows */
+template <typename T> int grow(octb200_pipeline* p, T*& ptr, size_t& have, size_t want) {
+	if (have >= want) return OCTB200_OK;
+	dfree(ptr); have = 0;
+	int rc = dalloc(p, &ptr, want);
+	if (rc == OCTB200_OK) have = want;
+	return rc;
+}
 
 /* pin a caller-owned host buffer unless the caller already did (cudaHostAlloc / cudaHostRegister / torch pin_memory).
  * *mine tells whether we have to unpin it later. */
@@ -535,6 +550,7 @@ int octb200_destroy(octb200_pipeline* p) {
 	dfree(p->dTw); dfree(p->dCtw); dfree(p->dSinCurve);
 	for (void*& c : p->dOutConv) { if (c) cudaFree(c); c = nullptr; }
 	octb200_enface_gather_close(p);
+	dfree(p->dSweepRaw); dfree(p->dSweepLut); dfree(p->dSweepOut); dfree(p->dSweepPhase); dfree(p->dSweepPhasor); dfree(p->dSweepMetric);
 	if (p->sCompute) cudaStreamDestroy(p->sCompute);
 	if (p->sH2D) cudaStreamDestroy(p->sH2D);
 	if (p->sD2H) cudaStreamDestroy(p->sD2H);
@@ -844,6 +860,88 @@ int octb200_enface_gather_close(octb200_pipeline* p) {
 	}
 	dfree(g.window); dfree(g.counter);
 	g.connected = false; g.world = 0; g.seq = 0; g.autoOn = false;
+	return OCTB200_OK;
+}
+
+/* ---------------- dispersion-estimator sweep ---------------- */
+int octb200_dispersion_sweep(octb200_pipeline* p, const void* raw, const octb200_sweep_config* c, const float* coeffs, float* metricsOut, float* ascansOut) {
+	if (!p || !raw || !c || !coeffs || !metricsOut) return fail(p, OCTB200_ERR_INVALID, "null argument");
+	if (c->lines < 1 || c->trials < 1 || c->trials > 65535 || c->metric < 0 || c->metric > 3) return fail(p, OCTB200_ERR_INVALID, "bad sweep configuration");
+	if (!(p->N == 1024 || p->N == 2048) || p->rawBytes != 2)
+		return fail(p, OCTB200_ERR_INVALID, "the dispersion sweep runs on the fused kernel: 1024 or 2048 samples per line in a 16-bit container");
+	if (c->logScale && !(c->logMax != c->logMin)) return fail(p, OCTB200_ERR_INVALID, "log scaling needs max != min");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	const octb200_params& q = p->prm;
+	const Stage st = select_stage(p);
+	if (q.resampling && !p->haveResample) return fail(p, OCTB200_ERR_NOT_READY, "resampling enabled but no resample curve set");
+	if (q.windowing && !p->haveWindow) return fail(p, OCTB200_ERR_NOT_READY, "windowing enabled but no window curve set");
+	const int N = p->N, H = p->H, K = (int)c->trials, L = (int)c->lines;
+
+	/* launch shape first: a stage that does not fit the fused kernel cannot be swept */
+	{
+		int g = 0, t = 0, sm = 0;
+		fused_launch_shape(p->R, st.sa, st.roll, SRC_RAW16, st.HB, st.HA, p->smCount, L, &g, &t, &sm);
+		if (t < 32 * p->R) return fail(p, OCTB200_ERR_INVALID, "this rolling window / interpolation does not fit the fused kernel");
+	}
+	int rc;
+	const size_t rawBytes = (size_t)L * N * 2;
+	if ((rc = grow(p, p->dSweepRaw, p->sweepRawBytes, rawBytes + 64))) return rc;
+	if ((rc = grow(p, p->dSweepLut, p->sweepLutElems, (size_t)K * 2 * N))) return rc;
+	if ((rc = grow(p, p->dSweepOut, p->sweepOutElems, (size_t)K * L * H))) return rc;
+	if (p->sweepPhaseElems < (size_t)K * N) { dfree(p->dSweepPhase); dfree(p->dSweepPhasor); p->sweepPhaseElems = 0; }
+	if (!p->dSweepPhase) {
+		if ((rc = dalloc(p, &p->dSweepPhase, (size_t)K * N))) return rc;
+		if ((rc = dalloc(p, &p->dSweepPhasor, (size_t)K * N))) return rc;
+		p->sweepPhaseElems = (size_t)K * N;
+	}
+	if ((rc = grow(p, p->dSweepMetric, p->sweepMetricElems, (size_t)K))) return rc;
+
+	/* raw center A-scans: host or device memory */
+	CK(p, cudaMemcpyAsync(p->dSweepRaw, raw, rawBytes, cudaMemcpyDefault, p->sCompute));
+
+	/* trial phase curves = OctAlgorithmParameters::updateDispersionCurve with (d0, d1, d2_k, d3_k); phasors on the device like
+	   fillDispersivePhase, then one stage-LUT image per trial */
+	std::vector<float> phase((size_t)K * N);
+	for (int k = 0; k < K; ++k) curves::dispersion(N, coeffs[4 * k], coeffs[4 * k + 1], coeffs[4 * k + 2], coeffs[4 * k + 3], phase.data() + (size_t)k * N);
+	CK(p, cudaMemcpyAsync(p->dSweepPhase, phase.data(), sizeof(float) * K * N, cudaMemcpyHostToDevice, p->sCompute));
+	launch_fill_phase(p->dSweepPhasor, p->dSweepPhase, K * N, p->sCompute); p->launches++;
+	std::vector<float2> phasor((size_t)K * N);
+	CK(p, cudaMemcpyAsync(phasor.data(), p->dSweepPhasor, sizeof(float2) * K * N, cudaMemcpyDeviceToHost, p->sCompute));
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	const float* res = q.resampling ? p->hResample.data() : nullptr;
+	const float* win = q.windowing ? p->hWindow.data() : nullptr;
+	std::vector<float4> luts((size_t)K * 2 * N), one;
+	for (int k = 0; k < K; ++k) {
+		build_stage_luts_paired(N, p->R, q.resamplingInterpolation == OCTB200_INTERP_CUBIC ? 1 : 0, res, win, phasor.data() + (size_t)k * N, one);
+		std::memcpy(luts.data() + (size_t)k * 2 * N, one.data(), sizeof(float4) * 2 * N);
+	}
+	CK(p, cudaMemcpyAsync(p->dSweepLut, luts.data(), sizeof(float4) * luts.size(), cudaMemcpyHostToDevice, p->sCompute));
+
+	/* ONE launch for all trials: gridDim.y = trials, every trial reads the same raw lines through its own LUT */
+	FusedArgs fa{};
+	fa.raw = reinterpret_cast<const uint16_t*>(p->dSweepRaw);
+	fa.lutB = p->dSweepLut; fa.tw = p->dTw; fa.ctw = p->dCtw; fa.meanLine = p->dMeanLine; fa.ppbg = p->dPpbg;
+	fa.totalSamples = (long long)L * N; fa.lines = L; fa.A = L;
+	fa.flip = 0; fa.bscanBase = 0; fa.shiftBits = q.bitshift ? 4 : 0; fa.W = st.W; fa.HB = st.HB; fa.HA = st.HA;
+	fa.out = p->dSweepOut;
+	fa.trials = K; fa.trialLutStride = 2 * N; fa.trialOutStride = (long long)L * H;
+	/* output in the units of the reference's CPU path (processor.tpp:424-470): IFFT normalised by 1/N;
+	   log: coeff * ((10 log10(|x|^2 / N) - min) / (max - min) + addend); linear: |x| */
+	EpiConsts e; std::memset(&e, 0, sizeof(e));
+	e.logMode = c->logScale ? 1 : 0;
+	if (c->logScale) {
+		const double range = (double)c->logMax - (double)c->logMin;
+		e.scaleA = (float)((double)c->logCoeff * 10.0 * std::log10(2.0) / range);
+		e.scaleB = (float)((double)c->logCoeff * ((-30.0 * std::log10((double)N) - (double)c->logMin) / range + (double)c->logAddend));
+	} else {
+		e.scaleA = (float)(1.0 / (double)N); e.scaleB = 0.0f;
+	}
+	fa.epi = e;
+	CK(p, launch_fused(p->R, st.sa, st.roll, SRC_RAW16, fa, p->smCount, p->sCompute)); p->launches++;
+	CK(p, launch_sweep_metric(p->dSweepMetric, p->dSweepOut, K, L, H, c->metric, c->metricThreshold, c->samplesToIgnore, p->sCompute)); p->launches++;
+	CK(p, cudaMemcpyAsync(metricsOut, p->dSweepMetric, sizeof(float) * K, cudaMemcpyDeviceToHost, p->sCompute));
+	if (ascansOut) CK(p, cudaMemcpyAsync(ascansOut, p->dSweepOut, sizeof(float) * (size_t)K * L * H, cudaMemcpyDeviceToHost, p->sCompute));
+	CK(p, cudaStreamSynchronize(p->sCompute));
 	return OCTB200_OK;
 }
 

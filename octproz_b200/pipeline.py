@@ -168,6 +168,30 @@ class OctPipeline:
     def enface_gather_close(self) -> None:
         self._ck(self._lib.octb200_enface_gather_close(self._h), "enface_gather_close")
 
+    # ------------------------------------------------------------------ dispersion-estimator sweep (include/octb200.h)
+    def dispersion_sweep(self, raw, coeffs, metric: int, threshold: float, samples_to_ignore: int, log_scale: bool,
+                         log_min: float = 0.0, log_max: float = 100.0, log_coeff: float = 1.0, log_addend: float = 0.0,
+                         want_ascans: bool = False):
+        """all trial coefficient sets {d0, d1, d2, d3} on the same A-scans in ONE launch of the fused kernel + one metric kernel
+        (replaces the per-trial CPU re-run of dispersionestimationengine.cpp:118-158).  raw: [lines][N] u16 (numpy or device tensor).
+        Returns metrics [trials] (and the A-scans [trials][lines][N/2] in the CPU path's units when asked)."""
+        self.push_params()
+        n = int(self.params.samplesPerLine)
+        co = np.ascontiguousarray(coeffs, np.float32).reshape(-1, 4)
+        if isinstance(raw, np.ndarray):
+            raw = np.ascontiguousarray(raw)
+            lines = raw.size // n
+        else:
+            lines = int(raw.numel()) // n
+        cfg = _lib.SweepConfig(lines=lines, trials=co.shape[0], metric=int(metric), metricThreshold=float(threshold),
+                               samplesToIgnore=int(samples_to_ignore), logScale=int(bool(log_scale)), logMin=float(log_min),
+                               logMax=float(log_max), logCoeff=float(log_coeff), logAddend=float(log_addend))
+        metrics = np.empty(co.shape[0], np.float32)
+        ascans = np.empty((co.shape[0], lines, n // 2), np.float32) if want_ascans else None
+        self._ck(self._lib.octb200_dispersion_sweep(self._h, _ptr(raw), C.byref(cfg), co.ctypes.data, metrics.ctypes.data,
+                                                    ascans.ctypes.data if ascans is not None else None), "dispersion_sweep")
+        return (metrics, ascans) if want_ascans else metrics
+
     # ------------------------------------------------------------------ results
     def output_ptr(self, buffer_nr: int = 0) -> int:
         return int(self._lib.octb200_output_device_ptr(self._h, buffer_nr) or 0)

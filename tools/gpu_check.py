@@ -221,5 +221,43 @@ def cmd_perf():
     json.dump(res, open(os.path.join(OUT, f"perf_{tag}.json"), "w"), indent=1)
 
 
+def cmd_estimator():
+    """dispersion estimator: GPU sweep (two launches per coefficient) vs the reference's CPU path re-run per trial"""
+    import time as _t
+    from octproz_b200.dispersion_estimator import DispersionEstimationEngine, DispersionEstimatorParameters, PEAK_VALUE
+    from oracle import estimator_oracle as eo
+    n, lines, trials = 1024, 512, 100
+    q = benchmark_params(n, lines, 1); q.update_all_curves()
+    raw = synth.make_volume(n, lines, 1, 12, resample=q.resampleCurve, dispersion=-q.dispersionCurve).reshape(lines, n)
+    p = OctPipeline(fft_mode=_lib.FFT_FUSED)
+    assert p.initializeCuda(None, None, q)
+    res = {}
+    for center in (10, 100):
+        eng = DispersionEstimationEngine(p)
+        prm = DispersionEstimatorParameters(numberOfCenterAscans=center, useLinearAscans=True, numberOfAscanSamplesToIgnore=15, sharpnessMetric=PEAK_VALUE,
+                                            d2start=-150.0, d2end=-50.0, d3start=-20.0, d3end=20.0, numberOfDispersionSamples=trials)
+        eng.setParams(prm)
+        eng.startDispersionEstimation(raw, 12, n, lines)
+        t0 = _t.perf_counter(); r = eng.startDispersionEstimation(raw, 12, n, lines); t_gpu = _t.perf_counter() - t0
+        off, cnt = eo.center_lines(lines, center)
+        block = raw[off:off + cnt]
+        rc = orc.RefCpu()
+
+        def ref_trials(pairs):
+            out = []
+            for d2, d3 in pairs:
+                qq = copy.copy(q); qq.d2, qq.d3 = float(d2), float(d3); qq.signalLogScaling = False; qq.ascansPerBscan = cnt
+                out.append(eo.ref_metric(rc.process(qq, block, threads=1), n // 2, eo.PEAK_VALUE, 0.0, 15))
+            return out
+        t0 = _t.perf_counter()
+        w = eo.estimate(ref_trials, dict(numberOfDispersionSamples=trials, d2start=-150.0, d2end=-50.0, d3start=-20.0, d3end=20.0))
+        t_cpu = _t.perf_counter() - t0
+        res[f"center{center}"] = {"gpu_s": t_gpu, "reference_cpu_s": t_cpu, "speedup": t_cpu / t_gpu, "best_gpu": [r["bestD2"], r["bestD3"]],
+                                  "best_reference": [w["bestD2"], w["bestD3"]], "trials_per_coefficient": trials}
+        print("estimator", center, json.dumps(res[f"center{center}"]), flush=True)
+    json.dump(res, open(os.path.join(OUT, "estimator.json"), "w"), indent=1)
+    p.cleanupCuda()
+
+
 if __name__ == "__main__":
-    {"perf": cmd_perf, "quick": cmd_quick, "parity": cmd_parity, "refcuda": cmd_refcuda, "timing": cmd_timing}[sys.argv[1]]()
+    {"estimator": cmd_estimator, "perf": cmd_perf, "quick": cmd_quick, "parity": cmd_parity, "refcuda": cmd_refcuda, "timing": cmd_timing}[sys.argv[1]]()
