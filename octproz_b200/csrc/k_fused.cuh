@@ -34,11 +34,19 @@ namespace octb200 {
 #define OCT_R1_THREADS 512
 #endif
 #ifndef OCT_R2_THREADS
-#define OCT_R2_THREADS 384
+#define OCT_R2_THREADS 512
 #endif
+/* threads per CTA (one CTA per SM): 16 warps x 128 registers fill the register file.  R = 2 used to run 12 warps at 168 registers;
+ * after the table reads moved to tensor memory its cubic / linear / plain variants need 124, so they run 16 warps as well
+ * (8 line groups instead of 6).  The 16-tap Lanczos stage keeps 12 warps: at 128 registers it spills. */
+#ifndef OCT_R2_THREADS_LANCZOS
+#define OCT_R2_THREADS_LANCZOS 384
+#endif
+constexpr int fused_max_threads(int R, int sa) {
+	return (R == 1) ? OCT_R1_THREADS : (sa == 2 /* SA_LANCZOS */ ? OCT_R2_THREADS_LANCZOS : OCT_R2_THREADS);
+}
 template <int R> struct FusedCfg {
 	static constexpr int N = 1024 * R;
-	static constexpr int MAX_THREADS = (R == 1) ? OCT_R1_THREADS : OCT_R2_THREADS;
 };
 
 /* shared-memory layout, shared by host (sizing) and device (carving) */
@@ -108,7 +116,7 @@ __device__ __forceinline__ void issue_line_load(const FusedArgs& a, int gline, u
 }
 
 template <int R, int SA, bool ROLL, int SRC>
-__global__ void __launch_bounds__(FusedCfg<R>::MAX_THREADS, 1) oct_fused_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(const FusedArgs a) {
 	constexpr int N = 1024 * R;
 	constexpr int H = N / 2;
 	/* halos exist only for the 16-tap Lanczos stage: compile-time zero otherwise */

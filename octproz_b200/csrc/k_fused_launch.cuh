@@ -5,7 +5,7 @@
 namespace octb200 {
 
 inline int fused_pick_groups(int R, int sa, bool roll, int src, int HB, int HA) {
-	const int maxThreads = (R == 1) ? FusedCfg<1>::MAX_THREADS : FusedCfg<2>::MAX_THREADS;
+	const int maxThreads = fused_max_threads(R, sa);
 	int groups = maxThreads / 32 / R;
 	while (groups > 0 && fused_smem_layout(R, sa, roll, src, HB, HA, groups).total > 227 * 1024) --groups;
 	if (R == 2 && groups > 15) groups = 15;     /* named barriers 1..15 */
