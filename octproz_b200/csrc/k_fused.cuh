@@ -330,18 +330,8 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 #else
 	__syncthreads();
 #endif
-	if (a.eg.world > 0 && threadIdx.x == 0) {
-		/* the last CTA to arrive publishes this rank's sequence number in every rank's flag word.  One system-scope fence by
-		 * this thread after the CTA barrier orders the peer stores of ALL its threads before the arrival (fence cumulativity:
-		 * the pattern of a grid-wide barrier) -- a fence per storing thread cost 4 % of the kernel */
-		__threadfence_system();
-		const unsigned done = atomicAdd(a.eg.counter, 1u);
-		if (done == gridDim.x - 1) {
-			*a.eg.counter = 0;
-			__threadfence_system();
-			for (int r = 0; r < a.eg.world; ++r) st_release_sys_u32(a.eg.flags[r] + a.eg.rank, a.eg.seq);
-		}
-	}
+	if (a.eg.world > 0) gather_push_and_publish(a.eg, (unsigned)a.lines);
+
 }
 
 }  // namespace octb200
