@@ -207,8 +207,10 @@ constexpr int bitrev_n(int g, int bits) {
  * Input  v[j] = x[j],  output v[r] = X[bitrev5(r)]  (same maps as fft32_inv_dif).
  * Unused outputs (the pruned upper half of the spectrum) are removed by dead-code elimination.
  */
+template <bool SKIP0 = false>
 OCT_HD void fft32_inv_dit(float2 (&v)[32]) {
-	static_for<0, 5>([&](auto sc) {
+	/* SKIP0: the caller has already formed v[j] +- v[j + 16] (stage A folds that butterfly into its window x phasor product) */
+	static_for<(SKIP0 ? 1 : 0), 5>([&](auto sc) {
 		constexpr int s = decltype(sc)::value;
 		constexpr int half = 16 >> s;
 		static_for<0, (1 << s)>([&](auto gc) {
@@ -224,11 +226,15 @@ OCT_HD void fft32_inv_dit(float2 (&v)[32]) {
 }
 
 /* the network the kernels use (OCT_FFT_DIF selects the plain multiply-then-butterfly form for A/B builds) */
+template <bool SKIP0 = false>
 OCT_HD void fft32_inv(float2 (&v)[32]) {
 #ifdef OCT_FFT_DIF
+	if constexpr (SKIP0) {      /* A/B builds: redo nothing, the first DIF stage has a twiddle -- not supported together */
+		static_assert(!SKIP0, "OCT_FFT_DIF cannot skip stage 0");
+	}
 	fft32_inv_dif(v);
 #else
-	fft32_inv_dit(v);
+	fft32_inv_dit<SKIP0>(v);
 #endif
 }
 

@@ -283,8 +283,8 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			for (int j = 0; j < 32; ++j) v[j] = __ldg(in + R * (lane + 32 * j) + p);
 		}
 
-		/* ---- 1024-point inverse FFT of this warp's sub-sequence ---- */
-		fft32_inv(v);
+		/* ---- 1024-point inverse FFT of this warp's sub-sequence (first butterfly stage already done by the 4-tap stage A) ---- */
+		fft32_inv<SRC == SRC_RAW16 && stage_a_fuses_stage0(SA)>(v);
 #if OCT_TMEM_LUT
 		exchange_store_tmem<R>(lane, v, tile, tq);
 #else

@@ -72,7 +72,7 @@ inline void build_stage_luts_paired(int N, int R, int interp, const float* resam
 	for (int p = 0; p < R; ++p)
 		for (int jj = 0; jj < 16; ++jj)
 			for (int lane = 0; lane < 32; ++lane) {
-				const int sa = lane + 64 * jj, sb = sa + 32;               /* rows j = 2jj and 2jj+1 */
+				const int sa = lane + 32 * jj, sb = sa + 512;              /* rows j = jj and jj + 16: the two inputs of the first FFT butterfly */
 				const float4 A = nat.B[(size_t)R * sa + p], B = nat.B[(size_t)R * sb + p];
 				float wa[4], wb[4];
 				tap_weights(interp, A.w, wa); tap_weights(interp, B.w, wb);

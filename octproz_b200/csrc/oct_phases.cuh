@@ -106,9 +106,14 @@ OCT_HD void sample_taps4_x2(const float* f, int oa, int ob, float2 W0, float2 W1
 	const float2 Y2 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4));
 	const float2 Y3 = make_float2(ldf(f, oa + 8), ldf(f, ob + 8));
 	const float2 y = pfma(W3, Y3, pfma(W2, Y2, pfma(W1, Y1, pmul(W0, Y0))));
-	outA = cscale(wa, y.x);
-	outB = cscale(wb, y.y);
+	/* the two samples are rows j and j + 16 of the lane: their first (twiddle-free) FFT butterfly is folded into the window x
+	 * phasor product -- out(j) = wa ya + wb yb, out(j+16) = wa ya - wb yb: 3 packed instructions instead of 4 */
+	const float2 t = cscale(wa, y.x);
+	outA = pfma(wb, make_float2(y.y, y.y), t);
+	outB = pfma(wb, make_float2(-y.y, -y.y), t);
 }
+/* stage A of these selectors leaves v[j] +- v[j+16] in the registers: the FFT skips its first stage */
+OCT_HD constexpr bool stage_a_fuses_stage0(int sa) { return sa == 3 /* SA_CUBIC */ || sa == 1 /* SA_LINEAR */; }
 
 OCT_HD float2 sample_none(const float* f, int m, float4 B) {
 	const float y = f[m];
@@ -143,7 +148,7 @@ OCT_HD float2 sample_lanczos(const float* f, int shift, float4 B) {
 }
 
 /* ---- stage A for one lane: 32 samples s = lane + 32 j of sub-sequence p (m = R*s + p) ----
- * LUT ("paired" layout, build_stage_luts_paired): rows j = 2jj and 2jj+1 of a lane share four float4s, stored as four planes
+ * LUT ("paired" layout, build_stage_luts_paired): rows j = jj and jj + 16 of a lane share four float4s, stored as four planes
  * of N/2 entries, entry e = p*512 + lane + 32 jj:
  *   P[e] = { wPx_a, wPy_a, wPx_b, wPy_b }   Q[e] = { off_a, off_b, t_a, t_b }   W01[e] = { w0a, w0b, w1a, w1b }   W23[e] = { w2a, w2b, w3a, w3b }
  * so every packed operand is an aligned register pair straight out of a 128-bit read. */
@@ -162,14 +167,14 @@ OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lu
 		if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
 			const float4 Wa = W01[lane + 32 * jj], Wb = W23[lane + 32 * jj];
 			sample_taps4_x2(f, lut_int(Qq.x), lut_int(Qq.y), make_float2(Wa.x, Wa.y), make_float2(Wa.z, Wa.w),
-			                make_float2(Wb.x, Wb.y), make_float2(Wb.z, Wb.w), wa, wb, v[2 * jj], v[2 * jj + 1]);
+			                make_float2(Wb.x, Wb.y), make_float2(Wb.z, Wb.w), wa, wb, v[jj], v[jj + 16]);
 		} else if constexpr (SA == SA_NONE) {
-			const int s = lane + 64 * jj;
-			v[2 * jj] = cscale(wa, f[R * s + p]);
-			v[2 * jj + 1] = cscale(wb, f[R * (s + 32) + p]);
+			const int s = lane + 32 * jj;
+			v[jj] = cscale(wa, f[R * s + p]);
+			v[jj + 16] = cscale(wb, f[R * (s + 512) + p]);
 		} else {
-			v[2 * jj] = sample_lanczos(f, shift, make_float4(Qq.x, Pq.x, Pq.y, Qq.z));
-			v[2 * jj + 1] = sample_lanczos(f, shift, make_float4(Qq.y, Pq.z, Pq.w, Qq.w));
+			v[jj] = sample_lanczos(f, shift, make_float4(Qq.x, Pq.x, Pq.y, Qq.z));
+			v[jj + 16] = sample_lanczos(f, shift, make_float4(Qq.y, Pq.z, Pq.w, Qq.w));
 		}
 	}
 }

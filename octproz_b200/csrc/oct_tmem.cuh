@@ -10,7 +10,7 @@
  * No tensor-core MMA is involved -- TMEM is used as what it physically is, a big lane-private register-file extension.
  *
  * Column map of one lane quadrant (512 columns allocated):
- *   [0,256)   stage LUT: 16 row pairs x 16 words { off_a off_b w0a w0b w1a w1b t_a t_b | w2a w2b w3a w3b wP_a wP_b }
+ *   [0,256)   stage LUT: 16 row pairs (rows j and j + 16) x 16 words { off_a off_b w0a w0b w1a w1b t_a t_b | w2a w2b w3a w3b wP_a wP_b }
  *   [256,320) inter-pass twiddles w^{k1 lane}, k1 = 0..31 (32 complex)
  *   [320,384) R = 2 only: combine twiddles w_2048^{lane + 32 k2}, k2 = 0..31
  *   MEAN      FPN mean line, 16 complex of the bins this warp finalises     PPBG  background, 16 floats
@@ -176,13 +176,14 @@ __device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int q
 template <int SA, int R>
 __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, int shift, uint32_t tq, float2 (&v)[32]) {
 	using M = TmemMap<R>;
-	/* table-read schedule: R = 2 has 168 registers per thread (one x16 read per row pair, next row pair prefetched); R = 1 has 128
-	 * (two x8 reads per row pair, only the first half prefetched) -- x16 prefetch at 128 registers spills (ptxas), measured slower */
+	/* table-read schedule at 128 registers per thread: two x8 reads per row pair, only the first half prefetched (mode 3).
+	 * Mode 2 (one x16 read per row pair, next row pair prefetched) needs more contiguous registers than ptxas finds: it spills
+	 * and was measured slower for both line lengths. */
 #ifndef OCT_STAGEA_MODE_R1
 #define OCT_STAGEA_MODE_R1 3
 #endif
 #ifndef OCT_STAGEA_MODE_R2
-#define OCT_STAGEA_MODE_R2 2
+#define OCT_STAGEA_MODE_R2 3
 #endif
 	constexpr int MODE = (R == 1) ? OCT_STAGEA_MODE_R1 : OCT_STAGEA_MODE_R2;
 	if constexpr (MODE == 2 && (SA == SA_CUBIC || SA == SA_LINEAR)) {
@@ -196,7 +197,7 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 			if constexpr (jj < 15) tmem_ld16_issue(tq + M::LUT + 16 * (jj + 1), q[c ^ 1]);
 			sample_taps4_x2(f, __float_as_int(q[c][0]), __float_as_int(q[c][1]), make_float2(q[c][2], q[c][3]), make_float2(q[c][4], q[c][5]),
 			                make_float2(q[c][8], q[c][9]), make_float2(q[c][10], q[c][11]), make_float2(q[c][12], q[c][13]),
-			                make_float2(q[c][14], q[c][15]), v[2 * jj], v[2 * jj + 1]);
+			                make_float2(q[c][14], q[c][15]), v[jj], v[jj + 16]);
 			if constexpr (jj < 15) tmem_ld16_wait(q[c ^ 1]);
 		});
 		return;
@@ -219,8 +220,9 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 			float2 y = pfma(make_float2(qa[c][4], qa[c][5]), Y1, pmul(make_float2(qa[c][2], qa[c][3]), Y0));
 			if constexpr (jj < 15) tmem_ld8_wait2(w, qa[c ^ 1]); else tmem_ld8_wait(w);
 			y = pfma(make_float2(w[2], w[3]), Y3, pfma(make_float2(w[0], w[1]), Y2, y));
-			v[2 * jj] = cscale(make_float2(w[4], w[5]), y.x);
-			v[2 * jj + 1] = cscale(make_float2(w[6], w[7]), y.y);
+			const float2 t = cscale(make_float2(w[4], w[5]), y.x);          /* first FFT butterfly folded in, see sample_taps4_x2 */
+			v[jj] = pfma(make_float2(w[6], w[7]), make_float2(y.y, y.y), t);
+			v[jj + 16] = pfma(make_float2(w[6], w[7]), make_float2(-y.y, -y.y), t);
 		});
 		return;
 	}
@@ -232,7 +234,7 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 			tmem_ld16(tq + M::LUT + 16 * jj, q);
 			sample_taps4_x2(f, __float_as_int(q[0]), __float_as_int(q[1]), make_float2(q[2], q[3]), make_float2(q[4], q[5]),
 			                make_float2(q[8], q[9]), make_float2(q[10], q[11]), make_float2(q[12], q[13]), make_float2(q[14], q[15]),
-			                v[2 * jj], v[2 * jj + 1]);
+			                v[jj], v[jj + 16]);
 			continue;
 		}
 		float q[8];
@@ -245,19 +247,20 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 			float w[8];
 			tmem_ld8(tq + M::LUT + 16 * jj + 8, w);         /* w2a w2b w3a w3b wPa.x wPa.y wPb.x wPb.y */
 			y = pfma(make_float2(w[2], w[3]), Y3, pfma(make_float2(w[0], w[1]), Y2, y));
-			v[2 * jj] = cscale(make_float2(w[4], w[5]), y.x);
-			v[2 * jj + 1] = cscale(make_float2(w[6], w[7]), y.y);
+			const float2 t = cscale(make_float2(w[4], w[5]), y.x);
+			v[jj] = pfma(make_float2(w[6], w[7]), make_float2(y.y, y.y), t);
+			v[jj + 16] = pfma(make_float2(w[6], w[7]), make_float2(-y.y, -y.y), t);
 		} else {
 			float w[8];
 			tmem_ld8(tq + M::LUT + 16 * jj + 8, w);
 			const float2 wa = make_float2(w[4], w[5]), wb = make_float2(w[6], w[7]);
 			if constexpr (SA == SA_NONE) {
-				const int s = lane + 64 * jj;
-				v[2 * jj] = cscale(wa, f[R * s + p]);
-				v[2 * jj + 1] = cscale(wb, f[R * (s + 32) + p]);
+				const int s = lane + 32 * jj;
+				v[jj] = cscale(wa, f[R * s + p]);
+				v[jj + 16] = cscale(wb, f[R * (s + 512) + p]);
 			} else {
-				v[2 * jj] = sample_lanczos(f, shift, make_float4(q[0], wa.x, wa.y, q[6]));
-				v[2 * jj + 1] = sample_lanczos(f, shift, make_float4(q[1], wb.x, wb.y, q[7]));
+				v[jj] = sample_lanczos(f, shift, make_float4(q[0], wa.x, wa.y, q[6]));
+				v[jj + 16] = sample_lanczos(f, shift, make_float4(q[1], wb.x, wb.y, q[7]));
 			}
 		}
 	}

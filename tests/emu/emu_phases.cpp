@@ -74,7 +74,7 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 			else if (sa == SA_LINEAR) { if (R == 1) stage_a<SA_LINEAR, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_LINEAR, 2>(lane, p, fslot, shift, B, v); }
 			else if (sa == SA_NONE) { if (R == 1) stage_a<SA_NONE, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_NONE, 2>(lane, p, fslot, shift, B, v); }
 			else { if (R == 1) stage_a<SA_LANCZOS, 1>(lane, p, fslot, shift, B, v); else stage_a<SA_LANCZOS, 2>(lane, p, fslot, shift, B, v); }
-			fft32_inv(v);
+			if (stage_a_fuses_stage0(sa)) fft32_inv<true>(v); else fft32_inv(v);
 			exchange_store(lane, v, tile[p].data(), tw.data());
 		}
 		for (int lane = 0; lane < 32; ++lane) {
