@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(256) enface_gather_kernel(const EnfaceGatherAr
 		if (done == gridDim.x - 1) {
 			*a.counter = 0;                                             /* next launch is stream ordered behind this one */
 			__threadfence_system();
-			for (int r = 0; r < a.world; ++r) st_release_sys_u32(a.flags[r] + a.rank, a.seq);
+#pragma unroll 1
+			for (int r = 0; r < a.world; ++r) st_relaxed_sys_u32(a.flags[r] + a.rank, a.seq);
 		}
 	}
 }

@@ -67,6 +67,10 @@ struct GatherDev {
 	int world, rank;
 };
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+/* after ONE __threadfence_system(): a relaxed system-scope store per flag word (fence + relaxed store = release; a st.release per
+ * peer would repeat the system fence world times in the tail of the kernel) */
+__device__ __forceinline__ void st_relaxed_sys_u32(unsigned* p, unsigned v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 /* phase 1 (per line, by the one lane that holds the depth bin): the en-face value goes into THIS rank's own frame window */
@@ -82,7 +86,7 @@ __device__ __forceinline__ void gather_push_and_publish(const GatherDev& g, unsi
 	if (threadIdx.x == 0) {
 		__threadfence();
 		atomicAdd(g.counter, 1u);
-		while (ld_acquire_sys_u32(g.counter) < gridDim.x) __nanosleep(64);
+		while (ld_acquire_gpu_u32(g.counter) < gridDim.x) __nanosleep(64);
 	}
 	__syncthreads();
 	if (g.world > 1) {
@@ -111,7 +115,8 @@ __device__ __forceinline__ void gather_push_and_publish(const GatherDev& g, unsi
 		if (done == 2u * gridDim.x - 1u) {
 			*g.counter = 0;              /* every CTA has left the spin above: safe to rearm for the next launch (stream ordered) */
 			__threadfence_system();
-			for (int r = 0; r < g.world; ++r) st_release_sys_u32(g.flags[r] + g.rank, g.seq);
+#pragma unroll 1
+			for (int r = 0; r < g.world; ++r) st_relaxed_sys_u32(g.flags[r] + g.rank, g.seq);
 		}
 	}
 }
