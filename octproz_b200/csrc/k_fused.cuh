@@ -79,7 +79,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll,
 	L.slotBytes = (src == SRC_RAW16) ? align_up(SE * 2, 128) : 0;
 	int work = R * XBUF_BYTES;
 	if (src == SRC_RAW16) {
-		int w2 = align_up((FSLOT_PAD + SE) * 4, 16) + (roll ? align_up((SE + 1) * 4, 16) : 0);
+		int w2 = align_up((FSLOT_PAD + SE + (R == 2 ? 4 : 0)) * 4, 16) + (roll ? align_up((SE + 1) * 4, 16) : 0);   /* R = 2: head room of the odd half */
 		if (w2 > work) work = w2;
 	}
 	L.workBytes = align_up(work, 128);
@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 
 	const int SE = HBv + N + HAv;
 	float* fslot = reinterpret_cast<float*>(work) + FSLOT_PAD;       /* slot element 0; FSLOT_PAD floats of head room */
-	unsigned* prefix = reinterpret_cast<unsigned*>(work + align_up((FSLOT_PAD + SE) * 4, 16));
+	unsigned* prefix = reinterpret_cast<unsigned*>(work + align_up((FSLOT_PAD + SE + (R == 2 ? 4 : 0)) * 4, 16));
+	/* R = 2, 4-tap stage, no rolling mean: the float slot is split by sample parity (see sample_taps4_x2) */
+	constexpr bool SPLIT = (SRC == SRC_RAW16) && stage_a_splits_slot(R, SA, ROLL);
 
 	const int G = gridDim.x * groupsPerCta;
 	const int g0 = blockIdx.x * groupsPerCta + grp;
@@ -222,13 +224,25 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 				uint2 w8[8];
 #pragma unroll
 				for (int i = 0; i < 8; ++i) w8[i] = s2[tig + 32 * R * i];
+				if constexpr (SPLIT) {
+					/* samples 4q .. 4q+3 -> E[2q], E[2q+1] and O[2q], O[2q+1] */
+					float2* e2 = reinterpret_cast<float2*>(fslot);
+					float2* o2 = reinterpret_cast<float2*>(fslot + SPLIT_ODD_BASE);
 #pragma unroll
-				for (int i = 0; i < 8; ++i) f4[tig + 32 * R * i] = cvt(w8[i]);
+					for (int i = 0; i < 8; ++i) {
+						const float4 c = cvt(w8[i]);
+						e2[tig + 32 * R * i] = make_float2(c.x, c.z);
+						o2[tig + 32 * R * i] = make_float2(c.y, c.w);
+					}
+				} else {
+#pragma unroll
+					for (int i = 0; i < 8; ++i) f4[tig + 32 * R * i] = cvt(w8[i]);
+				}
 				/* the remaining HB + HA halo samples (Lanczos only) */
 				for (int q4 = N / 4 + tig; q4 < SE / 4; q4 += 32 * R) f4[q4] = cvt(s2[q4]);
 				if constexpr (SA == SA_CUBIC && !ROLL) {
 					/* mirrored first tap of the cubic: f[-1] = f[1] (cuda_code.cu:284) */
-					if (tig == 0) fslot[HBv - 1] = (float)(reinterpret_cast<const uint16_t*>(slot)[HBv + 1] >> sh);
+					if (tig == 0) fslot[SPLIT ? SPLIT_ODD_BASE - 1 : HBv - 1] = (float)(reinterpret_cast<const uint16_t*>(slot)[HBv + 1] >> sh);
 				}
 			}
 			if constexpr (ROLL) {

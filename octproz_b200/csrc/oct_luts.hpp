@@ -62,13 +62,30 @@ inline void tap_weights(int interp, float tf, float (&w)[4]) {
 	}
 }
 
-/* paired layout for the fused kernel (see stage_a): 2N float4s = four planes [ P | Q | W01 | W23 ] of N/2 entries */
+/* paired layout for the fused kernel (see stage_a): 2N float4s = four planes [ P | Q | W01 | W23 ] of N/2 entries.
+ * taps = 0: Q = { off_a, off_b, t_a, t_b } (byte offset of tap n1 and fractional position: Lanczos, no resampling)
+ * taps = 1: 4-tap interpolators, natural float slot: Q = { offX_a, offX_b, offY_a, offY_b } with offX = 4 (n1 - 1), offY = offX + 8,
+ *           weights in tap order
+ * taps = 2: 4-tap interpolators, parity-split slot (R = 2): the taps n1-1 .. n1+2 are two consecutive elements of the even half (X) and
+ *           two of the odd half (Y); the weights are permuted per sample to match */
 inline void build_stage_luts_paired(int N, int R, int interp, const float* resample, const float* window, const float2* phasor,
-                                    std::vector<float4>& out) {
+                                    std::vector<float4>& out, int taps = 0) {
 	StageLuts nat;
 	build_stage_luts(N, 1, resample, window, phasor, nat);      /* natural order: nat.B[m] = {off, wPx, wPy, t} */
 	out.assign((size_t)2 * N, make_float4(0, 0, 0, 0));
 	const int half = N / 2;
+	auto tap_offsets = [&](float offBits, float& ox, float& oy, float (&w)[4]) {
+		int o; std::memcpy(&o, &offBits, 4);
+		const int t0 = o / 4 - 1;                               /* first tap n1 - 1 (-1 = the mirrored pad sample) */
+		if (taps == 1) { ox = int_as_float(4 * t0); oy = int_as_float(4 * t0 + 8); return; }
+		/* X is ALWAYS the even half and Y the odd half: one gather instruction of a warp then stays inside one half (lane stride
+		 * ~0.85 floats, conflict free); mixing the halves in one instruction collides them bank against bank */
+		const int k = (t0 >= 0) ? t0 / 2 : -1;                  /* floor(t0 / 2) for t0 >= -1 */
+		const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+		oy = int_as_float(4 * (SPLIT_ODD_BASE + k));            /* O[k] O[k+1] */
+		if ((t0 & 1) == 0) { ox = int_as_float(4 * k);       w[0] = w0; w[1] = w2; w[2] = w1; w[3] = w3; }    /* taps E[k] O[k] E[k+1] O[k+1] */
+		else               { ox = int_as_float(4 * (k + 1)); w[0] = w1; w[1] = w3; w[2] = w0; w[3] = w2; }    /* taps O[k] E[k+1] O[k+1] E[k+2] */
+	};
 	for (int p = 0; p < R; ++p)
 		for (int jj = 0; jj < 16; ++jj)
 			for (int lane = 0; lane < 32; ++lane) {
@@ -78,7 +95,13 @@ inline void build_stage_luts_paired(int N, int R, int interp, const float* resam
 				tap_weights(interp, A.w, wa); tap_weights(interp, B.w, wb);
 				const size_t idx = (size_t)p * 512 + lane + 32 * jj;
 				out[idx] = make_float4(A.y, A.z, B.y, B.z);
-				out[half + idx] = make_float4(A.x, B.x, A.w, B.w);
+				if (taps == 0) {
+					out[half + idx] = make_float4(A.x, B.x, A.w, B.w);
+				} else {
+					float xa, ya, xb, yb;
+					tap_offsets(A.x, xa, ya, wa); tap_offsets(B.x, xb, yb, wb);
+					out[half + idx] = make_float4(xa, xb, ya, yb);
+				}
 				out[2 * half + idx] = make_float4(wa[0], wb[0], wa[1], wb[1]);
 				out[3 * half + idx] = make_float4(wa[2], wb[2], wa[3], wb[3]);
 			}

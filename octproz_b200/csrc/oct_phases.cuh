@@ -73,6 +73,10 @@ OCT_HD int lut_int(float f) {
  * One 16-byte shared-memory read per sample; the interpolation polynomial is evaluated in registers in the
  * reference's form, two samples per packed (f32x2) instruction. */
 constexpr int FSLOT_PAD = 4;
+/* parity-split float slot of a 2048-sample line: E[k] = f[2k] at float index k, O[k] = f[2k+1] at float index SPLIT_ODD_BASE + k
+ * (4 floats of head room before the odd half: O[-1] mirrors f[1] for the cubic's first tap) */
+constexpr int SPLIT_ODD_BASE = 1024 + 4;
+OCT_HD constexpr bool stage_a_splits_slot(int R, int sa, bool roll) { return R == 2 && !roll && (sa == 3 /* SA_CUBIC */ || sa == 1 /* SA_LINEAR */); }
 
 OCT_HD float ldf(const float* f, int byteOff) {
 	return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(f) + byteOff);
@@ -97,14 +101,18 @@ OCT_HD float2 sample_cubic(const float* f, float4 B) {           /* cuda_code.cu
 }
 /* two samples at once, tap-weight form: y = sum_k w_k x[n1-1+k] with the four weights of BOTH samples precomputed per lane
  * (they are the same for every A-scan): linear (cuda_code.cu:229: 0, 1-t, t, 0) or Catmull-Rom (cuda_code.cu:258-271 expanded per
- * tap).  4 packed instructions for two samples instead of 12 for the Horner form -- the fp32 pipe bounds this kernel.
- * oa/ob = byte offsets of tap n1 of the two samples, W[k] = (w_k of sample a, w_k of sample b), wa/wb = window*phasor. */
-OCT_HD void sample_taps4_x2(const float* f, int oa, int ob, float2 W0, float2 W1, float2 W2, float2 W3, float2 wa, float2 wb,
+ * tap).  4 packed instructions for two samples instead of 12 for the Horner form.
+ * The taps of a sample are f[x], f[x+4], f[y], f[y+4] (byte offsets from the table) with weights W0..W3: in the natural slot
+ * y = x + 8 and the weights are in tap order; in the parity-split slot of R = 2 (even samples in one half, odd samples in the
+ * other, so that the lanes of a warp -- which walk the line with stride ~1.7 samples -- touch each half with stride < 1 and
+ * stay bank-conflict free) x points into the even half, y into the odd half and the host permutes the weights per sample.
+ * W[k] = (w of sample a, w of sample b), wa/wb = window*phasor. */
+OCT_HD void sample_taps4_x2(const float* f, int xa, int xb, int ya, int yb, float2 W0, float2 W1, float2 W2, float2 W3, float2 wa, float2 wb,
                             float2& outA, float2& outB) {
-	const float2 Y0 = make_float2(ldf(f, oa - 4), ldf(f, ob - 4));
-	const float2 Y1 = make_float2(ldf(f, oa), ldf(f, ob));
-	const float2 Y2 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4));
-	const float2 Y3 = make_float2(ldf(f, oa + 8), ldf(f, ob + 8));
+	const float2 Y0 = make_float2(ldf(f, xa), ldf(f, xb));
+	const float2 Y1 = make_float2(ldf(f, xa + 4), ldf(f, xb + 4));
+	const float2 Y2 = make_float2(ldf(f, ya), ldf(f, yb));
+	const float2 Y3 = make_float2(ldf(f, ya + 4), ldf(f, yb + 4));
 	const float2 y = pfma(W3, Y3, pfma(W2, Y2, pfma(W1, Y1, pmul(W0, Y0))));
 	/* the two samples are rows j and j + 16 of the lane: their first (twiddle-free) FFT butterfly is folded into the window x
 	 * phasor product -- out(j) = wa ya + wb yb, out(j+16) = wa ya - wb yb: 3 packed instructions instead of 4 */
@@ -150,7 +158,8 @@ OCT_HD float2 sample_lanczos(const float* f, int shift, float4 B) {
 /* ---- stage A for one lane: 32 samples s = lane + 32 j of sub-sequence p (m = R*s + p) ----
  * LUT ("paired" layout, build_stage_luts_paired): rows j = jj and jj + 16 of a lane share four float4s, stored as four planes
  * of N/2 entries, entry e = p*512 + lane + 32 jj:
- *   P[e] = { wPx_a, wPy_a, wPx_b, wPy_b }   Q[e] = { off_a, off_b, t_a, t_b }   W01[e] = { w0a, w0b, w1a, w1b }   W23[e] = { w2a, w2b, w3a, w3b }
+ *   P[e] = { wPx_a, wPy_a, wPx_b, wPy_b }   Q[e] = { off_a, off_b, t_a, t_b } (Lanczos / none) or { offX_a, offX_b, offY_a, offY_b } (4-tap)
+ *   W01[e] = { w0a, w0b, w1a, w1b }   W23[e] = { w2a, w2b, w3a, w3b }
  * so every packed operand is an aligned register pair straight out of a 128-bit read. */
 template <int SA, int R>
 OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lut, float2 (&v)[32]) {
@@ -166,7 +175,7 @@ OCT_HD void stage_a(int lane, int p, const float* f, int shift, const float4* lu
 		const float2 wa = make_float2(Pq.x, Pq.y), wb = make_float2(Pq.z, Pq.w);
 		if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
 			const float4 Wa = W01[lane + 32 * jj], Wb = W23[lane + 32 * jj];
-			sample_taps4_x2(f, lut_int(Qq.x), lut_int(Qq.y), make_float2(Wa.x, Wa.y), make_float2(Wa.z, Wa.w),
+			sample_taps4_x2(f, lut_int(Qq.x), lut_int(Qq.y), lut_int(Qq.z), lut_int(Qq.w), make_float2(Wa.x, Wa.y), make_float2(Wa.z, Wa.w),
 			                make_float2(Wb.x, Wb.y), make_float2(Wb.z, Wb.w), wa, wb, v[jj], v[jj + 16]);
 		} else if constexpr (SA == SA_NONE) {
 			const int s = lane + 32 * jj;

@@ -176,44 +176,23 @@ __device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int q
 template <int SA, int R>
 __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, int shift, uint32_t tq, float2 (&v)[32]) {
 	using M = TmemMap<R>;
-	/* table-read schedule at 128 registers per thread: two x8 reads per row pair, only the first half prefetched (mode 3).
-	 * Mode 2 (one x16 read per row pair, next row pair prefetched) needs more contiguous registers than ptxas finds: it spills
-	 * and was measured slower for both line lengths. */
-#ifndef OCT_STAGEA_MODE_R1
-#define OCT_STAGEA_MODE_R1 3
-#endif
-#ifndef OCT_STAGEA_MODE_R2
-#define OCT_STAGEA_MODE_R2 3
-#endif
-	constexpr int MODE = (R == 1) ? OCT_STAGEA_MODE_R1 : OCT_STAGEA_MODE_R2;
-	if constexpr (MODE == 2 && (SA == SA_CUBIC || SA == SA_LINEAR)) {
-		/* software pipelined: row pair jj+1 is being read from tensor memory while row pair jj is gathered and evaluated */
-		float q[2][16];
-		tmem_ld16_issue(tq + M::LUT, q[0]);
-		tmem_ld16_wait(q[0]);
-		static_for<0, 16>([&](auto jc) {
-			constexpr int jj = decltype(jc)::value;
-			constexpr int c = jj & 1;
-			if constexpr (jj < 15) tmem_ld16_issue(tq + M::LUT + 16 * (jj + 1), q[c ^ 1]);
-			sample_taps4_x2(f, __float_as_int(q[c][0]), __float_as_int(q[c][1]), make_float2(q[c][2], q[c][3]), make_float2(q[c][4], q[c][5]),
-			                make_float2(q[c][8], q[c][9]), make_float2(q[c][10], q[c][11]), make_float2(q[c][12], q[c][13]),
-			                make_float2(q[c][14], q[c][15]), v[jj], v[jj + 16]);
-			if constexpr (jj < 15) tmem_ld16_wait(q[c ^ 1]);
-		});
-		return;
-	}
-	if constexpr (MODE == 3 && (SA == SA_CUBIC || SA == SA_LINEAR)) {
-		/* two x8 reads per row pair; the first half of the NEXT row pair (tap offsets, first weights) is prefetched while the
-		 * current one is gathered; the second half (late weights, window x phasor) is read while the gathers are in flight */
+	if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
+		/* 4-tap interpolators.  Table row pair = [ offX_a offX_b w0a w0b | w1a w1b offY_a offY_b || w2a w2b w3a w3b | wPa wPb ]:
+		 * the taps of a sample are f[offX], f[offX+4], f[offY], f[offY+4] with weights w0..w3 (natural slot: offY = offX + 8;
+		 * parity-split slot of R = 2: one pair from the even half, one from the odd half, weights permuted on the host).
+		 * Two x8 reads per row pair at 128 registers per thread: the first half of the NEXT row pair (tap offsets, first weights)
+		 * is prefetched while the current one is gathered; the second half (late weights, window x phasor) is read while the
+		 * gathers are in flight.  (One x16 read per row pair with the next one prefetched needs more contiguous registers than
+		 * ptxas finds: it spills and was measured slower.) */
 		float qa[2][8];
 		tmem_ld8_issue(tq + M::LUT, qa[0]);
 		tmem_ld8_wait(qa[0]);
 		static_for<0, 16>([&](auto jc) {
 			constexpr int jj = decltype(jc)::value;
 			constexpr int c = jj & 1;
-			const int oa = __float_as_int(qa[c][0]), ob = __float_as_int(qa[c][1]);
-			const float2 Y0 = make_float2(ldf(f, oa - 4), ldf(f, ob - 4)), Y1 = make_float2(ldf(f, oa), ldf(f, ob));
-			const float2 Y2 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4)), Y3 = make_float2(ldf(f, oa + 8), ldf(f, ob + 8));
+			const int xa = __float_as_int(qa[c][0]), xb = __float_as_int(qa[c][1]), ya = __float_as_int(qa[c][6]), yb = __float_as_int(qa[c][7]);
+			const float2 Y0 = make_float2(ldf(f, xa), ldf(f, xb)), Y1 = make_float2(ldf(f, xa + 4), ldf(f, xb + 4));
+			const float2 Y2 = make_float2(ldf(f, ya), ldf(f, yb)), Y3 = make_float2(ldf(f, ya + 4), ldf(f, yb + 4));
 			float w[8];
 			tmem_ld8_issue(tq + M::LUT + 16 * jj + 8, w);
 			if constexpr (jj < 15) tmem_ld8_issue(tq + M::LUT + 16 * (jj + 1), qa[c ^ 1]);
@@ -228,40 +207,17 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 	}
 #pragma unroll
 	for (int jj = 0; jj < 16; ++jj) {
-		if constexpr ((SA == SA_CUBIC || SA == SA_LINEAR) && R == 2) {
-			/* 168 registers per thread are available at R = 2 (6 line groups): one wide read */
-			float q[16];
-			tmem_ld16(tq + M::LUT + 16 * jj, q);
-			sample_taps4_x2(f, __float_as_int(q[0]), __float_as_int(q[1]), make_float2(q[2], q[3]), make_float2(q[4], q[5]),
-			                make_float2(q[8], q[9]), make_float2(q[10], q[11]), make_float2(q[12], q[13]), make_float2(q[14], q[15]),
-			                v[jj], v[jj + 16]);
-			continue;
-		}
-		float q[8];
-		tmem_ld8(tq + M::LUT + 16 * jj, q);                 /* off_a off_b w0a w0b w1a w1b t_a t_b */
-		if constexpr (SA == SA_CUBIC || SA == SA_LINEAR) {
-			const int oa = __float_as_int(q[0]), ob = __float_as_int(q[1]);
-			float2 y = pmul(make_float2(q[2], q[3]), make_float2(ldf(f, oa - 4), ldf(f, ob - 4)));
-			y = pfma(make_float2(q[4], q[5]), make_float2(ldf(f, oa), ldf(f, ob)), y);
-			const float2 Y2 = make_float2(ldf(f, oa + 4), ldf(f, ob + 4)), Y3 = make_float2(ldf(f, oa + 8), ldf(f, ob + 8));
-			float w[8];
-			tmem_ld8(tq + M::LUT + 16 * jj + 8, w);         /* w2a w2b w3a w3b wPa.x wPa.y wPb.x wPb.y */
-			y = pfma(make_float2(w[2], w[3]), Y3, pfma(make_float2(w[0], w[1]), Y2, y));
-			const float2 t = cscale(make_float2(w[4], w[5]), y.x);
-			v[jj] = pfma(make_float2(w[6], w[7]), make_float2(y.y, y.y), t);
-			v[jj + 16] = pfma(make_float2(w[6], w[7]), make_float2(-y.y, -y.y), t);
+		float q[8], w[8];
+		tmem_ld8(tq + M::LUT + 16 * jj, q);                 /* off_a off_b . . . . t_a t_b */
+		tmem_ld8(tq + M::LUT + 16 * jj + 8, w);             /* . . . . wPa.x wPa.y wPb.x wPb.y */
+		const float2 wa = make_float2(w[4], w[5]), wb = make_float2(w[6], w[7]);
+		if constexpr (SA == SA_NONE) {
+			const int s = lane + 32 * jj;
+			v[jj] = cscale(wa, f[R * s + p]);
+			v[jj + 16] = cscale(wb, f[R * (s + 512) + p]);
 		} else {
-			float w[8];
-			tmem_ld8(tq + M::LUT + 16 * jj + 8, w);
-			const float2 wa = make_float2(w[4], w[5]), wb = make_float2(w[6], w[7]);
-			if constexpr (SA == SA_NONE) {
-				const int s = lane + 32 * jj;
-				v[jj] = cscale(wa, f[R * s + p]);
-				v[jj + 16] = cscale(wb, f[R * (s + 512) + p]);
-			} else {
-				v[jj] = sample_lanczos(f, shift, make_float4(q[0], wa.x, wa.y, q[6]));
-				v[jj + 16] = sample_lanczos(f, shift, make_float4(q[1], wb.x, wb.y, q[7]));
-			}
+			v[jj] = sample_lanczos(f, shift, make_float4(q[0], wa.x, wa.y, q[6]));
+			v[jj + 16] = sample_lanczos(f, shift, make_float4(q[1], wb.x, wb.y, q[7]));
 		}
 	}
 }

@@ -91,7 +91,7 @@ struct octb200_pipeline {
 	std::vector<float> hResample, hDispersion, hWindow, hPpbg;
 	bool haveResample = false, haveDispersion = false, haveWindow = false;
 	bool lutsDirty = true;
-	int lutSa = -1, lutInterp = -1; bool lutWin = false, lutDisp = false;
+	int lutSa = -1, lutInterp = -1; bool lutRoll = false, lutWin = false, lutDisp = false;
 
 	bool fpnDetermined = false;
 	unsigned bufferNumberInVolume = 0, streamedBuffers = 0, streamingBufferNumber = 0, floatStreamingBufferNumber = 0, currentBufferNr = 0;
@@ -192,6 +192,13 @@ Stage select_stage(const octb200_pipeline* p) {
 	return s;
 }
 
+/* table flavour of the fused kernel's stage A (oct_luts.hpp build_stage_luts_paired): 4-tap stages carry two tap offsets, and the
+ * R = 2 kernel without rolling mean reads a parity-split float slot */
+int lut_taps_mode(int R, const Stage& st) {
+	if (!(st.sa == SA_CUBIC || st.sa == SA_LINEAR)) return 0;
+	return stage_a_splits_slot(R, st.sa, st.roll) ? 2 : 1;
+}
+
 int rebuild_luts(octb200_pipeline* p) {
 	const octb200_params& q = p->prm;
 	const Stage st = select_stage(p);
@@ -215,7 +222,7 @@ int rebuild_luts(octb200_pipeline* p) {
 	StageLuts l;
 	if (p->N == 1024 || p->N == 2048) {
 		std::vector<float4> paired;
-		build_stage_luts_paired(N, p->R, interp == OCTB200_INTERP_CUBIC ? 1 : 0, res, win, ph, paired);
+		build_stage_luts_paired(N, p->R, interp == OCTB200_INTERP_CUBIC ? 1 : 0, res, win, ph, paired, lut_taps_mode(p->R, st));
 		CK(p, cudaMemcpyAsync(p->dLutB, paired.data(), sizeof(float4) * 2 * N, cudaMemcpyHostToDevice, p->sCompute));
 		CK(p, cudaStreamSynchronize(p->sCompute));
 	}
@@ -223,7 +230,7 @@ int rebuild_luts(octb200_pipeline* p) {
 	CK(p, cudaMemcpyAsync(p->dLutB1, l.B.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
 	CK(p, cudaStreamSynchronize(p->sCompute));
 	p->lutsDirty = false;
-	p->lutSa = st.sa; p->lutInterp = interp; p->lutWin = q.windowing != 0; p->lutDisp = q.dispersionCompensation != 0;
+	p->lutSa = st.sa; p->lutRoll = st.roll; p->lutInterp = interp; p->lutWin = q.windowing != 0; p->lutDisp = q.dispersionCompensation != 0;
 	return OCTB200_OK;
 }
 
@@ -298,7 +305,7 @@ cudaError_t launch_gather_standalone(octb200_pipeline* p, const GatherDev& d) {
 int run_chain(octb200_pipeline* p, const void* dRaw) {
 	octb200_params& q = p->prm;
 	const Stage st = select_stage(p);
-	if (p->lutsDirty || st.sa != p->lutSa) { int rc = rebuild_luts(p); if (rc) return rc; }
+	if (p->lutsDirty || st.sa != p->lutSa || st.roll != p->lutRoll) { int rc = rebuild_luts(p); if (rc) return rc; }
 	if (q.postProcessBackgroundRemoval && p->hPpbg.empty() && !q.postProcessBackgroundRecordingRequested) {
 		/* the reference starts with a zeroed background line (cuda_code.cu:1122) */
 	}
@@ -912,7 +919,8 @@ int octb200_dispersion_sweep(octb200_pipeline* p, const void* raw, const octb200
 	const float* win = q.windowing ? p->hWindow.data() : nullptr;
 	std::vector<float4> luts((size_t)K * 2 * N), one;
 	for (int k = 0; k < K; ++k) {
-		build_stage_luts_paired(N, p->R, q.resamplingInterpolation == OCTB200_INTERP_CUBIC ? 1 : 0, res, win, phasor.data() + (size_t)k * N, one);
+		build_stage_luts_paired(N, p->R, q.resamplingInterpolation == OCTB200_INTERP_CUBIC ? 1 : 0, res, win, phasor.data() + (size_t)k * N, one,
+		                        lut_taps_mode(p->R, st));
 		std::memcpy(luts.data() + (size_t)k * 2 * N, one.data(), sizeof(float4) * 2 * N);
 	}
 	CK(p, cudaMemcpyAsync(p->dSweepLut, luts.data(), sizeof(float4) * luts.size(), cudaMemcpyHostToDevice, p->sCompute));
@@ -966,7 +974,7 @@ int octb200_time_kernel(octb200_pipeline* p, const void* dRaw, int iters, float*
 	if (!p || !dRaw || iters < 1 || !msPerIter) return fail(p, OCTB200_ERR_INVALID, "bad argument");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	const Stage st = select_stage(p);
-	if (p->lutsDirty || st.sa != p->lutSa) { int rc = rebuild_luts(p); if (rc) return rc; }
+	if (p->lutsDirty || st.sa != p->lutSa || st.roll != p->lutRoll) { int rc = rebuild_luts(p); if (rc) return rc; }
 	const bool fpn = p->prm.fixedPatternNoiseRemoval != 0;
 	float* slab = p->dVolume + (size_t)(p->S / 2) * p->bufferNumberInVolume;
 	CK(p, cudaEventRecord(p->evTiming[6], p->sCompute));

@@ -56,7 +56,9 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 	const int R = N / 1024;
 	if (R != 1 && R != 2) return -1;
 	std::vector<float4> lut;
-	build_stage_luts_paired(N, R, interp, resample, window, reinterpret_cast<const float2*>(phasor), lut);
+	const bool four = (sa == SA_CUBIC || sa == SA_LINEAR);
+	const bool split = stage_a_splits_slot(R, sa, false);
+	build_stage_luts_paired(N, R, interp, resample, window, reinterpret_cast<const float2*>(phasor), lut, four ? (split ? 2 : 1) : 0);
 	std::vector<float2> tw, ctw;
 	build_twiddles_1024(tw);
 	build_combine_twiddles_2048(ctw);
@@ -64,6 +66,15 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 	e.fpn = meanLine != nullptr; e.ppbg = ppbg != nullptr; e.ppbgWeight = ppbgW; e.ppbgOffset = ppbgO;
 	/* cubic: the kernel mirrors f[-1] = f[1]; the caller's buffer has room in front of the line */
 	if (sa == SA_CUBIC) const_cast<float*>(fslot)[-1] = fslot[1];
+	/* R = 2, 4-tap: the kernel's conversion writes the slot split by sample parity */
+	std::vector<float> splitSlot;
+	if (split) {
+		splitSlot.assign(FSLOT_PAD + SPLIT_ODD_BASE + 1024 + 8, 0.0f);
+		float* e = splitSlot.data() + FSLOT_PAD;
+		for (int k = 0; k < 1024; ++k) { e[k] = fslot[2 * k]; e[SPLIT_ODD_BASE + k] = fslot[2 * k + 1]; }
+		e[SPLIT_ODD_BASE - 1] = fslot[1];
+		fslot = e;
+	}
 	static float2 regs[2][32][32];
 	std::vector<float2> tile[2] = { std::vector<float2>(XBUF_FLOAT2), std::vector<float2>(XBUF_FLOAT2) };
 	for (int p = 0; p < R; ++p) {
