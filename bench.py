@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--mode", default="fused", choices=["fused", "split", "cufft"])
     ap.add_argument("--enface", default="p2p", choices=["p2p", "nccl"], help="multi-GPU en-face gather: own peer-memory kernel or NCCL")
+    ap.add_argument("--no-packed", action="store_true", help="skip the 12-bit packed-input extension measurement")
     ap.add_argument("--cpu-bscans", type=int, default=0, help="B-scans in the cpu_baseline sample (0 = auto)")
     args = ap.parse_args()
 
@@ -329,6 +330,46 @@ def main():
     checksum = int(h_stream[0][:4096].view(np.uint16).sum())
     p.cuda_unregisterStreamingBuffers()
 
+    # ---- extension beside the headline (N = 1, 12-bit workload): the same volume delivered 12-bit PACKED (3 bytes per 2 samples,
+    #      include/octb200.h OCTB200_PACK_12P; the reference only takes containers).  Reported separately, never as `value` / `e2e`. ----
+    packed = None
+    if world == 1 and bits == 12 and args.mode == "fused" and not args.no_packed:
+        from octproz_b200.packing import pack12
+        pp = OctPipeline(fft_mode=mode, device=local, input_packing=_lib.PACK_12P)
+        qp = copy.deepcopy(q)
+        if pp.initializeCuda(None, None, qp):
+            hp = [torch.from_numpy(pack12(x)).pin_memory() for x in raw_np]
+            dp = [x.cuda() for x in hp]
+            pp.process_device(dp[0]); pp.sync()
+            for i in range(5):
+                pp.process_device(dp[i & 1])
+            pp.sync()
+            n_res = min(args.steps, 200)
+            pp.event_record(0)
+            for i in range(n_res):
+                pp.process_device(dp[i & 1])
+            pp.event_record(1)
+            ms_p = pp.event_elapsed_ms(0, 1) / n_res
+            qp.streamToHost = True
+            hs2 = [np.zeros(conv_bytes, np.uint8) for _ in range(2)]
+            pp.cuda_registerStreamingBuffers(hs2[0], hs2[1], conv_bytes)
+            for i in range(3):
+                pp.octCudaPipeline(hp[i & 1].numpy())
+            pp.sync()
+            n_e2e = min(args.steps, 100)
+            t0 = time.perf_counter()
+            for i in range(n_e2e):
+                pp.octCudaPipeline(hp[i & 1].numpy())
+            pp.sync()
+            dt = time.perf_counter() - t0
+            packed = {"input": "12-bit packed (Mono12p), extension", "value": ascans_per_step / (ms_p * 1e3), "ms_per_step": ms_p,
+                      "e2e": {"value": ascans_per_step * n_e2e / dt / 1e6, "h2d_bytes_per_step": int(hp[0].numel()), "d2h_bytes_per_step": conv_bytes,
+                              "ms_per_step": dt * 1e3 / n_e2e, "steps": n_e2e},
+                      "unit": "MHz (1e6 A-scans/s)", "checksum": int(hs2[0][:4096].view(np.uint16).sum()) + int(hs2[1][:4096].view(np.uint16).sum())}
+            pp.cuda_unregisterStreamingBuffers()
+            pp.cleanupCuda()
+            del hp, dp
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1:
@@ -356,6 +397,8 @@ def main():
                     "ms_per_step": e2e_s * 1e3 / e2e_steps, "steps": e2e_steps, "timer": "host wall clock between device synchronisations, max over ranks",
                     "checksum": checksum},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "host_cores": ncores}
+    if packed is not None:
+        line["packed12"] = packed
     print(json.dumps(line), flush=True)
     return 0
 

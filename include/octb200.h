@@ -54,6 +54,13 @@ enum { OCTB200_WIN_HANNING = 0, OCTB200_WIN_GAUSS = 1, OCTB200_WIN_SINE = 2,
 /* octalgorithmparameters.h:177-180 */
 enum { OCTB200_DISPLAY_AVERAGING = 0, OCTB200_DISPLAY_MIP = 1 };
 
+/* raw input packing.  CONTAINER = the reference's format (u8 / u16 / u32 containers, cuda_code.cu:116-125).  12P = an
+   extension the reference does not have (docs/docs/faq.md: 12-bit data must be delivered in 16-bit containers): 12-bit samples
+   packed little-endian, two samples per three bytes (GenICam PFNC "Mono12p": sample k of a line occupies bits [12k, 12k+12) of the
+   line's bit string), bitDepth must be 12; a raw buffer then has samples*3/2 bytes -- a quarter less PCIe and HBM input traffic.
+   The fused kernel unpacks in its slot conversion; Lanczos / rolling-mean / SPLIT / CUFFT chains unpack once into HBM first. */
+enum { OCTB200_PACK_CONTAINER = 0, OCTB200_PACK_12P = 1 };
+
 /* which kernels run the FFT stage */
 enum {
 	OCTB200_FFT_AUTO = 0,        /* FUSED when samplesPerLine is 1024 or 2048 and the container is u16, else best available */
@@ -74,7 +81,8 @@ typedef struct {
 	int32_t  fftMode;           /* OCTB200_FFT_* */
 	uint32_t bscanIndexBase;    /* multi-GPU shards: index (within the un-sharded buffer) of this shard's
 	                               first B-scan, so "flip every even B-scan" (cuda_code.cu:795) keeps its parity */
-	uint32_t reserved[3];
+	uint32_t inputPacking;      /* OCTB200_PACK_*: how the raw buffer stores its samples */
+	uint32_t reserved[2];
 } octb200_config;
 
 /* the [processing] block of OctAlgorithmParameters (octalgorithmparameters.h:108-166, 195-199) */

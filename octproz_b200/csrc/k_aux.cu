@@ -437,6 +437,23 @@ cudaError_t launch_sweep_metric(float* metrics, const float* data, int trials, i
 	sweep_metric_kernel<<<trials, 128, (size_t)lines * sizeof(float), st>>>(metrics, data, lines, H, metric, thr, ignore);
 	return cudaGetLastError();
 }
+/* ------------------------------------------------------------------ 12-bit packed -> u16 containers
+ * little-endian bit packing (GenICam Mono12p): sample k of an octet lives in bits [12k, 12k+12) of its 96 bits */
+__global__ void __launch_bounds__(256) unpack12_kernel(uint4* __restrict__ out, const unsigned* __restrict__ in, long long octets) {
+	for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < octets; o += (long long)gridDim.x * blockDim.x) {
+		const unsigned a0 = __ldg(in + 3 * o), a1 = __ldg(in + 3 * o + 1), a2 = __ldg(in + 3 * o + 2);
+		const unsigned s0 = a0 & 0xFFFu, s1 = (a0 >> 12) & 0xFFFu, s2 = __funnelshift_r(a0, a1, 24) & 0xFFFu, s3 = (a1 >> 4) & 0xFFFu;
+		const unsigned s4 = (a1 >> 16) & 0xFFFu, s5 = __funnelshift_r(a1, a2, 28) & 0xFFFu, s6 = (a2 >> 8) & 0xFFFu, s7 = a2 >> 20;
+		out[o] = make_uint4(s0 | (s1 << 16), s2 | (s3 << 16), s4 | (s5 << 16), s6 | (s7 << 16));
+	}
+}
+cudaError_t launch_unpack12(uint16_t* out, const void* in, long long octets, int smCount, cudaStream_t st) {
+	long long blocks = (octets + 255) / 256;
+	if (blocks > (long long)smCount * 16) blocks = (long long)smCount * 16;
+	unpack12_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(out), static_cast<const unsigned*>(in), octets);
+	return cudaGetLastError();
+}
+
 /* u8 voxels in the layout of the GL_R8 3-D texture (x = A-scan, y = B-scan in volume, z flipped depth), cuda_code.cu:928-940 */
 __global__ void __launch_bounds__(256) volume_u8_kernel(uint8_t* __restrict__ tex, const float* __restrict__ buf, long long samples,
                                                          unsigned bufferNr, unsigned B, unsigned A, unsigned Btot, unsigned depth) {

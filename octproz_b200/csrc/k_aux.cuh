@@ -48,6 +48,7 @@ cudaError_t launch_enface_gather(const EnfaceGatherArgs& a, cudaStream_t st);
 cudaError_t launch_enface_wait(const unsigned* flags, int world, unsigned seq, cudaStream_t st);
 
 cudaError_t launch_sweep_metric(float* metrics, const float* data, int trials, int lines, int H, int metric, float thr, int ignore, cudaStream_t st);
+cudaError_t launch_unpack12(uint16_t* out, const void* in, long long octets, int smCount, cudaStream_t st);
 void launch_fill_phase(float2* ph, const float* phase, int n, cudaStream_t st);
 cudaError_t launch_pre(const PreArgs& a, int rawBytes, int sa, bool roll, int smCount, cudaStream_t st);
 cudaError_t launch_post(const PostArgs& a, int smCount, cudaStream_t st);

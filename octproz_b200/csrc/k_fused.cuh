@@ -67,7 +67,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll,
 	off += 128;      /* TMEM base address word */
 	(void)H;
 #else
-	L.offB = off;    off += (src == SRC_RAW16) ? 2 * N * 16 : 0;
+	L.offB = off;    off += (src_is_raw(src)) ? 2 * N * 16 : 0;
 	L.offTw = off;   off += 1024 * 8;
 	L.offCtw = off;  off += (R == 2) ? 1024 * 8 : 0;
 	L.offMean = off; off += H * 8;
@@ -76,9 +76,9 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll,
 	off = align_up(off, 128);
 	L.offGroups = off;
 	const int SE = HB + N + HA;
-	L.slotBytes = (src == SRC_RAW16) ? align_up(SE * 2, 128) : 0;
+	L.slotBytes = (src_is_raw(src)) ? align_up(SE * 2, 128) : 0;
 	int work = R * XBUF_BYTES;
-	if (src == SRC_RAW16) {
+	if (src_is_raw(src)) {
 		int w2 = align_up((FSLOT_PAD + SE + (R == 2 ? 4 : 0)) * 4, 16) + (roll ? align_up((SE + 1) * 4, 16) : 0);   /* R = 2: head room of the odd half */
 		if (w2 > work) work = w2;
 	}
@@ -95,13 +95,14 @@ __device__ __forceinline__ void group_sync(int barId) {
 }
 
 /* one lane: start the asynchronous load of raw line `gline` (with halos) into `slot` */
-template <int R, bool HALO>
+template <int R, bool HALO, bool PACKED = false>
 __device__ __forceinline__ void issue_line_load(const FusedArgs& a, int gline, unsigned char* slot, uint64_t* bar) {
 	constexpr int N = 1024 * R;
 	if constexpr (!HALO) {
 		/* no halo (every stage but Lanczos): one aligned copy of exactly the line, nothing to clip */
-		mbar_arrive_expect_tx(bar, (uint32_t)(N * 2));
-		bulk_g2s(slot, a.raw + (size_t)gline * N, (uint32_t)(N * 2), bar);
+		constexpr uint32_t LB = PACKED ? (uint32_t)(N * 3 / 2) : (uint32_t)(N * 2);
+		mbar_arrive_expect_tx(bar, LB);
+		bulk_g2s(slot, reinterpret_cast<const unsigned char*>(a.raw) + (size_t)gline * LB, LB, bar);
 		return;
 	}
 	const long long lo = (long long)gline * N - a.HB;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	const uint32_t tq = tmemBase + ((uint32_t)(warp & 3) << 21);     /* lane quadrant of this warp: lane field = bits 31:16, 32 lanes per quadrant */
 	{
 		const int nWarps = blockDim.x >> 5, quadrant = warp & 3;
-		tmem_fill<R>(tq, quadrant, warp >> 2, (nWarps - quadrant + 3) >> 2, lane, a, a.lutB + (size_t)blockIdx.y * a.trialLutStride, SRC == SRC_RAW16);
+		tmem_fill<R>(tq, quadrant, warp >> 2, (nWarps - quadrant + 3) >> 2, lane, a, a.lutB + (size_t)blockIdx.y * a.trialLutStride, src_is_raw(SRC));
 	}
 	tmem_fence_before_sync();
 	__syncthreads();
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			uint4* d = reinterpret_cast<uint4*>(smem + off);
 			for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
 		};
-		if constexpr (SRC == SRC_RAW16) fill(L.offB, a.lutB + (size_t)blockIdx.y * a.trialLutStride, 2 * N * 16);
+		if constexpr (src_is_raw(SRC)) fill(L.offB, a.lutB + (size_t)blockIdx.y * a.trialLutStride, 2 * N * 16);
 		fill(L.offTw, a.tw, 1024 * 8);
 		if constexpr (R == 2) fill(L.offCtw, a.ctw, 1024 * 8);
 		if (a.epi.fpn && a.cplxOut == nullptr) fill(L.offMean, a.meanLine, H * 8);
@@ -183,17 +184,17 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	float* fslot = reinterpret_cast<float*>(work) + FSLOT_PAD;       /* slot element 0; FSLOT_PAD floats of head room */
 	unsigned* prefix = reinterpret_cast<unsigned*>(work + align_up((FSLOT_PAD + SE + (R == 2 ? 4 : 0)) * 4, 16));
 	/* R = 2, 4-tap stage, no rolling mean: the float slot is split by sample parity (see sample_taps4_x2) */
-	constexpr bool SPLIT = (SRC == SRC_RAW16) && stage_a_splits_slot(R, SA, ROLL);
+	constexpr bool SPLIT = (src_is_raw(SRC)) && stage_a_splits_slot(R, SA, ROLL);
 
 	const int G = gridDim.x * groupsPerCta;
 	const int g0 = blockIdx.x * groupsPerCta + grp;
 
-	if constexpr (SRC == SRC_RAW16) {
+	if constexpr (src_is_raw(SRC)) {
 		if (tig == 0) { mbar_init(bar, 1); mbar_fence_init(); }
 	}
 	__syncthreads();
-	if constexpr (SRC == SRC_RAW16) {
-		if (tig == 0 && g0 < a.lines) issue_line_load<R, SA == SA_LANCZOS>(a, g0, slot, bar);
+	if constexpr (src_is_raw(SRC)) {
+		if (tig == 0 && g0 < a.lines) issue_line_load<R, SA == SA_LANCZOS, SRC == SRC_RAW12P>(a, g0, slot, bar);
 	}
 
 #ifdef OCT_STAGGER_NS
@@ -207,11 +208,43 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	for (int gline = g0; gline < a.lines; gline += G, ++it) {
 		float2 v[32];
 
-		if constexpr (SRC == SRC_RAW16) {
+		if constexpr (src_is_raw(SRC)) {
 			mbar_wait(bar, (uint32_t)(it & 1));
 
 			/* ---- slot conversion: inputToCufftComplex[_and_bitshift] once per sample (cuda_code.cu:109-147) ---- */
-			{
+			if constexpr (SRC == SRC_RAW12P) {
+				/* 12-bit packed, little endian: eight samples in three 32-bit words; 4 octets per thread and 1024 samples */
+				static_assert(SA != SA_LANCZOS && !ROLL, "packed input: the host unpacks for the halo / rolling-mean stages");
+				const unsigned* s1 = reinterpret_cast<const unsigned*>(slot);
+				float4* f4 = reinterpret_cast<float4*>(fslot);
+				unsigned w[4][3];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int o = tig + 32 * R * i;
+					w[i][0] = s1[3 * o]; w[i][1] = s1[3 * o + 1]; w[i][2] = s1[3 * o + 2];
+				}
+				auto f12 = [](unsigned v) { return __uint_as_float(0x4B000000u | (v & 0xFFFu)) - 8388608.0f; };
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int o = tig + 32 * R * i;
+					const unsigned a0 = w[i][0], a1 = w[i][1], a2 = w[i][2];
+					const float x0 = f12(a0), x1 = f12(a0 >> 12), x2 = f12(__funnelshift_r(a0, a1, 24)), x3 = f12(a1 >> 4);
+					const float x4 = f12(a1 >> 16), x5 = f12(__funnelshift_r(a1, a2, 28)), x6 = f12(a2 >> 8), x7 = f12(a2 >> 20);
+					if constexpr (SPLIT) {
+						float4* e4 = reinterpret_cast<float4*>(fslot);
+						float4* o4 = reinterpret_cast<float4*>(fslot + SPLIT_ODD_BASE);
+						e4[o] = make_float4(x0, x2, x4, x6);
+						o4[o] = make_float4(x1, x3, x5, x7);
+					} else {
+						f4[2 * o] = make_float4(x0, x1, x2, x3);
+						f4[2 * o + 1] = make_float4(x4, x5, x6, x7);
+					}
+				}
+				if constexpr (SA == SA_CUBIC) {
+					/* mirrored first tap of the cubic: f[-1] = f[1] (cuda_code.cu:284) */
+					if (tig == 0) fslot[SPLIT ? SPLIT_ODD_BASE - 1 : -1] = f12(s1[0] >> 12);
+				}
+			} else {
 				const uint2* s2 = reinterpret_cast<const uint2*>(slot);
 				float4* f4 = reinterpret_cast<float4*>(fslot);
 				const unsigned sh = (unsigned)a.shiftBits;
@@ -263,7 +296,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			}
 			group_sync<R>(barId);
 			/* raw slot consumed: refill it with the next line of this group */
-			if (tig == 0 && gline + G < a.lines) issue_line_load<R, SA == SA_LANCZOS>(a, gline + G, slot, bar);
+			if (tig == 0 && gline + G < a.lines) issue_line_load<R, SA == SA_LANCZOS, SRC == SRC_RAW12P>(a, gline + G, slot, bar);
 			if constexpr (ROLL) {
 				const int W = a.W;
 				for (int q = tig; q < SE; q += 32 * R) {
@@ -298,7 +331,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 		}
 
 		/* ---- 1024-point inverse FFT of this warp's sub-sequence (first butterfly stage already done by the 4-tap stage A) ---- */
-		fft32_inv<SRC == SRC_RAW16 && stage_a_fuses_stage0(SA)>(v);
+		fft32_inv<src_is_raw(SRC) && stage_a_fuses_stage0(SA)>(v);
 #if OCT_TMEM_LUT
 		exchange_store_tmem<R>(lane, v, tile, tq);
 #else

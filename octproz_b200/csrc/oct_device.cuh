@@ -123,7 +123,7 @@ __device__ __forceinline__ void gather_push_and_publish(const GatherDev& g, unsi
 
 /* ---------------- argument block of the fused / own-FFT kernels ---------------- */
 struct FusedArgs {
-	const uint16_t* raw;     /* SRC_RAW16: [lines][N] u16 (whole raw buffer, halo reads clip to [0,totalSamples)) */
+	const uint16_t* raw;     /* SRC_RAW16: [lines][N] u16 (whole raw buffer, halo reads clip to [0,totalSamples)); SRC_RAW12P: [lines][N*3/2] bytes */
 	const float2* cin;       /* SRC_CPLX : [lines][N] float2 FFT input written by the pre-FFT kernel */
 	float* out;              /* [lines][N/2] processed output slab (flip folded into the line address) */
 	float2* cplxOut;         /* != NULL: write the pre-FPN complex bins [lines][N/2] instead (FPN determination pass) */
@@ -148,6 +148,10 @@ struct FusedArgs {
 	long long trialOutStride;/* floats between the output slabs of consecutive trials */
 };
 
-enum { SRC_RAW16 = 0, SRC_CPLX = 1 };
+/* where a line comes from: u16 containers (the reference's raw format), float2 FFT input written by the pre-FFT kernel, or
+ * 12-bit samples packed little-endian, two per three bytes (GenICam "Mono12p": an extension -- the reference only takes containers,
+ * docs/docs/faq.md -- that cuts the PCIe / HBM input bytes by a quarter) */
+enum { SRC_RAW16 = 0, SRC_CPLX = 1, SRC_RAW12P = 2 };
+__host__ __device__ constexpr bool src_is_raw(int src) { return src == SRC_RAW16 || src == SRC_RAW12P; }
 
 }  // namespace octb200

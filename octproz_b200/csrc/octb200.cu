@@ -59,6 +59,9 @@ struct octb200_pipeline {
 	octb200_config cfg{};
 	octb200_params prm{};
 	int N = 0, A = 0, B = 0, V = 1, H = 0, lines = 0, rawBytes = 2, R = 1;
+	bool packed12 = false;            /* raw input is 12-bit packed (OCTB200_PACK_12P): 3 bytes per 2 samples */
+	size_t inBytes = 0;               /* bytes of one raw input buffer */
+	uint16_t* dUnpacked = nullptr;    /* u16 containers of a packed buffer, for the stages that cannot read it directly */
 	long long S = 0;
 	int device = 0, smCount = 148;
 	int mode = OCTB200_FFT_FUSED;
@@ -323,6 +326,18 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 	}
 	if (mode != OCTB200_FFT_FUSED) { int rc = ensure_fft_buffer(p); if (rc) return rc; }
 
+	/* 12-bit packed input: the fused kernel unpacks it in its slot conversion (4-tap / plain stage, no rolling mean); every other
+	   stage reads u16 containers, so the buffer is unpacked once into HBM first */
+	int rawSrc = SRC_RAW16;
+	if (p->packed12) {
+		if (mode == OCTB200_FFT_FUSED && st.sa != SA_LANCZOS && !st.roll) rawSrc = SRC_RAW12P;
+		else {
+			if (!p->dUnpacked) { int rc = dalloc(p, &p->dUnpacked, (size_t)p->S + 32); if (rc) return rc; }
+			CK(p, launch_unpack12(p->dUnpacked, dRaw, p->S / 8, p->smCount, p->sCompute)); p->launches++;
+			dRaw = p->dUnpacked;
+		}
+	}
+
 	if (p->floatCopyPending) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evFloatCopied, 0)); p->floatCopyPending = false; }
 
 	const bool fpn = q.fixedPatternNoiseRemoval != 0;
@@ -362,7 +377,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		po.flip = q.bscanFlip; po.bscanBase = p->cfg.bscanIndexBase;
 		CK(p, launch_post(po, p->smCount, p->sCompute)); p->launches++;
 	} else {
-		const int src = (mode == OCTB200_FFT_FUSED) ? SRC_RAW16 : SRC_CPLX;
+		const int src = (mode == OCTB200_FFT_FUSED) ? rawSrc : SRC_CPLX;
 		if (determine) {
 			int rc = ensure_fpn_scratch(p, (size_t)fpnHeight * p->H); if (rc) return rc;
 			if (src == SRC_CPLX) { PreArgs pa = pre_args(p, st, dRaw, fpnHeight); CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++; }
@@ -474,6 +489,12 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	p->H = p->N / 2; p->lines = p->A * p->B; p->S = S;
 	p->rawBytes = cfg->bitDepth <= 8 ? 1 : (cfg->bitDepth <= 16 ? 2 : 4);   /* bytesPerSample, cuda_code.cu:1077 */
 	p->R = p->N == 2048 ? 2 : 1;
+	p->packed12 = cfg->inputPacking == OCTB200_PACK_12P;
+	if (cfg->inputPacking > OCTB200_PACK_12P || (p->packed12 && (cfg->bitDepth != 12 || (cfg->samplesPerLine % 32) != 0))) {
+		delete p;
+		return fail(nullptr, OCTB200_ERR_INVALID, "inputPacking %u needs bitDepth 12 and samplesPerLine a multiple of 32", cfg->inputPacking);
+	}
+	p->inBytes = p->packed12 ? (size_t)S * 3 / 2 : (size_t)S * p->rawBytes;
 	const bool fftSize = (p->N == 1024 || p->N == 2048);
 	int mode = cfg->fftMode;
 	if (mode == OCTB200_FFT_AUTO) mode = fftSize ? (p->rawBytes == 2 ? OCTB200_FFT_FUSED : OCTB200_FFT_SPLIT) : OCTB200_FFT_CUFFT;
@@ -506,7 +527,7 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	p->dRaw.assign(slots, nullptr); p->evRawReady.assign(slots, nullptr); p->evRawFree.assign(slots, nullptr);
 	for (int i = 0; i < slots; ++i) {
 		unsigned char* r = nullptr;
-		RCC(dalloc(p, &r, (size_t)S * p->rawBytes + 64)); p->dRaw[i] = r;
+		RCC(dalloc(p, &r, p->inBytes + 64)); p->dRaw[i] = r;
 		CKC(cudaEventCreateWithFlags(&p->evRawReady[i], cudaEventDisableTiming));
 		CKC(cudaEventCreateWithFlags(&p->evRawFree[i], cudaEventDisableTiming));
 	}
@@ -557,6 +578,7 @@ int octb200_destroy(octb200_pipeline* p) {
 	dfree(p->dTw); dfree(p->dCtw); dfree(p->dSinCurve);
 	for (void*& c : p->dOutConv) { if (c) cudaFree(c); c = nullptr; }
 	octb200_enface_gather_close(p);
+	dfree(p->dUnpacked);
 	dfree(p->dSweepRaw); dfree(p->dSweepLut); dfree(p->dSweepOut); dfree(p->dSweepPhase); dfree(p->dSweepPhasor); dfree(p->dSweepMetric);
 	if (p->sCompute) cudaStreamDestroy(p->sCompute);
 	if (p->sH2D) cudaStreamDestroy(p->sH2D);
@@ -644,7 +666,7 @@ int octb200_register_host_buffers(octb200_pipeline* p, void* h1, void* h2) {
 	if (!p || !h1) return fail(p, OCTB200_ERR_INVALID, "null argument");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	if (p->hostRegistered) octb200_unregister_host_buffers(p);
-	const size_t bytes = (size_t)p->S * p->rawBytes;
+	const size_t bytes = p->inBytes;
 	CK(p, pin_host(h1, bytes, &p->hostBufMine[0]));
 	p->hostBuf[0] = h1; p->hostBuf[1] = nullptr; p->hostBufMine[1] = false;
 	if (h2 && h2 != h1) {
@@ -716,7 +738,7 @@ int octb200_process_host(octb200_pipeline* p, const void* hRaw) {
 		return run_chain(p, p->slot >= 0 ? p->dRaw[p->slot] : p->lastDeviceRaw);
 	}
 	const int s = (p->slot + 1) % (int)p->dRaw.size();
-	const size_t bytes = (size_t)p->S * p->rawBytes;
+	const size_t bytes = p->inBytes;
 	CK(p, cudaStreamWaitEvent(p->sH2D, p->evRawFree[s], 0));       /* kernels that still read this slot */
 	CK(p, cudaMemcpyAsync(p->dRaw[s], hRaw, bytes, cudaMemcpyHostToDevice, p->sH2D));   /* cuda_code.cu:1404 */
 	CK(p, cudaEventRecord(p->evRawReady[s], p->sH2D));
@@ -980,11 +1002,13 @@ int octb200_time_kernel(octb200_pipeline* p, const void* dRaw, int iters, float*
 	CK(p, cudaEventRecord(p->evTiming[6], p->sCompute));
 	for (int i = 0; i < iters; ++i) {
 		if (p->mode == OCTB200_FFT_CUFFT) {
+			if (p->packed12) return fail(p, OCTB200_ERR_INVALID, "time_kernel: packed input is only timed on the direct fused path");
 			PreArgs pa = pre_args(p, st, dRaw, p->lines);
 			int rc = ensure_fft_buffer(p); if (rc) return rc;
 			CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute));
 		} else {
-			const int src = (p->mode == OCTB200_FFT_FUSED) ? SRC_RAW16 : SRC_CPLX;
+			const int src = (p->mode == OCTB200_FFT_FUSED) ? ((p->packed12 && st.sa != SA_LANCZOS && !st.roll) ? SRC_RAW12P : SRC_RAW16) : SRC_CPLX;
+			if (p->packed12 && src != SRC_RAW12P) return fail(p, OCTB200_ERR_INVALID, "time_kernel: packed input is only timed on the direct fused path");
 			if (src == SRC_CPLX) { int rc = ensure_fft_buffer(p); if (rc) return rc; }
 			FusedArgs fa = fused_args(p, st, dRaw, p->lines);
 			fa.out = slab; fa.epi = epi_for(p, fpn && p->fpnDetermined, false);
