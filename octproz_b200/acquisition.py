@@ -80,8 +80,12 @@ class VirtualOCTSystem(AcquisitionSystem):
     """file replay (virtualoctsystem.cpp).  Settings keys = virtualoctsystemsettingsdialog.h:27-38."""
 
     def __init__(self, file_path: str, bit_depth: int, width: int, height: int, depth: int, buffers_per_volume: int = 1,
-                 buffers_from_file: int = 2, bscan_offset: int = 0, wait_time_us: int = 0, sync_with_processing: bool = True):
+                 buffers_from_file: int = 2, bscan_offset: int = 0, wait_time_us: int = 0, sync_with_processing: bool = True,
+                 packed12: bool = False):
+        """packed12: the file holds 12-bit samples packed two per three bytes (octproz_b200/packing.py) instead of containers --
+        an extension over the reference's raw format; pair it with OctPipeline(input_packing=PACK_12P)"""
         super().__init__()
+        self.packed12 = packed12
         self.file_path, self.bscan_offset, self.wait_time_us = file_path, bscan_offset, wait_time_us
         self.buffers_from_file, self.sync_with_processing = buffers_from_file, sync_with_processing
         self.params = AcquisitionParams(width, height, depth, buffers_per_volume, bit_depth)
@@ -91,8 +95,12 @@ class VirtualOCTSystem(AcquisitionSystem):
         if not os.path.isfile(self.file_path):
             return False
         p = self.params
-        elem = int(math.ceil(p.bitDepth / 8.0))
-        return self.buffer.allocateMemory(2, p.samplesPerLine * p.ascansPerBscan * p.bscansPerBuffer * elem)
+        return self.buffer.allocateMemory(2, self._bytes(p.samplesPerLine * p.ascansPerBscan * p.bscansPerBuffer))
+
+    def _bytes(self, samples: int) -> int:
+        if self.packed12:
+            return samples * 3 // 2
+        return samples * int(math.ceil(self.params.bitDepth / 8.0))
 
     def startAcquisition(self) -> None:
         if not self.init():
@@ -100,14 +108,13 @@ class VirtualOCTSystem(AcquisitionSystem):
                 self.on_acquisition_stopped()
             return
         p = self.params
-        elem = int(math.ceil(p.bitDepth / 8.0))
-        n_elem = p.bscansPerBuffer * p.samplesPerLine * p.ascansPerBscan
-        offset = self.bscan_offset * p.samplesPerLine * p.ascansPerBscan * elem            # virtualoctsystem.cpp:167
+        n_bytes = self._bytes(p.bscansPerBuffer * p.samplesPerLine * p.ascansPerBscan)
+        offset = self._bytes(self.bscan_offset * p.samplesPerLine * p.ascansPerBscan)      # virtualoctsystem.cpp:167
         with open(self.file_path, "rb") as f:
             f.seek(offset)
-            b0 = f.read(n_elem * elem)
-            f.seek(offset + (n_elem * elem if self.buffers_from_file == 2 else 0))          # :175-179
-            b1 = f.read(n_elem * elem)
+            b0 = f.read(n_bytes)
+            f.seek(offset + (n_bytes if self.buffers_from_file == 2 else 0))                # :175-179
+            b1 = f.read(n_bytes)
         for dst, src in ((self.buffer.bufferArray[0], b0), (self.buffer.bufferArray[1], b1)):
             dst[: len(src)] = np.frombuffer(src, np.uint8)
         self.acqusitionRunning = True

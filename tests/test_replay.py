@@ -99,3 +99,18 @@ def test_replay_through_the_cuda_pipeline(tmp_path):
     # the last processed buffer is one of the two halves of the file (which one depends on where the handshake started)
     reports = [parity_report(out, orc.process(q, vol[i * b:(i + 1) * b])[0], q) for i in range(2)]
     assert min(r["frac_outside"] for r in reports) <= 1e-4, reports
+
+
+def test_packed12_file_replay_delivers_packed_buffers(tmp_path):
+    """extension: a raw file of 12-bit packed samples is replayed with 3/2 bytes per sample"""
+    from octproz_b200.packing import pack12, unpack12
+    n, a, b = 64, 4, 2
+    vol = (np.arange(2 * b * a * n, dtype=np.uint32) * 7 % 4096).astype(np.uint16).reshape(2 * b, a, n)
+    path = str(tmp_path / "packed.raw")
+    pack12(vol).tofile(path)
+    vos = VirtualOCTSystem(path, 12, n, a, b, packed12=True, sync_with_processing=False)
+    seen = []
+    vos.on_acquisition_started = lambda s: (seen.extend(unpack12(np.array(s.buffer.bufferArray[i][: b * a * n * 3 // 2])) for i in (0, 1)), s.stopAcquisition())
+    vos.startAcquisition()
+    assert len(seen) == 2
+    assert np.array_equal(seen[0].reshape(b, a, n), vol[:b]) and np.array_equal(seen[1].reshape(b, a, n), vol[b:])
