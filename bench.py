@@ -156,6 +156,9 @@ def main():
     ap.add_argument("--enface", default="p2p", choices=["p2p", "nccl"], help="multi-GPU en-face gather: own peer-memory kernel or NCCL")
     ap.add_argument("--no-packed", action="store_true", help="skip the 12-bit packed-input extension measurement")
     ap.add_argument("--cpu-bscans", type=int, default=0, help="B-scans in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-numa", action="store_true", help="do not move the host thread to the GPU-local CPUs before pinning the host buffers")
+    ap.add_argument("--separate-conversion", action="store_true",
+                    help="end-to-end leg: floatToOutput as its own pass (the reference's order) instead of folded into the fused kernel's epilogue")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -202,6 +205,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mode = {"fused": _lib.FFT_FUSED, "split": _lib.FFT_SPLIT, "cufft": _lib.FFT_CUFFT}[args.mode]
 
+    # host buffers are pinned from a thread on the GPU-local CPUs: first touch puts them on the GPU's NUMA node (octproz_b200/hostmem.py)
+    from octproz_b200.hostmem import local_affinity
+    aff = local_affinity(local, cpus=set() if args.no_numa else None)
+    host_numa = aff.__enter__()
+
     raw_np = [make_raw(q, seed_offset=16 * rank), make_raw(q, seed_offset=16 * rank + 8)]
     h_raw = [torch.from_numpy(x).pin_memory() for x in raw_np]
     d_raw = [x.cuda(non_blocking=False) for x in h_raw]             # two distinct 256 MiB inputs: larger than L2 (126 MB)
@@ -210,7 +218,8 @@ def main():
     h_stream = [np.zeros(conv_bytes, np.uint8) for _ in range(2)]   # plain host memory; the library pins it like the reference (cuda_code.cu:661)
 
     qq = copy.deepcopy(q)
-    p = OctPipeline(fft_mode=mode, device=local, bscan_index_base=(rank * b) % 2)
+    p = OctPipeline(fft_mode=mode, device=local, bscan_index_base=(rank * b) % 2,
+                    flags=_lib.FLAG_SEPARATE_CONVERSION if args.separate_conversion else 0)
     if not p.initializeCuda(None, None, qq):
         raise SystemExit("initializeCuda failed: " + getattr(p, "_create_error", ""))
     enface = torch.empty(a * b, dtype=torch.float32, device="cuda")
@@ -316,6 +325,7 @@ def main():
         p.octCudaPipeline(h_raw[i & 1].numpy())
     sync_all()
     e2e_steps = max(1, min(args.steps, 200))
+    e2e_launches0 = p.launch_count()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         p.octCudaPipeline(h_raw[i & 1].numpy())
@@ -328,6 +338,7 @@ def main():
     clocks = sampler.stop()
     e2e_mhz = world * ascans_per_step * e2e_steps / e2e_s / 1e6
     checksum = int(h_stream[0][:4096].view(np.uint16).sum())
+    e2e_launches = (p.launch_count() - e2e_launches0) / e2e_steps
     p.cuda_unregisterStreamingBuffers()
 
     # ---- extension beside the headline (N = 1, 12-bit workload): the same volume delivered 12-bit PACKED (3 bytes per 2 samples,
@@ -370,6 +381,8 @@ def main():
             pp.cleanupCuda()
             del hp, dp
 
+    aff.__exit__(None, None, None)          # the CPU baseline gets every core again
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1:
@@ -395,7 +408,10 @@ def main():
                                                                        if gather_impl == "p2p" else ", NCCL all-gather of the en-face slice every step") if world > 1 else "")),
             "e2e": {"value": e2e_mhz, "unit": "MHz (1e6 A-scans/s)", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": conv_bytes,
                     "ms_per_step": e2e_s * 1e3 / e2e_steps, "steps": e2e_steps, "timer": "host wall clock between device synchronisations, max over ranks",
-                    "checksum": checksum},
+                    "checksum": checksum, "gpu_launches_per_step": e2e_launches,
+                    "conversion": "floatToOutput as a separate pass" if args.separate_conversion or args.mode != "fused"
+                    else "floatToOutput folded into the fused kernel's epilogue (u16 line written beside the float line)",
+                    "host_numa": host_numa},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "host_cores": ncores}
     if packed is not None:
         line["packed12"] = packed

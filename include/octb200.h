@@ -61,6 +61,11 @@ enum { OCTB200_DISPLAY_AVERAGING = 0, OCTB200_DISPLAY_MIP = 1 };
    The fused kernel unpacks in its slot conversion; Lanczos / rolling-mean / SPLIT / CUFFT chains unpack once into HBM first. */
 enum { OCTB200_PACK_CONTAINER = 0, OCTB200_PACK_12P = 1 };
 
+/* octb200_config.flags.  SEPARATE_CONVERSION: run floatToOutput (cuda_code.cu:943-967) as its own pass over the finished slab, as
+   the reference does (cuda_code.cu:1366), instead of writing the converted u16 line from the fused kernel's epilogue (the default
+   when the slab is final after that kernel; results are bit-identical, the flag exists for A/B measurement) */
+enum { OCTB200_FLAG_SEPARATE_CONVERSION = 1 };
+
 /* which kernels run the FFT stage */
 enum {
 	OCTB200_FFT_AUTO = 0,        /* FUSED when samplesPerLine is 1024 or 2048 and the container is u16, else best available */
@@ -82,7 +87,8 @@ typedef struct {
 	uint32_t bscanIndexBase;    /* multi-GPU shards: index (within the un-sharded buffer) of this shard's
 	                               first B-scan, so "flip every even B-scan" (cuda_code.cu:795) keeps its parity */
 	uint32_t inputPacking;      /* OCTB200_PACK_*: how the raw buffer stores its samples */
-	uint32_t reserved[2];
+	uint32_t flags;             /* OCTB200_FLAG_* */
+	uint32_t reserved[1];
 } octb200_config;
 
 /* the [processing] block of OctAlgorithmParameters (octalgorithmparameters.h:108-166, 195-199) */

@@ -35,13 +35,14 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NOT_READY = 0, -1, -2, -3, -4
 FFT_AUTO, FFT_FUSED, FFT_SPLIT, FFT_CUFFT = 0, 1, 2, 3
 INTERP_LINEAR, INTERP_CUBIC, INTERP_LANCZOS = 0, 1, 2
 PACK_CONTAINER, PACK_12P = 0, 1
+FLAG_SEPARATE_CONVERSION = 1
 
 
 class Config(C.Structure):
     _fields_ = [("samplesPerLine", C.c_uint32), ("ascansPerBscan", C.c_uint32), ("bscansPerBuffer", C.c_uint32),
                 ("buffersPerVolume", C.c_uint32), ("bitDepth", C.c_uint32), ("device", C.c_int32),
                 ("rawSlots", C.c_int32), ("fftMode", C.c_int32), ("bscanIndexBase", C.c_uint32),
-                ("inputPacking", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+                ("inputPacking", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32 * 1)]
 
 
 class Params(C.Structure):

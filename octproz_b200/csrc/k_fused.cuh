@@ -116,7 +116,9 @@ __device__ __forceinline__ void issue_line_load(const FusedArgs& a, int gline, u
 	bulk_g2s(slot + (clo - lo) * 2, a.raw + clo, bytes, bar);
 }
 
-template <int R, int SA, bool ROLL, int SRC>
+/* CONV: the epilogue also writes the line converted to u16 containers (floatToOutput, cuda_code.cu:943-967) into a.convOut.  A kernel
+ * template parameter, not a run-time branch: the kernels without conversion stay instruction-for-instruction what they were. */
+template <int R, int SA, bool ROLL, int SRC, bool CONV = false>
 __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(const FusedArgs a) {
 	constexpr int N = 1024 * R;
 	constexpr int H = N / 2;
@@ -362,7 +364,10 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			float* o = a.out + (size_t)blockIdx.y * a.trialOutStride + ((size_t)b * a.A + al) * H;
 #if OCT_TMEM_LUT
 			float egVal = 0.f;
-			if (R == 1 || p == 0) epilogue_tmem<R, 0>(lane, v, a.epi, tq, o, egK2, egVal); else epilogue_tmem<R, 16>(lane, v, a.epi, tq, o, egK2, egVal);
+			ConvOut co;
+			co.line = CONV ? a.convOut + ((size_t)b * a.A + al) * H : nullptr;
+			co.scale = a.convScale;
+			if (R == 1 || p == 0) epilogue_tmem<R, 0, CONV>(lane, v, a.epi, tq, o, co, egK2, egVal); else epilogue_tmem<R, 16, CONV>(lane, v, a.epi, tq, o, co, egK2, egVal);
 			if (egK2 >= 0 && (R == 1 || p == (egK2 >> 4)) && lane == (int)(a.eg.frameNr & 31u)) gather_store(a.eg, (unsigned)(b * a.A + al), egVal);
 #else
 			if (R == 1 || p == 0) epilogue_scaled<0>(lane, v, a.epi, sMean, sPpbg, o); else epilogue_scaled<16>(lane, v, a.epi, sMean, sPpbg, o);

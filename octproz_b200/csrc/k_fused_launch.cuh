@@ -12,12 +12,13 @@ inline int fused_pick_groups(int R, int sa, bool roll, int src, int HB, int HA) 
 	return groups;
 }
 
-template <int R, int SA, bool ROLL, int SRC>
+template <int R, int SA, bool ROLL, int SRC, bool CONV = false>
 cudaError_t launch_fused_t(const FusedArgs& a, int smCount, cudaStream_t st) {
+	if (CONV != (a.convOut != nullptr)) return cudaErrorInvalidValue;
 	const int groups = fused_pick_groups(R, SA, ROLL, SRC, a.HB, a.HA);
 	if (groups < 1) return cudaErrorInvalidConfiguration;
 	const FusedSmem L = fused_smem_layout(R, SA, ROLL, SRC, a.HB, a.HA, groups);
-	auto k = oct_fused_kernel<R, SA, ROLL, SRC>;
+	auto k = oct_fused_kernel<R, SA, ROLL, SRC, CONV>;
 	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
 	if (e != cudaSuccess) return e;
 	int grid = smCount;

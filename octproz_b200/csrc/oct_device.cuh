@@ -146,6 +146,11 @@ struct FusedArgs {
 	int trials;              /* 0 / 1: plain launch */
 	int trialLutStride;      /* float4 elements between the LUT images of consecutive trials */
 	long long trialOutStride;/* floats between the output slabs of consecutive trials */
+	/* floatToOutput (cuda_code.cu:943-967) folded into the epilogue: besides the float line, the same pass writes the line converted to
+	 * the acquisition's u16 container (the buffer the stream-to-host D2H copies), so the converted output costs 1 B/sample of extra
+	 * writes instead of a second kernel reading the slab back (6 B per output).  NULL: off. */
+	unsigned short* convOut; /* [lines][N/2] u16 containers, same line order as `out` */
+	float convScale;         /* 2^bits - 1 of cuda_code.cu:948-958 (1023, 4095, 65535) */
 };
 
 /* where a line comes from: u16 containers (the reference's raw format), float2 FFT input written by the pre-FFT kernel, or

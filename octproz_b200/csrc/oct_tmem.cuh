@@ -263,9 +263,18 @@ __device__ __forceinline__ void combine_store_tmem(int lane, int p, float2 (&v)[
 	});
 }
 
-/* ---- epilogue with the FPN line / background from TMEM (cf. epilogue_scaled_t) ---- */
-template <int R, int K2LO, bool LOG, bool FPN, bool PPBG>
-__device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, int egK2, float& egVal) {
+/* ---- epilogue with the FPN line / background from TMEM (cf. epilogue_scaled_t) ----
+ * CONV: floatToOutput (cuda_code.cu:943-967) into u16 containers in the same pass (the fused kernel only takes u16 raw data, and the
+ * output container is the input's).  The reference computes
+ * (container)((double)saturate(x) * K), K = 2^bits - 1, i.e. floor of the exact product.  One round-toward-zero FMA gives the same
+ * integer without the conversion pipe: saturate(x) * K + 2^23 rounded toward zero is exactly 2^23 + floor(saturate(x) * K)
+ * (the product is >= 0 and K < 2^23, so the ulp of the sum is 1), and its low mantissa bits are the container value. */
+struct ConvOut {
+	unsigned short* line;    /* converted line (same bin order as outLine); unused without CONV */
+	float scale;
+};
+template <int R, int K2LO, bool LOG, bool FPN, bool PPBG, bool CONV>
+__device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co, int egK2, float& egVal) {
 	using M = TmemMap<R>;
 	const float sA = e.scaleA, sB = e.scaleB, bw = e.ppbgWeight, bo = e.ppbgOffset;
 	static_for<0, 4>([&](auto gc) {
@@ -284,23 +293,24 @@ __device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32],
 			float o = LOG ? fmaf(oct_lg2(pw), sA, sB) : fmaf(oct_sqrt(pw), sA, sB);
 			if constexpr (PPBG) o = saturate01(o - fmaf(bw, bgv[i], bo));
 			outLine[z] = o;
+			if constexpr (CONV) co.line[z] = (unsigned short)__float_as_uint(__fmaf_rz(__saturatef(o), co.scale, 8388608.0f));
 			if (k2 == egK2) egVal = o;                   /* uniform compare: the displayed en-face bin stays in a register */
 		});
 	});
 }
-template <int R, int K2LO>
-__device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, int egK2, float& egVal) {
+/* runtime flags -> one uniform branch per line instead of three per output */
+template <int R, int K2LO, bool CONV>
+__device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co, int egK2, float& egVal) {
 	const int sel = (e.logMode ? 1 : 0) | (e.fpn ? 2 : 0) | (e.ppbg ? 4 : 0);
 	switch (sel) {
-	case 0: epilogue_tmem_t<R, K2LO, false, false, false>(lane, v, e, tq, outLine, egK2, egVal); break;
-	case 1: epilogue_tmem_t<R, K2LO, true, false, false>(lane, v, e, tq, outLine, egK2, egVal); break;
-	case 2: epilogue_tmem_t<R, K2LO, false, true, false>(lane, v, e, tq, outLine, egK2, egVal); break;
-	case 3: epilogue_tmem_t<R, K2LO, true, true, false>(lane, v, e, tq, outLine, egK2, egVal); break;
-	case 4: epilogue_tmem_t<R, K2LO, false, false, true>(lane, v, e, tq, outLine, egK2, egVal); break;
-	case 5: epilogue_tmem_t<R, K2LO, true, false, true>(lane, v, e, tq, outLine, egK2, egVal); break;
-	case 6: epilogue_tmem_t<R, K2LO, false, true, true>(lane, v, e, tq, outLine, egK2, egVal); break;
-	default: epilogue_tmem_t<R, K2LO, true, true, true>(lane, v, e, tq, outLine, egK2, egVal); break;
+	case 0: epilogue_tmem_t<R, K2LO, false, false, false, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 1: epilogue_tmem_t<R, K2LO, true, false, false, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 2: epilogue_tmem_t<R, K2LO, false, true, false, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 3: epilogue_tmem_t<R, K2LO, true, true, false, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 4: epilogue_tmem_t<R, K2LO, false, false, true, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 5: epilogue_tmem_t<R, K2LO, true, false, true, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 6: epilogue_tmem_t<R, K2LO, false, true, true, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	default: epilogue_tmem_t<R, K2LO, true, true, true, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
 	}
 }
-
 }  // namespace octb200

@@ -354,6 +354,14 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 	int fpnHeight = (int)q.bscansForNoiseDetermination * p->A;
 	if (fpnHeight > p->lines) fpnHeight = p->lines;
 
+	/* converted output for the stream-to-host path (cuda_code.cu:1357-1372): which of the two device buffers this call fills, and
+	   whether floatToOutput is folded into the main kernel's epilogue (the slab must be final after it, u16 containers) */
+	const bool wantConv = q.streamToHost && p->hostStream[0] && p->hostStream[1];
+	const bool convThisBuffer = wantConv && (p->streamedBuffers % (q.streamingBuffersToSkip + 1) == 0);     /* cuda_code.cu:1358 */
+	const int convSlot = convThisBuffer ? (int)((p->streamingBufferNumber + 1) % 2) : -1;
+	const bool convFused = convThisBuffer && mode == OCTB200_FFT_FUSED && !sinus && !ppbgRecord && p->rawBytes == 2 &&
+	                       !(p->cfg.flags & OCTB200_FLAG_SEPARATE_CONVERSION);
+
 	bool gatherDone = false;
 	if (mode == OCTB200_FFT_CUFFT) {
 		PreArgs pa = pre_args(p, st, dRaw, p->lines);
@@ -395,6 +403,11 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 			fa.eg = next_gather(p, p->eg.autoFrame, p->eg.autoFrames, p->eg.autoFn);
 			gatherDone = true;
 		}
+		if (convFused) {
+			if (p->convPending[convSlot]) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evConvFree[convSlot], 0)); p->convPending[convSlot] = false; }
+			fa.convOut = static_cast<unsigned short*>(p->dOutConv[convSlot]);
+			fa.convScale = (float)((1u << (p->cfg.bitDepth <= 10 ? 10 : p->cfg.bitDepth <= 12 ? 12 : 16)) - 1u);
+		}
 		CK(p, launch_fused(p->R, st.sa, st.roll, src, fa, p->smCount, p->sCompute)); p->launches++;
 	}
 
@@ -420,7 +433,6 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 
 	/* ---- streaming to the host (cuda_code.cu:1357-1386,1595-1604) ---- */
 	const bool wantFloat = q.streamFloatToHost && p->hostFloat[0] && p->hostFloat[1];
-	const bool wantConv = q.streamToHost && p->hostStream[0] && p->hostStream[1];
 	if (wantFloat || wantConv) CK(p, cudaEventRecord(p->evComputeDone, p->sCompute));
 	if (wantFloat) {
 		p->floatStreamingBufferNumber = (p->floatStreamingBufferNumber + 1) % 2;
@@ -432,13 +444,15 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 	}
 	if (wantConv) {
 		p->currentBufferNr = p->bufferNumberInVolume;
-		if (p->streamedBuffers % (q.streamingBuffersToSkip + 1) == 0) {
+		if (convThisBuffer) {
 			p->streamedBuffers = 0;
-			p->streamingBufferNumber = (p->streamingBufferNumber + 1) % 2;
-			const int i = (int)p->streamingBufferNumber;
-			if (p->convPending[i]) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evConvFree[i], 0)); p->convPending[i] = false; }
-			CK(p, launch_float_to_output(p->dOutConv[i], slab, (int)p->cfg.bitDepth, p->S / 2, p->smCount, p->sCompute)); p->launches++;
-			CK(p, cudaEventRecord(p->evComputeDone, p->sCompute));
+			p->streamingBufferNumber = (unsigned)convSlot;
+			const int i = convSlot;
+			if (!convFused) {
+				if (p->convPending[i]) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evConvFree[i], 0)); p->convPending[i] = false; }
+				CK(p, launch_float_to_output(p->dOutConv[i], slab, (int)p->cfg.bitDepth, p->S / 2, p->smCount, p->sCompute)); p->launches++;
+				CK(p, cudaEventRecord(p->evComputeDone, p->sCompute));
+			}
 			CK(p, cudaStreamWaitEvent(p->sD2H, p->evComputeDone, 0));
 			CK(p, cudaMemcpyAsync(p->hostStream[i], p->dOutConv[i], (size_t)(p->S / 2) * p->rawBytes, cudaMemcpyDeviceToHost, p->sD2H));
 			CK(p, cudaEventRecord(p->evConvFree[i], p->sD2H)); p->convPending[i] = true;

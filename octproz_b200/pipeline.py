@@ -32,13 +32,14 @@ def _ptr(x) -> int:
 
 class OctPipeline:
     def __init__(self, fft_mode: int = _lib.FFT_AUTO, device: int = -1, raw_slots: int = 2, bscan_index_base: int = 0,
-                 input_packing: int = _lib.PACK_CONTAINER):
+                 input_packing: int = _lib.PACK_CONTAINER, flags: int = 0):
         """input_packing = PACK_12P: the raw buffers hold 12-bit samples packed two per three bytes (octproz_b200.packing.pack12),
-        an extension over the reference's container formats"""
+        an extension over the reference's container formats.  flags: _lib.FLAG_* (octb200_config.flags)"""
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self._fft_mode, self._device, self._raw_slots, self._bscan_base = fft_mode, device, raw_slots, bscan_index_base
         self._packing = input_packing
+        self._flags = flags
         self.params: OctAlgorithmParameters | None = None
         self._callbacks = None
 
@@ -62,7 +63,7 @@ class OctPipeline:
         (numpy arrays or None); they are pinned like the reference does (cuda_code.cu:1135-1136)."""
         cfg = _lib.Config(int(params.samplesPerLine), int(params.ascansPerBscan), int(params.bscansPerBuffer),
                           int(params.buffersPerVolume), int(params.bitDepth), int(self._device), int(self._raw_slots),
-                          int(self._fft_mode), int(self._bscan_base), int(self._packing))
+                          int(self._fft_mode), int(self._bscan_base), int(self._packing), int(self._flags))
         rc = self._lib.octb200_create(C.byref(cfg), C.byref(self._h))
         if rc != _lib.OK:
             self._h = C.c_void_p()
