@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			if (R == 1 || p == 0) epilogue_tmem<R, 0, CONV>(lane, v, a.epi, tq, o, co, egK2, egVal); else epilogue_tmem<R, 16, CONV>(lane, v, a.epi, tq, o, co, egK2, egVal);
 			if (egK2 >= 0 && (R == 1 || p == (egK2 >> 4)) && lane == (int)(a.eg.frameNr & 31u)) gather_store(a.eg, (unsigned)(b * a.A + al), egVal);
 #else
+			static_assert(!CONV, "the converted output is written by the tensor-memory epilogue only (OCT_TMEM_LUT = 1)");
 			if (R == 1 || p == 0) epilogue_scaled<0>(lane, v, a.epi, sMean, sPpbg, o); else epilogue_scaled<16>(lane, v, a.epi, sMean, sPpbg, o);
 #endif
 		}

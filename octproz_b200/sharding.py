@@ -4,7 +4,8 @@ Every stage of the path is per A-scan or per B-scan, so the shards never exchang
   * the fixed-pattern-noise line (N complex floats, 8 KB): determined by rank 0 from the first B-scans of the buffer
     (cuda_code.cu:1520-1522) and broadcast once (or per buffer in continuous mode);
   * the displayed en-face slice: each rank extracts its A x B_local floats, one all_gather assembles the frame
-    (the only collective on the display path; the volume itself stays sharded in HBM).
+    (the only collective on the display path; the volume itself stays sharded in HBM);
+  * the 3-D volume view, when enabled: each rank's u8 voxels, one all_gather (`volume_view`).
 The en-face gather has two implementations: `enface` (local extraction + one all_gather: NCCL / gloo) and
 `connect_enface_peers` + `enface_p2p` (the library's own kernel stores every value straight into all ranks' frame windows
 over NVLink peer memory and publishes a sequence flag: one kernel, no NCCL call on the display path).
@@ -103,6 +104,25 @@ class ShardedPipeline:
         # the reference writes the frame reversed (index (E-1)-i): global order = shards in reverse rank order
         out = [parts[r][: a * shard_bounds(btot, self.world, r)[1]] for r in reversed(range(self.world))]
         return torch.cat(out)
+
+    # ---- 3-D volume view of the whole (sharded) volume ----
+    def volume_view(self, local_tex):
+        """local_tex: torch uint8 [N/2][B_local][A], this rank's voxels as octb200_volume_u8 lays them out (the GL_R8 3-D texture of
+        updateDisplayedVolume, cuda_code.cu:915-941: x = A-scan, y = B-scan, z = flipped depth).  Returns the texture of the whole
+        volume [N/2][B_total][A] on every rank: one all_gather (64 MiB at 1024 x 512 x 256); the shards are slabs
+        in y, so the gathered parts are concatenated along the B-scan axis of every depth plane."""
+        import torch
+        a, btot = int(self.full.ascansPerBscan), int(self.full.bscansPerBuffer)
+        h = int(self.full.samplesPerLine) // 2
+        mine = local_tex.reshape(h, self.count, a)
+        if self.world == 1 or self.dist is None:
+            return mine
+        counts = [shard_bounds(btot, self.world, r)[1] for r in range(self.world)]
+        pad = torch.zeros((h, max(counts), a), dtype=torch.uint8, device=mine.device)
+        pad[:, : self.count] = mine
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(parts, pad)
+        return torch.cat([parts[r][:, : counts[r]] for r in range(self.world)], dim=1)
 
     # ---- en-face frame gathered by the library's own kernel over peer memory (include/octb200.h: octb200_enface_gather_*) ----
     def connect_enface_peers(self, device=None) -> None:

@@ -156,6 +156,29 @@ def test_full_size_properties():
     p.cleanupCuda()
 
 
+def test_full_size_config4_properties():
+    """BASELINE config 4 at its full size -- 2048 x 1024 x 512, 16-bit (2 GiB raw, 2 GiB processed), full chain with FPN, B-scan
+    flip and sinusoidal scan correction: the buffer is a tile of 8 unique B-scans, so the output is periodic, its first tile is
+    bit-identical to processing the 8 B-scans alone (same FPN line, same kernels) and matches the oracle."""
+    n, a, b = 2048, 1024, 512
+    q = benchmark_params(n, a, b, 16); q.bscanFlip = True; q.sinusoidalScanCorrection = True; q.update_all_curves()
+    small = synth.make_volume(n, a, 8, 16, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+    raw = np.ascontiguousarray(np.tile(small, (b // 8, 1, 1)))
+    assert raw.nbytes == 2 << 30
+    out, ml = run(q, raw, _lib.FFT_FUSED)
+    del raw
+    assert out.shape == (b, a, n // 2) and np.isfinite(out).all()
+    for k in (1, 17, 63):
+        assert np.array_equal(out[:8], out[8 * k:8 * k + 8]), f"tile {k} differs from tile 0"
+    qs = copy.deepcopy(q); qs.bscansPerBuffer = 8
+    out8, ml8 = run(qs, small, _lib.FFT_FUSED)
+    assert np.array_equal(ml8, ml), "FPN line must come from the first B-scan only (cuda_code.cu:1520-1522)"
+    assert np.array_equal(out8, out[:8]), "full-size launch vs the unique tile alone"
+    ref8, _, _ = orc.process(qs, small, mean_line=ml.astype(np.float64), determine_fpn=False)
+    assert_parity(out[:8], ref8, q, max_frac_outside=1e-5, what="config 4 full size vs oracle on the unique tile",
+                  atol_abs=4e-6 * float(np.abs(ml).max()))
+
+
 @pytest.mark.parametrize("mode", list(MODES))
 def test_adversarial_lines(mode):
     n = 1024

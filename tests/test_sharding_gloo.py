@@ -90,6 +90,12 @@ def _worker(rank, world, port, raw, q, ref, ref_enface, errs):
         extract = lambda f, nf, fn: torch.from_numpy(orc.enface_frame(sp.pipe.out, h, q.ascansPerBscan, cnt, f, nf, fn))  # noqa: E731
         full = sp.enface(17, 1, 0, extract)
         assert np.allclose(full.numpy(), ref_enface, rtol=0, atol=2e-6), f"rank {rank}: en-face gather order"
+        # 3-D volume view: u8 texture [depth][B-scan][A-scan] of the whole volume assembled from the per-rank slabs
+        # (cuda_code.cu:928-940); voxel values encode their global coordinates so the order is checked exactly
+        zz, yy, xx = np.meshgrid(np.arange(h), np.arange(q.bscansPerBuffer), np.arange(q.ascansPerBscan), indexing="ij")
+        want_tex = ((zz * 7 + yy * 13 + xx * 3) % 256).astype(np.uint8)
+        full_tex = sp.volume_view(torch.from_numpy(np.ascontiguousarray(want_tex[:, lo:lo + cnt])))
+        assert np.array_equal(full_tex.numpy(), want_tex), f"rank {rank}: volume view order"
         # peer-memory gather: handle exchange + window geometry (the kernel itself is covered by the GPU tests)
         sp.connect_enface_peers()
         g = sp.pipe.gather
