@@ -341,6 +341,35 @@ def main():
     e2e_launches = (p.launch_count() - e2e_launches0) / e2e_steps
     p.cuda_unregisterStreamingBuffers()
 
+    # ---- what the host link of this box can do (context for e2e): pinned H2D of one raw buffer alone, and with a D2H of the
+    #      converted-output size running the other way at the same time (the steady state of the end-to-end loop) ----
+    link = None
+    try:
+        d_probe = torch.empty_like(d_raw[0]); d_conv = torch.empty(conv_bytes, dtype=torch.uint8, device="cuda")
+        h_conv = torch.empty(conv_bytes, dtype=torch.uint8).pin_memory()
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        def h2d_rate(with_d2h, reps=8):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(s_up):
+                e0.record()
+                for i in range(reps):
+                    d_probe.copy_(h_raw[i & 1], non_blocking=True)
+                e1.record()
+            if with_d2h:
+                with torch.cuda.stream(s_dn):
+                    for i in range(2 * reps):
+                        h_conv.copy_(d_conv, non_blocking=True)
+            torch.cuda.synchronize()
+            return bytes_in * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        h2d_rate(False, 2)
+        alone, duplex = h2d_rate(False), h2d_rate(True)
+        link = {"h2d_gbs_alone": alone, "h2d_gbs_with_concurrent_d2h": duplex,
+                "e2e_h2d_gbs": bytes_in * e2e_steps / e2e_s / 1e9, "e2e_frac_of_duplex_h2d": bytes_in * e2e_steps / e2e_s / 1e9 / duplex}
+        del d_probe, d_conv, h_conv
+    except Exception as e:  # noqa: BLE001
+        link = {"error": repr(e)}
+
     # ---- extension beside the headline (N = 1, 12-bit workload): the same volume delivered 12-bit PACKED (3 bytes per 2 samples,
     #      include/octb200.h OCTB200_PACK_12P; the reference only takes containers).  Reported separately, never as `value` / `e2e`. ----
     packed = None
@@ -411,7 +440,7 @@ def main():
                     "checksum": checksum, "gpu_launches_per_step": e2e_launches,
                     "conversion": "floatToOutput as a separate pass" if args.separate_conversion or args.mode != "fused"
                     else "floatToOutput folded into the fused kernel's epilogue (u16 line written beside the float line)",
-                    "host_numa": host_numa},
+                    "host_numa": host_numa, "link": link},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "host_cores": ncores}
     if packed is not None:
         line["packed12"] = packed

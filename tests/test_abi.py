@@ -59,3 +59,16 @@ def test_no_cpu_fallback_without_gpu():
     cfg = _lib.Config(1024, 16, 2, 1, 12, -1, 0, 0, 0)
     rc = L.octb200_create(C.byref(cfg), C.byref(h))
     assert rc == _lib.ERR_CUDA and not h        # fails loudly, never computes on the host
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/octb200.h compiles as strict C99 and a C program drives the library through it (tests/abi/abi_c99.c)"""
+    import subprocess
+    exe = str(tmp_path / "abi_c99")
+    libdir = os.path.join(ROOT, "octproz_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi", "abi_c99.c"), "-o", exe, "-L" + libdir, "-loctb200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "abi ok" in out.stdout
+    assert f"sizeof_config {C.sizeof(_lib.Config)} sizeof_params {C.sizeof(_lib.Params)}" in out.stdout
