@@ -259,5 +259,51 @@ def cmd_estimator():
     p.cleanupCuda()
 
 
+def cmd_randomref():
+    """the seeded random configurations of tests/random_configs.py against the LIVE reference CUDA build (oracle/_ref/libref_cuda.so)
+    on the same raw buffers: per configuration and mode, the parity metric of tests/util.py at the strict 1e-4 tolerance"""
+    from tests.random_configs import describe, random_chain_config
+    from tests.util import parity_report
+    seed = 0x0C7B200 + 7
+    rc = orc.RefCuda()
+    res = []
+    for n in (1024, 2048):
+        for i in range(18):
+            rng = np.random.default_rng([seed, n, i])
+            q, extras = random_chain_config(rng, n)
+            rc.configure(q)
+            q.resampleCurve, q.dispersionCurve, q.windowCurve = rc.curves()
+            raw = synth.make_volume(n, q.ascansPerBscan, q.bscansPerBuffer, q.bitDepth, resample=q.resampleCurve if q.resampling else None,
+                                    dispersion=q.dispersionCurve if q.dispersionCompensation else None)
+            h1 = np.ascontiguousarray(raw).copy(); h2 = h1.copy()
+            rc.init(h1, h2)
+            if extras["pp_background"] is not None:
+                rc.L.refcuda_set_postprocess_background(extras["pp_background"].ctypes.data, n // 2)
+            rc.process(h1)
+            ref = rc.output(0)
+            ml = rc.mean_line() if q.fixedPatternNoiseRemoval else None
+            rc.cleanup()
+            floor = 4e-6 * float(np.abs(ml).max()) if ml is not None else 0.0
+            row = {"n": n, "i": i, "config": describe(q)}
+            for mname, mode in MODES.items():
+                qq = copy.deepcopy(q)
+                p = OctPipeline(fft_mode=mode)
+                assert p.initializeCuda(None, None, qq), getattr(p, "_create_error", "")
+                if ml is not None:
+                    p.set_fpn_mean_line(ml)
+                if extras["pp_background"] is not None:
+                    qq.loadPostProcessingBackground(extras["pp_background"])
+                p.octCudaPipeline(h1); p.sync()
+                out = p.copy_output(0)
+                p.cleanupCuda()
+                row[mname] = parity_report(out, ref, q, saturated=bool(q.postProcessBackgroundRemoval), atol_abs=floor)
+            res.append(row)
+            print("randomref", n, i, {m: (round(row[m]["max_ratio"], 2), row[m]["frac_outside"]) for m in MODES}, flush=True)
+    json.dump(res, open(os.path.join(OUT, "randomref.json"), "w"), indent=1)
+    worst = max(max(r[m]["frac_outside"] for m in MODES) for r in res)
+    print("randomref worst frac_outside", worst, flush=True)
+
+
 if __name__ == "__main__":
-    {"estimator": cmd_estimator, "perf": cmd_perf, "quick": cmd_quick, "parity": cmd_parity, "refcuda": cmd_refcuda, "timing": cmd_timing}[sys.argv[1]]()
+    {"estimator": cmd_estimator, "perf": cmd_perf, "quick": cmd_quick, "parity": cmd_parity, "refcuda": cmd_refcuda, "timing": cmd_timing,
+     "randomref": cmd_randomref}[sys.argv[1]]()
