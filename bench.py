@@ -37,7 +37,11 @@ WORKLOADS = {
     # name: (samplesPerLine, ascansPerBscan, bscansPerBuffer, bitDepth)
     "1024x512x256-12bit": (1024, 512, 256, 12),
     "2048x1024x128-16bit": (2048, 1024, 128, 16),
+    # BASELINE.json configs[3]: "2048-sample A-scan x 1024 x 512 16-bit, full pipeline incl. FPN + sinusoidal correction" (2 GiB raw per buffer)
+    "2048x1024x512-16bit-config4": (2048, 1024, 512, 16),
 }
+# parameter overrides on top of the benchmark INI settings, per workload
+WORKLOAD_PARAMS = {"2048x1024x512-16bit-config4": dict(bscanFlip=True, sinusoidalScanCorrection=True)}
 DEFAULT_WORKLOAD = "1024x512x256-12bit"
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -165,10 +169,13 @@ def main():
     n, a, b, bits = WORKLOADS[args.workload]
     from octproz_b200 import benchmark_params
     q = benchmark_params(n, a, b, bits)
+    for k, v in WORKLOAD_PARAMS.get(args.workload, {}).items():
+        setattr(q, k, v)
     q.update_all_curves()
     ncores = os.cpu_count() or 1
     ascans_per_step = a * b
-    config = {"workload": f"{args.workload} volume, benchmark INI settings (cubic k-lin + dispersion + Hann + FPN once + log), "
+    extra_chain = " + B-scan flip + sinusoidal scan correction" if q.sinusoidalScanCorrection else ""
+    config = {"workload": f"{args.workload} volume, benchmark INI settings (cubic k-lin + dispersion + Hann + FPN once + log){extra_chain}, "
                           f"u16 container, synthetic", "samples_per_ascan": n, "ascans_per_bscan": a, "bscans_per_buffer": b,
               "bit_depth": bits}
 
@@ -432,7 +439,7 @@ def main():
             "volumes_per_s": value * 1e6 / ascans_per_step, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours",
-            "config": dict(config, mode=args.mode, l2="two alternating 256 MiB inputs and 256 MiB outputs per GPU: larger than the 126 MB L2",
+            "config": dict(config, mode=args.mode, l2=f"two alternating {bytes_in >> 20} MiB inputs and {(n // 2) * a * b * 4 >> 20} MiB outputs per GPU: larger than the 126 MB L2",
                            parallelism=f"b-scan sharding x{world}" + ((", en-face slice gathered every step inside the fused kernel's epilogue over NVLink peer memory"
                                                                        if gather_impl == "p2p" else ", NCCL all-gather of the en-face slice every step") if world > 1 else "")),
             "e2e": {"value": e2e_mhz, "unit": "MHz (1e6 A-scans/s)", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": conv_bytes,

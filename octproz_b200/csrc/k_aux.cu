@@ -246,31 +246,79 @@ cudaError_t launch_fpn_minvar(float2* meanLine, const float2* in, int bins, int 
 }
 
 /* ------------------------------------------------------------------ sinusoidal scan correction */
+/* cuda_code.cu:491-514 (+ the D2D copy of :1552, which disappears: the main kernel writes the source into a scratch slab).
+ * out[l][k][j] = lerp(in[flat line l*A + n][j], in[flat line l*A + n + 1][j], x - n), x = curve[k], n = (int)x; the reference
+ * addresses the slab flat (so n + 1 may be line 0 of the next B-scan) and leaves the very last line of the buffer untouched.
+ * One warp per output line: x, n and the two source lines are warp-uniform, the line is moved as float4 (no per-element integer
+ * division, which made the first version of this kernel instruction-bound: three 64-bit div/mod per output).  Neighbouring output
+ * lines share their source lines (d curve / dk is 0.64 in the middle of the scan), consecutive warps take consecutive lines, so
+ * the second read of a source line hits L1/L2: DRAM traffic is ~4 B read + 4 B written per output.
+ * Optional in the same pass: post-process background removal (cuda_code.cu:757-767) and, CONV, the converted u16 line of
+ * floatToOutput (cuda_code.cu:943-967; same round-toward-zero FMA as the fused kernel's epilogue, oct_tmem.cuh). */
+__device__ __forceinline__ float sinus_lerp(float f0, float f1, float fr) { return f0 + (f1 - f0) * fr; }
+__device__ __forceinline__ unsigned short to_u16_container(float v, float scale) {
+	return (unsigned short)__float_as_uint(__fmaf_rz(__saturatef(v), scale, 8388608.0f));
+}
+template <bool CONV>
 __global__ void __launch_bounds__(256) sinusoidal_kernel(float* __restrict__ out, const float* __restrict__ in,
-                                                         const float* __restrict__ curve, int H, int A, long long samples,
-                                                         int ppbgOn, const float* __restrict__ ppbg, float w, float o) {
-	for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < samples; idx += (long long)gridDim.x * blockDim.x) {
-		float r;
-		const int j = (int)(idx % H);
-		if (idx < samples - H) {
-			const int k = (int)((idx / H) % A);
-			const long long l = idx / ((long long)H * A);
-			const float x = __ldg(curve + k);
-			const long long x0 = (long long)((int)x) * H + j + l * (long long)H * A;
-			const float f0 = in[x0], f1 = in[x0 + H];
-			r = f0 + (f1 - f0) * (x - (float)(int)x);
+                                                         const float* __restrict__ curve, int H, int A, int lines, int vec,
+                                                         int ppbgOn, const float* __restrict__ ppbg, float w, float o,
+                                                         unsigned short* __restrict__ conv, float convScale) {
+	const int lane = threadIdx.x & 31;
+	const int warpsPerBlock = blockDim.x >> 5;
+	for (int line = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); line < lines; line += gridDim.x * warpsPerBlock) {
+		const int l = line / A, k = line - l * A;
+		const bool last = line == lines - 1;      /* the last line keeps its uncorrected value (cuda_code.cu:499) */
+		const float x = last ? 0.0f : __ldg(curve + k);
+		const int n = (int)x;
+		const float fr = x - (float)n;
+		const float* s0 = last ? in + (size_t)line * H : in + ((size_t)l * A + n) * H;
+		const float* s1 = last ? s0 : s0 + H;
+		float* d = out + (size_t)line * H;
+		unsigned short* c = CONV ? conv + (size_t)line * H : nullptr;
+		if (vec) {
+			const int H4 = H >> 2;
+#pragma unroll 4
+			for (int j4 = lane; j4 < H4; j4 += 32) {
+				const float4 a = *reinterpret_cast<const float4*>(s0 + 4 * j4);
+				const float4 b = *reinterpret_cast<const float4*>(s1 + 4 * j4);
+				float4 r;
+				if (last) r = a;
+				else r = make_float4(sinus_lerp(a.x, b.x, fr), sinus_lerp(a.y, b.y, fr), sinus_lerp(a.z, b.z, fr), sinus_lerp(a.w, b.w, fr));
+				if (ppbgOn) {
+					const float4 g = __ldg(reinterpret_cast<const float4*>(ppbg) + j4);
+					r.x = saturate01(r.x - fmaf(w, g.x, o)); r.y = saturate01(r.y - fmaf(w, g.y, o));
+					r.z = saturate01(r.z - fmaf(w, g.z, o)); r.w = saturate01(r.w - fmaf(w, g.w, o));
+				}
+				*reinterpret_cast<float4*>(d + 4 * j4) = r;
+				if constexpr (CONV)
+					*reinterpret_cast<ushort4*>(c + 4 * j4) = make_ushort4(to_u16_container(r.x, convScale), to_u16_container(r.y, convScale),
+					                                                       to_u16_container(r.z, convScale), to_u16_container(r.w, convScale));
+			}
 		} else {
-			r = in[idx];   /* the last line keeps its uncorrected value (cuda_code.cu:499) */
+			for (int j = lane; j < H; j += 32) {
+				const float a = s0[j];
+				float r = last ? a : sinus_lerp(a, s1[j], fr);
+				if (ppbgOn) r = saturate01(r - fmaf(w, __ldg(ppbg + j), o));
+				d[j] = r;
+				if constexpr (CONV) c[j] = to_u16_container(r, convScale);
+			}
 		}
-		if (ppbgOn) r = saturate01(r - fmaf(w, __ldg(ppbg + j), o));
-		out[idx] = r;
 	}
 }
 cudaError_t launch_sinusoidal(float* out, const float* in, const float* curve, int H, int A, long long samples,
-                              int ppbgOn, const float* ppbg, float w, float o, int smCount, cudaStream_t st) {
-	long long blocks = (samples + 255) / 256;
-	if (blocks > (long long)smCount * 16) blocks = (long long)smCount * 16;
-	sinusoidal_kernel<<<(int)blocks, 256, 0, st>>>(out, in, curve, H, A, samples, ppbgOn, ppbg, w, o);
+                              int ppbgOn, const float* ppbg, float w, float o, unsigned short* conv, float convScale,
+                              int smCount, cudaStream_t st) {
+	const long long lines64 = samples / H;
+	if (lines64 < 1 || lines64 > 0x7fffffffLL) return cudaErrorInvalidValue;
+	const int lines = (int)lines64;
+	/* float4 / ushort4 path: line length a multiple of four and every base pointer 16-byte aligned (8 for the containers) */
+	const uintptr_t al = reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(in) | (ppbgOn ? reinterpret_cast<uintptr_t>(ppbg) : 0);
+	const int vec = (H % 4 == 0) && (al & 15) == 0 && (reinterpret_cast<uintptr_t>(conv) & 7) == 0;
+	long long blocks = ((long long)lines + 7) / 8;
+	if (blocks > (long long)smCount * 8) blocks = (long long)smCount * 8;
+	if (conv) sinusoidal_kernel<true><<<(int)blocks, 256, 0, st>>>(out, in, curve, H, A, lines, vec, ppbgOn, ppbg, w, o, conv, convScale);
+	else sinusoidal_kernel<false><<<(int)blocks, 256, 0, st>>>(out, in, curve, H, A, lines, vec, ppbgOn, ppbg, w, o, nullptr, 0.f);
 	return cudaGetLastError();
 }
 

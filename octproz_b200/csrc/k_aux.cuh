@@ -54,7 +54,8 @@ cudaError_t launch_pre(const PreArgs& a, int rawBytes, int sa, bool roll, int sm
 cudaError_t launch_post(const PostArgs& a, int smCount, cudaStream_t st);
 cudaError_t launch_fpn_minvar(float2* meanLine, const float2* in, int bins, int stride, int height, cudaStream_t st);
 cudaError_t launch_sinusoidal(float* out, const float* in, const float* curve, int H, int A, long long samples,
-                              int ppbgOn, const float* ppbg, float w, float o, int smCount, cudaStream_t st);
+                              int ppbgOn, const float* ppbg, float w, float o, unsigned short* conv, float convScale,
+                              int smCount, cudaStream_t st);
 cudaError_t launch_ppbg_record(float* bg, const float* data, int H, int A, cudaStream_t st);
 cudaError_t launch_ppbg_remove(float* data, const float* bg, float w, float o, int H, long long samples, int smCount, cudaStream_t st);
 cudaError_t launch_bscan_frame(float* disp, const float* vol, unsigned Btot, unsigned F, unsigned frameNr, unsigned nFrames, int fn, cudaStream_t st);

@@ -359,8 +359,10 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 	const bool wantConv = q.streamToHost && p->hostStream[0] && p->hostStream[1];
 	const bool convThisBuffer = wantConv && (p->streamedBuffers % (q.streamingBuffersToSkip + 1) == 0);     /* cuda_code.cu:1358 */
 	const int convSlot = convThisBuffer ? (int)((p->streamingBufferNumber + 1) % 2) : -1;
-	const bool convFused = convThisBuffer && mode == OCTB200_FFT_FUSED && !sinus && !ppbgRecord && p->rawBytes == 2 &&
-	                       !(p->cfg.flags & OCTB200_FLAG_SEPARATE_CONVERSION);
+	const bool convFoldable = convThisBuffer && !ppbgRecord && p->rawBytes == 2 && !(p->cfg.flags & OCTB200_FLAG_SEPARATE_CONVERSION);
+	const bool convInSinus = convFoldable && sinus;                                  /* the sinusoidal kernel writes the final slab: any FFT mode */
+	const bool convFused = convFoldable && !sinus && mode == OCTB200_FFT_FUSED;      /* the fused kernel's epilogue does */
+	const float convScale = (float)((1u << (p->cfg.bitDepth <= 10 ? 10 : p->cfg.bitDepth <= 12 ? 12 : 16)) - 1u);   /* cuda_code.cu:948-958 */
 
 	bool gatherDone = false;
 	if (mode == OCTB200_FFT_CUFFT) {
@@ -406,14 +408,16 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		if (convFused) {
 			if (p->convPending[convSlot]) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evConvFree[convSlot], 0)); p->convPending[convSlot] = false; }
 			fa.convOut = static_cast<unsigned short*>(p->dOutConv[convSlot]);
-			fa.convScale = (float)((1u << (p->cfg.bitDepth <= 10 ? 10 : p->cfg.bitDepth <= 12 ? 12 : 16)) - 1u);
+			fa.convScale = convScale;
 		}
 		CK(p, launch_fused(p->R, st.sa, st.roll, src, fa, p->smCount, p->sCompute)); p->launches++;
 	}
 
 	if (sinus) {
+		if (convInSinus && p->convPending[convSlot]) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evConvFree[convSlot], 0)); p->convPending[convSlot] = false; }
 		CK(p, launch_sinusoidal(slab, p->dTmp, p->dSinCurve, p->H, p->A, p->S / 2, ppbgFoldSinus ? 1 : 0, p->dPpbg,
-		                        q.postProcessBackgroundWeight, q.postProcessBackgroundOffset, p->smCount, p->sCompute)); p->launches++;
+		                        q.postProcessBackgroundWeight, q.postProcessBackgroundOffset,
+		                        convInSinus ? static_cast<unsigned short*>(p->dOutConv[convSlot]) : nullptr, convScale, p->smCount, p->sCompute)); p->launches++;
 	}
 	if (ppbgRecord) {
 		/* cuda_code.cu:1558-1567: record from the first B-scan of this buffer, hand it to the host, then remove */
@@ -448,7 +452,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 			p->streamedBuffers = 0;
 			p->streamingBufferNumber = (unsigned)convSlot;
 			const int i = convSlot;
-			if (!convFused) {
+			if (!convFused && !convInSinus) {
 				if (p->convPending[i]) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evConvFree[i], 0)); p->convPending[i] = false; }
 				CK(p, launch_float_to_output(p->dOutConv[i], slab, (int)p->cfg.bitDepth, p->S / 2, p->smCount, p->sCompute)); p->launches++;
 				CK(p, cudaEventRecord(p->evComputeDone, p->sCompute));

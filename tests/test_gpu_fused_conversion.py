@@ -2,7 +2,8 @@
 bit-identical to (a) the oracle's floatToOutput of the float volume the same call produced, (b) the stand-alone conversion pass
 (OCTB200_FLAG_SEPARATE_CONVERSION, the reference's own order of kernels, cuda_code.cu:1366) -- over interpolators, FPN, flip,
 log / linear scaling that over- and undershoots [0, 1], background removal, 10/12/16-bit containers, N = 1024 / 2048, packed input,
-and chains where the slab is NOT final after the main kernel (sinusoidal correction: the separate pass must be kept)."""
+and chains where the slab is NOT final after the main kernel (sinusoidal correction: the kernel that writes the final slab
+converts, in every FFT mode; u8 containers and SPLIT / CUFFT chains without it keep the separate pass)."""
 import copy
 
 import numpy as np
@@ -89,15 +90,54 @@ def test_fused_conversion_packed_input_and_buffer_alternation():
     assert np.array_equal(conv3, conv) and l3 == 1
 
 
-def test_separate_pass_kept_when_the_slab_is_not_final():
-    """sinusoidal scan correction rewrites the slab after the main kernel (cuda_code.cu:1552): the conversion must read the corrected
-    slab, i.e. stay a pass of its own"""
+def stream_mode(q, raw, mode, flags=0):
+    """like stream() for any FFT mode: (float volume, streamed containers of the second call, launches of the second call)"""
+    n, a, b = int(q.samplesPerLine), int(q.ascansPerBscan), int(q.bscansPerBuffer)
+    qq = copy.deepcopy(q); qq.streamToHost = True
+    dt = np.uint8 if q.bitDepth <= 8 else np.uint16
+    s = [np.zeros((b, a, n // 2), dt) for _ in range(2)]
+    got = []
+    p = OctPipeline(fft_mode=mode, flags=flags)
+    assert p.initializeCuda(None, None, qq), getattr(p, "_create_error", "")
+    p.cuda_registerStreamingBuffers(s[0], s[1], s[0].nbytes)
+    p.set_callbacks(streaming=lambda ptr: got.append(ptr))
+    buf = np.ascontiguousarray(raw)
+    p.octCudaPipeline(buf); p.sync()
+    l0 = p.launch_count()
+    p.octCudaPipeline(buf); p.sync()
+    launches = p.launch_count() - l0
+    vol = p.copy_output(0)
+    out = (s[0] if got[-1] == s[0].ctypes.data else s[1]).copy()
+    p.cuda_unregisterStreamingBuffers(); p.cleanupCuda()
+    return vol, out, launches
+
+
+@pytest.mark.parametrize("mode,launches", [(_lib.FFT_FUSED, 2), (_lib.FFT_SPLIT, 3), (_lib.FFT_CUFFT, 4)], ids=["fused", "split", "cufft"])
+def test_conversion_folded_into_the_sinusoidal_kernel(mode, launches):
+    """sinusoidal scan correction rewrites the slab after the main kernel (cuda_code.cu:1552): the kernel that writes the FINAL slab
+    also writes the converted line, whatever ran the FFT -- no separate floatToOutput pass, same bits"""
     n = 1024
-    q = benchmark_params(n, 32, 2); q.sinusoidalScanCorrection = True; q.update_all_curves()
+    q = benchmark_params(n, 32, 2); q.sinusoidalScanCorrection = True; q.bscanFlip = True; q.update_all_curves()
     raw = synth.make_volume(n, 32, 2, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
-    vol, conv, l = stream(q, raw)
+    vol, conv, l = stream_mode(q, raw, mode)
+    vol_s, conv_s, l_s = stream_mode(q, raw, mode, flags=_lib.FLAG_SEPARATE_CONVERSION)
+    assert np.array_equal(vol, vol_s) and np.array_equal(conv, conv_s)
     assert np.array_equal(conv, orc.float_to_output(vol, 12))
-    assert l == 3                                       # main kernel + sinusoidal correction + floatToOutput
+    assert l == launches and l_s == launches + 1, (l, l_s)
+
+
+def test_separate_pass_kept_where_nothing_can_fold_it():
+    """SPLIT / CUFFT chains without a sinusoidal pass, and u8 containers, keep floatToOutput as its own kernel"""
+    n = 1024
+    q = benchmark_params(n, 16, 2); q.update_all_curves()
+    raw = synth.make_volume(n, 16, 2, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+    for mode, launches in ((_lib.FFT_SPLIT, 3), (_lib.FFT_CUFFT, 4)):
+        vol, conv, l = stream_mode(q, raw, mode)
+        assert np.array_equal(conv, orc.float_to_output(vol, 12)) and l == launches, (mode, l)
+    q8 = benchmark_params(n, 16, 2, 8); q8.sinusoidalScanCorrection = True; q8.update_all_curves()
+    raw8 = synth.make_volume(n, 16, 2, 8, resample=q8.resampleCurve, dispersion=q8.dispersionCurve)
+    vol, conv, l = stream_mode(q8, raw8, _lib.FFT_AUTO)
+    assert conv.dtype == np.uint8 and np.array_equal(conv, orc.float_to_output(vol, 8))
 
 
 def test_special_values_convert_like_the_reference():

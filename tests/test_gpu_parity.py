@@ -211,6 +211,24 @@ def test_other_containers_and_line_lengths(bits, n):
         assert_parity(out, ref, q, max_frac_outside=1e-4, what="u32 bitshift")
 
 
+@pytest.mark.parametrize("n,a,b", [(100, 7, 3), (1024, 1, 4), (1024, 2, 3), (1024, 3, 2), (1664, 5, 2), (2048, 64, 1)])
+def test_sinusoidal_correction_geometries(n, a, b):
+    """the sinusoidal kernel (cuda_code.cu:491-514) on line lengths that are not a multiple of four (scalar path), on tiny B-scans
+    where the reference's flat addressing takes the second source line from the NEXT B-scan (A = 1, 2, 3: n + 1 = A), with the
+    background removal folded in, and the untouched last line of the buffer"""
+    q = benchmark_params(n, a, b); q.fixedPatternNoiseRemoval = False; q.sinusoidalScanCorrection = True; q.bscanFlip = True
+    q.postProcessBackgroundRemoval = (a % 2 == 1); q.postProcessBackgroundWeight = 0.6; q.postProcessBackgroundOffset = 0.01
+    q.update_all_curves()
+    bg = (0.1 + 0.05 * np.cos(np.arange(n // 2) / 9.0)).astype(np.float32) if q.postProcessBackgroundRemoval else None
+    raw = synth.make_volume(n, a, b, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+    ref, _, _ = orc.process(q, raw, pp_background=bg)
+    out, _ = run(q, raw, _lib.FFT_AUTO, pp_background=bg)
+    assert_parity(out, ref, q, max_frac_outside=1e-4, saturated=bool(q.postProcessBackgroundRemoval), what=f"sinusoidal N={n} A={a} B={b}")
+    plain = copy.deepcopy(q); plain.sinusoidalScanCorrection = False
+    uncorrected, _ = run(plain, raw, _lib.FFT_AUTO, pp_background=bg)
+    assert np.array_equal(out[-1, -1], uncorrected[-1, -1]), "the last line of the buffer stays uncorrected (cuda_code.cu:499)"
+
+
 def test_fpn_determination_modes_and_slabs():
     n, a, b = 1024, 36, 2
     q = benchmark_params(n, a, b); q.buffersPerVolume = 2; q.bscansForNoiseDetermination = 2; q.update_all_curves()
