@@ -184,26 +184,42 @@ cudaError_t launch_pre(const PreArgs& a, int rawBytes, int sa, bool roll, int sm
 }
 
 /* ------------------------------------------------------------------ post kernel (after cuFFT) */
-__global__ void __launch_bounds__(256) oct_post_kernel(const PostArgs a) {
+/* meanALineSubtraction + postProcessTruncateLog/Lin + bscanFlip (+ postProcessBackgroundRemoval) in one pass over the kept half of
+ * the spectrum (cuda_code.cu:567-584, 699-741, 757-767, 787-807).  One warp per A-scan: line / B-scan / flip bookkeeping is
+ * warp-uniform (no per-element 64-bit division), two bins per 16-byte load. */
+__device__ __forceinline__ float post_one(float2 c, int z, const PostArgs& a) {
+	if (a.epi.fpn) { const float2 m = __ldg(a.meanLine + z); c.x -= m.x; c.y -= m.y; }
+	float o = scale_output(c.x, c.y, a.epi);
+	if (a.epi.ppbg) o = saturate01(o - fmaf(a.epi.ppbgWeight, __ldg(a.ppbg + z), a.epi.ppbgOffset));
+	return o;
+}
+__global__ void __launch_bounds__(256) oct_post_kernel(const PostArgs a, int vec) {
 	const int H = a.N / 2;
-	const long long total = (long long)a.lines * H;
-	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-		const int line = (int)(i / H), z = (int)(i - (long long)line * H);
-		float2 c = a.in[(size_t)line * a.N + z];
-		if (a.epi.fpn) { const float2 m = __ldg(a.meanLine + z); c.x -= m.x; c.y -= m.y; }
-		float o = scale_output(c.x, c.y, a.epi);
-		if (a.epi.ppbg) o = saturate01(o - fmaf(a.epi.ppbgWeight, __ldg(a.ppbg + z), a.epi.ppbgOffset));
+	const int lane = threadIdx.x & 31, warpsPerBlock = blockDim.x >> 5;
+	for (int line = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); line < a.lines; line += gridDim.x * warpsPerBlock) {
 		int b = line / a.A, al = line - b * a.A;
 		if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u) al = a.A - 1 - al;
-		a.out[((size_t)b * a.A + al) * H + z] = o;
+		const float2* in = a.in + (size_t)line * a.N;
+		float* out = a.out + ((size_t)b * a.A + al) * H;
+		if (vec) {
+#pragma unroll 4
+			for (int z2 = lane; z2 < (H >> 1); z2 += 32) {
+				const float4 c = *reinterpret_cast<const float4*>(in + 2 * z2);
+				*reinterpret_cast<float2*>(out + 2 * z2) = make_float2(post_one(make_float2(c.x, c.y), 2 * z2, a), post_one(make_float2(c.z, c.w), 2 * z2 + 1, a));
+			}
+		} else {
+			for (int z = lane; z < H; z += 32) out[z] = post_one(in[z], z, a);
+		}
 	}
 }
 cudaError_t launch_post(const PostArgs& a, int smCount, cudaStream_t st) {
-	const long long total = (long long)a.lines * (a.N / 2);
-	long long blocks = (total + 255) / 256;
-	if (blocks > (long long)smCount * 16) blocks = (long long)smCount * 16;
+	long long blocks = ((long long)a.lines + 7) / 8;
+	if (blocks > (long long)smCount * 8) blocks = (long long)smCount * 8;
 	if (blocks < 1) blocks = 1;
-	oct_post_kernel<<<(int)blocks, 256, 0, st>>>(a);
+	/* 16-byte loads / 8-byte stores: even number of kept bins, line starts aligned */
+	const int H = a.N / 2;
+	const int vec = (H % 2 == 0) && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0;
+	oct_post_kernel<<<(int)blocks, 256, 0, st>>>(a, vec);
 	return cudaGetLastError();
 }
 
@@ -502,23 +518,58 @@ cudaError_t launch_unpack12(uint16_t* out, const void* in, long long octets, int
 	return cudaGetLastError();
 }
 
-/* u8 voxels in the layout of the GL_R8 3-D texture (x = A-scan, y = B-scan in volume, z flipped depth), cuda_code.cu:928-940 */
-__global__ void __launch_bounds__(256) volume_u8_kernel(uint8_t* __restrict__ tex, const float* __restrict__ buf, long long samples,
-                                                         unsigned bufferNr, unsigned B, unsigned A, unsigned Btot, unsigned depth) {
-	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < samples; i += (long long)gridDim.x * blockDim.x) {
-		const unsigned y = (unsigned)((i / depth) % A);
-		const unsigned z = (depth - 1) - (unsigned)(i % depth);
-		const unsigned x = (unsigned)(i / ((long long)A * depth)) + bufferNr * B;
-		const unsigned char voxel = (unsigned char)((double)buf[i] * 255.0);
-		/* surf3Dwrite(voxel, surf, y, x, z): texture dims (width=A, height=Btot, depth) */
-		tex[((size_t)z * Btot + x) * A + y] = voxel;
+/* u8 voxels in the layout of the GL_R8 3-D texture (x = A-scan, y = B-scan in volume, z flipped depth), cuda_code.cu:928-940.
+ * The slab is [B-scan][A-scan][depth] with depth fastest, the texture [depth][B-scan][A-scan] with the A-scan fastest: a transpose of
+ * every B-scan.  The reference (and the first version here) wrote one byte per thread with a stride of A * Btot bytes -- every byte
+ * its own 32-byte sector.  Here a block moves a 64 (A-scans) x 64 (depth) tile through shared memory: coalesced 128-byte reads along
+ * the depth, conversion, 64-byte row writes along the A-scan axis. */
+constexpr int VT = 64, VPITCH = 68;
+__global__ void __launch_bounds__(256) volume_u8_kernel(uint8_t* __restrict__ tex, const float* __restrict__ buf,
+                                                         unsigned bufferNr, unsigned B, unsigned A, unsigned Btot, unsigned depth,
+                                                         unsigned tilesA, unsigned tilesZ, unsigned tiles, int vec) {
+	__shared__ __align__(16) unsigned char tile[VT * VPITCH];
+	const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (unsigned t = blockIdx.x; t < tiles; t += gridDim.x) {
+		const unsigned tz = t % tilesZ, ta = (t / tilesZ) % tilesA, bl = t / (tilesZ * tilesA);
+		const unsigned a0 = ta * VT, z0 = tz * VT;
+		/* load + convert: warp w takes A-scans a0 + w, a0 + w + 8, ...; lanes run along the depth */
+#pragma unroll
+		for (unsigned r = 0; r < VT / 8; ++r) {
+			const unsigned al = warp + 8 * r, a = a0 + al;
+			if (a < A) {
+				const float* line = buf + ((size_t)bl * A + a) * depth;
+#pragma unroll
+				for (unsigned h = 0; h < 2; ++h) {
+					const unsigned zl = lane + 32 * h, z = z0 + zl;
+					if (z < depth) tile[zl * VPITCH + al] = (unsigned char)((double)line[z] * 255.0);     /* cuda_code.cu:935 */
+				}
+			}
+		}
+		__syncthreads();
+		/* store: texture row (z', y) holds A bytes; 16 threads write one 64-byte row segment */
+		const unsigned y = bl + bufferNr * B;
+#pragma unroll
+		for (unsigned it = 0; it < 4; ++it) {
+			const unsigned zl = (threadIdx.x >> 4) + 16 * it, z = z0 + zl, c = (threadIdx.x & 15) * 4, a = a0 + c;
+			if (z < depth && a < A) {
+				unsigned char* dst = tex + ((size_t)(depth - 1 - z) * Btot + y) * A + a;
+				if (vec && a + 3 < A) *reinterpret_cast<unsigned*>(dst) = *reinterpret_cast<const unsigned*>(tile + zl * VPITCH + c);
+				else for (unsigned k = 0; k < 4 && a + k < A; ++k) dst[k] = tile[zl * VPITCH + c + k];
+			}
+		}
+		__syncthreads();
 	}
 }
 cudaError_t launch_volume_u8(uint8_t* tex, const float* buf, long long samples, unsigned bufferNr, unsigned B, unsigned A, unsigned Btot,
                              unsigned depth, int smCount, cudaStream_t st) {
-	long long blocks = (samples + 255) / 256;
-	if (blocks > (long long)smCount * 16) blocks = (long long)smCount * 16;
-	volume_u8_kernel<<<(int)blocks, 256, 0, st>>>(tex, buf, samples, bufferNr, B, A, Btot, depth);
+	if (samples != (long long)B * A * depth) return cudaErrorInvalidValue;
+	const unsigned tilesA = (A + VT - 1) / VT, tilesZ = (depth + VT - 1) / VT;
+	const unsigned long long tiles64 = (unsigned long long)tilesA * tilesZ * B;
+	if (tiles64 == 0 || tiles64 > 0x7fffffffULL) return cudaErrorInvalidValue;
+	const unsigned tiles = (unsigned)tiles64;
+	const int vec = (A % 4 == 0) && (reinterpret_cast<uintptr_t>(tex) & 3) == 0;
+	unsigned blocks = tiles < (unsigned)smCount * 8u ? tiles : (unsigned)smCount * 8u;
+	volume_u8_kernel<<<blocks, 256, 0, st>>>(tex, buf, bufferNr, B, A, Btot, depth, tilesA, tilesZ, tiles, vec);
 	return cudaGetLastError();
 }
 

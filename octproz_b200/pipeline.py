@@ -210,6 +210,10 @@ class OctPipeline:
         self._ck(self._lib.octb200_copy_output(self._h, out.ctypes.data, buffer_nr), "copy_output")
         return out
 
+    def current_buffer_nr(self) -> int:
+        """slab of the volume the last process call wrote (bufferNumberInVolume, cuda_code.cu:1530-1535)"""
+        return int(self._lib.octb200_current_buffer_nr(self._h))
+
     def volume_u8(self, buffer_nr: int, d_out) -> None:
         self._ck(self._lib.octb200_volume_u8(self._h, buffer_nr, _ptr(d_out)), "volume_u8")
 

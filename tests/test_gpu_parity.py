@@ -352,16 +352,44 @@ def test_error_behaviour():
     assert L.octb200_destroy(h) == 0
 
 
-def test_volume_u8_layout():
+@pytest.mark.parametrize("n,a,b", [(1024, 8, 3), (100, 70, 2), (2048, 130, 1), (1024, 64, 2)])
+def test_volume_u8_layout(n, a, b):
+    """updateDisplayedVolume (cuda_code.cu:915-941) as a tiled transpose: full and partial 64 x 64 tiles, A not a multiple of four
+    (byte-wise stores), depth not a multiple of 64"""
     import torch
-    n, a, b = 1024, 8, 3
     q = benchmark_params(n, a, b); q.fixedPatternNoiseRemoval = False; q.update_all_curves()
     raw = synth.make_volume(n, a, b, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
     p = OctPipeline(); assert p.initializeCuda(None, None, copy.deepcopy(q))
     p.octCudaPipeline(raw); p.sync(); vol = p.copy_output(0)
-    tex = torch.zeros(n // 2 * b * a, dtype=torch.uint8, device="cuda")
+    assert vol.min() >= 0.0 and vol.max() < 1.0                        # inside [0,1): the conversion is a plain truncation
+    tex = torch.full((n // 2 * b * a + 64,), 0xAB, dtype=torch.uint8, device="cuda")
     p.volume_u8(0, tex); p.sync(); torch.cuda.synchronize()
-    t = tex.cpu().numpy().reshape(n // 2, b, a)                        # [z][B-scan][A-scan], z flipped (cuda_code.cu:935)
-    expect = np.clip(vol.astype(np.float64) * 255.0, 0, 255).astype(np.uint8)     # values here are inside [0,1)
+    host = tex.cpu().numpy()
+    assert (host[n // 2 * b * a:] == 0xAB).all(), "wrote past the texture"
+    t = host[: n // 2 * b * a].reshape(n // 2, b, a)                   # [z][B-scan][A-scan], z flipped (cuda_code.cu:935)
+    expect = (vol.astype(np.float64) * 255.0).astype(np.uint8)
     assert np.array_equal(t, expect.transpose(2, 0, 1)[::-1])
+    p.cleanupCuda()
+
+
+def test_volume_u8_slab_of_a_multi_buffer_volume():
+    """buffersPerVolume = 2: the second buffer lands in B-scans [B, 2B) of the texture (cuda_code.cu:931 bufferNr * bscansPerBuffer)"""
+    import torch
+    n, a, b = 1024, 12, 2
+    q = benchmark_params(n, a, b); q.fixedPatternNoiseRemoval = False; q.buffersPerVolume = 2; q.update_all_curves()
+    raws = [synth.make_volume(n, a, b, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve, b_offset=4 * i) for i in range(2)]
+    p = OctPipeline(); assert p.initializeCuda(None, None, copy.deepcopy(q))
+    tex = torch.zeros(n // 2 * 2 * b * a, dtype=torch.uint8, device="cuda")
+    vols = {}
+    for raw in raws:
+        p.octCudaPipeline(raw); p.sync()
+        nr = p.current_buffer_nr()
+        vols[nr] = p.copy_output(nr)
+        p.volume_u8(nr, tex)
+    p.sync(); torch.cuda.synchronize()
+    assert sorted(vols) == [0, 1]
+    t = tex.cpu().numpy().reshape(n // 2, 2 * b, a)
+    for nr, vol in vols.items():
+        expect = (vol.astype(np.float64) * 255.0).astype(np.uint8).transpose(2, 0, 1)[::-1]
+        assert np.array_equal(t[:, nr * b:(nr + 1) * b], expect), f"slab {nr}"
     p.cleanupCuda()

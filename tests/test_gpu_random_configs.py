@@ -67,8 +67,11 @@ def test_random_configuration_matches_live_reference_cuda(i, n):
     rc = orc.RefCuda(); rc.configure(q)
     ours = (q.resampleCurve, q.dispersionCurve, q.windowCurve)
     q.resampleCurve, q.dispersionCurve, q.windowCurve = rc.curves()
+    # libref_cuda.so carries the reference's host code as nvcc's host pass compiles it (no -O2): its Gauss window differs from the
+    # qmake-release (-O2) build of the same source by 1-3 ulp in a few elements.  Bit-identity of our generators is pinned against
+    # the -O2 build (tests/test_random_curves.py, tests/golden/luts.npz); here the curves only have to be the same curves.
     for mine, theirs in zip(ours, (q.resampleCurve, q.dispersionCurve, q.windowCurve)):
-        assert np.array_equal(mine, theirs), "curve generators must be bit-identical to the reference's host code"
+        assert np.allclose(mine, theirs, rtol=1e-6, atol=1e-7), "curve generators vs the reference's host code"
     raw = synth.make_volume(n, q.ascansPerBscan, q.bscansPerBuffer, q.bitDepth, resample=q.resampleCurve if q.resampling else None,
                             dispersion=q.dispersionCurve if q.dispersionCompensation else None)
     h1 = np.ascontiguousarray(raw).copy(); h2 = h1.copy()

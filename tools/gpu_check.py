@@ -304,6 +304,40 @@ def cmd_randomref():
     print("randomref worst frac_outside", worst, flush=True)
 
 
+def cmd_display():
+    """device time of the display / aux kernels at the BASELINE size (1024 x 512 x 256): 3-D volume texture, en-face and B-scan frames,
+    stand-alone floatToOutput, and the post-FFT passes of the 2048 x 1024 x 128 chain with sinusoidal correction"""
+    import torch
+    res = {}
+    n, a, b = 1024, 512, 256
+    q = benchmark_params(n, a, b); q.update_all_curves()
+    small = synth.make_volume(n, a, 8, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+    raw = np.ascontiguousarray(np.tile(small, (b // 8, 1, 1)))
+    d = torch.from_numpy(raw.view(np.int16)).cuda()
+    p = OctPipeline(fft_mode=_lib.FFT_FUSED)
+    assert p.initializeCuda(None, None, copy.deepcopy(q))
+    p.process_device(d); p.sync()
+    tex = torch.zeros(n // 2 * a * b, dtype=torch.uint8, device="cuda")
+    conv = torch.zeros(n // 2 * a * b, dtype=torch.int16, device="cuda")
+    dB = torch.empty(n // 2 * a, dtype=torch.float32, device="cuda"); dE = torch.empty(a * b, dtype=torch.float32, device="cuda")
+
+    def timed(name, fn, iters=20):
+        fn(); p.sync()
+        p.event_record(0)
+        for _ in range(iters):
+            fn()
+        p.event_record(1)
+        res[name] = p.event_elapsed_ms(0, 1) / iters * 1e3
+        print("display", name, f"{res[name]:.1f} us", flush=True)
+    timed("volume_u8 (64 MiB texture)", lambda: p.volume_u8(0, tex))
+    timed("float_to_output stand-alone (u16)", lambda: p.float_to_output(0, conv))
+    timed("enface_frame 1 frame", lambda: p.changeDisplayedEnFaceFrame(100, 1, 0, dE))
+    timed("enface_frame 16-frame average", lambda: p.changeDisplayedEnFaceFrame(100, 16, 0, dE))
+    timed("bscan_frame 1 frame", lambda: p.changeDisplayedBscanFrame(100, 1, 0, dB))
+    p.cleanupCuda()
+    json.dump(res, open(os.path.join(OUT, "display_kernels_us.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     {"estimator": cmd_estimator, "perf": cmd_perf, "quick": cmd_quick, "parity": cmd_parity, "refcuda": cmd_refcuda, "timing": cmd_timing,
-     "randomref": cmd_randomref}[sys.argv[1]]()
+     "randomref": cmd_randomref, "display": cmd_display}[sys.argv[1]]()
