@@ -88,6 +88,25 @@ __device__ __forceinline__ void tmem_ld8_wait2(float (&r)[8], float (&s)[8]) {
 	             : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
 	               "+f"(s[0]), "+f"(s[1]), "+f"(s[2]), "+f"(s[3]), "+f"(s[4]), "+f"(s[5]), "+f"(s[6]), "+f"(s[7]) :: "memory");
 }
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, float (&r)[4]) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4_wait(float (&r)[4]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld2_issue(uint32_t taddr, float (&r)[2]) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=f"(r[0]), "=f"(r[1]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld2_wait(float (&r)[2]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]) :: "memory");
+}
+/* width picked by the array type */
+__device__ __forceinline__ void tmem_ldx_issue(uint32_t taddr, float (&r)[8]) { tmem_ld8_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ldx_issue(uint32_t taddr, float (&r)[4]) { tmem_ld4_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ldx_issue(uint32_t taddr, float (&r)[2]) { tmem_ld2_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ldx_wait(float (&r)[8]) { tmem_ld8_wait(r); }
+__device__ __forceinline__ void tmem_ldx_wait(float (&r)[4]) { tmem_ld4_wait(r); }
+__device__ __forceinline__ void tmem_ldx_wait(float (&r)[2]) { tmem_ld2_wait(r); }
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&r)[4]) {
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(taddr));
 	asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]) :: "memory");
@@ -222,27 +241,35 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 	}
 }
 
-/* ---- inter-pass twiddle + transpose store, twiddles from TMEM (cf. exchange_store): w^{k1 lane} at columns TW + 2 k1 ---- */
+/* ---- inter-pass twiddle + transpose store, twiddles from TMEM (cf. exchange_store): w^{k1 lane} at columns TW + 2 k1 ----
+ * OCT_XCHG_X = registers per tensor-memory read (8: four twiddles, 4: two, 2: one).  The read of chunk c+1 is in flight while
+ * chunk c is multiplied and stored.  ptxas hoists these reads for latency and, when the destination tuple is still live, copies the
+ * old values out of it: the wider the tuple, the more MOVs (x8: 66 per line). */
+#ifndef OCT_XCHG_X
+#define OCT_XCHG_X 8
+#endif
 template <int R>
 __device__ __forceinline__ void exchange_store_tmem(int lane, const float2 (&v)[32], float2* xbuf, uint32_t tq) {
 	using M = TmemMap<R>;
-	/* the twiddles of chunk c+1 are read from tensor memory while chunk c is multiplied and stored */
-	float t[2][8];
-	tmem_ld8_issue(tq + M::TW, t[0]);
-	tmem_ld8_wait(t[0]);
-	static_for<0, 8>([&](auto cc) {
-		constexpr int c = decltype(cc)::value;            /* k1 = 4c .. 4c+3 */
+	constexpr int X = OCT_XCHG_X, TW = X / 2, CH = 32 / TW;       /* twiddles per read, reads per line */
+	float t[2][X];
+	auto issue = [&](int c, float (&dst)[X]) { tmem_ldx_issue(tq + M::TW + X * c, dst); };
+	auto wait = [&](float (&dst)[X]) { tmem_ldx_wait(dst); };
+	issue(0, t[0]);
+	wait(t[0]);
+	static_for<0, CH>([&](auto cc) {
+		constexpr int c = decltype(cc)::value;            /* k1 = TW c .. TW c + TW - 1 */
 		constexpr int b = c & 1;
-		if constexpr (c < 7) tmem_ld8_issue(tq + M::TW + 8 * (c + 1), t[b ^ 1]);
-		static_for<0, 4>([&](auto ic) {
+		if constexpr (c < CH - 1) issue(c + 1, t[b ^ 1]);
+		static_for<0, TW>([&](auto ic) {
 			constexpr int i = decltype(ic)::value;
-			constexpr int k1 = 4 * c + i;
+			constexpr int k1 = TW * c + i;
 			constexpr int r = bitrev5(k1);
 			float2 val = v[r];
 			if constexpr (k1 != 0) val = cmul(val, make_float2(t[b][2 * i], t[b][2 * i + 1]));
 			xbuf[k1 * XPITCH + lane] = val;
 		});
-		if constexpr (c < 7) tmem_ld8_wait(t[b ^ 1]);
+		if constexpr (c < CH - 1) wait(t[b ^ 1]);
 	});
 }
 
@@ -273,7 +300,7 @@ struct ConvOut {
 	unsigned short* line;    /* converted line (same bin order as outLine); unused without CONV */
 	float scale;
 };
-template <int R, int K2LO, bool LOG, bool FPN, bool PPBG, bool CONV>
+template <int R, int K2LO, bool LOG, bool FPN, bool PPBG, bool CONV, bool EG>
 __device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co, int egK2, float& egVal) {
 	using M = TmemMap<R>;
 	const float sA = e.scaleA, sB = e.scaleB, bw = e.ppbgWeight, bo = e.ppbgOffset;
@@ -294,23 +321,30 @@ __device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32],
 			if constexpr (PPBG) o = saturate01(o - fmaf(bw, bgv[i], bo));
 			outLine[z] = o;
 			if constexpr (CONV) co.line[z] = (unsigned short)__float_as_uint(__fmaf_rz(__saturatef(o), co.scale, 8388608.0f));
-			if (k2 == egK2) egVal = o;                   /* uniform compare: the displayed en-face bin stays in a register */
+			if constexpr (EG) { if (k2 == egK2) egVal = o; }   /* uniform compare: the displayed en-face bin stays in a register */
 		});
 	});
 }
-/* runtime flags -> one uniform branch per line instead of three per output */
-template <int R, int K2LO, bool CONV>
-__device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co, int egK2, float& egVal) {
+/* runtime flags -> one uniform branch per line instead of several per output.  EG (the en-face gather keeps one output per line in a
+ * register) is a variant of its own: without it the per-output compare + select would cost 32 instructions per line for nothing */
+template <int R, int K2LO, bool CONV, bool EG>
+__device__ __forceinline__ void epilogue_tmem_sel(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co, int egK2, float& egVal) {
 	const int sel = (e.logMode ? 1 : 0) | (e.fpn ? 2 : 0) | (e.ppbg ? 4 : 0);
 	switch (sel) {
-	case 0: epilogue_tmem_t<R, K2LO, false, false, false, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
-	case 1: epilogue_tmem_t<R, K2LO, true, false, false, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
-	case 2: epilogue_tmem_t<R, K2LO, false, true, false, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
-	case 3: epilogue_tmem_t<R, K2LO, true, true, false, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
-	case 4: epilogue_tmem_t<R, K2LO, false, false, true, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
-	case 5: epilogue_tmem_t<R, K2LO, true, false, true, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
-	case 6: epilogue_tmem_t<R, K2LO, false, true, true, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
-	default: epilogue_tmem_t<R, K2LO, true, true, true, CONV>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 0: epilogue_tmem_t<R, K2LO, false, false, false, CONV, EG>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 1: epilogue_tmem_t<R, K2LO, true, false, false, CONV, EG>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 2: epilogue_tmem_t<R, K2LO, false, true, false, CONV, EG>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 3: epilogue_tmem_t<R, K2LO, true, true, false, CONV, EG>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 4: epilogue_tmem_t<R, K2LO, false, false, true, CONV, EG>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 5: epilogue_tmem_t<R, K2LO, true, false, true, CONV, EG>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	case 6: epilogue_tmem_t<R, K2LO, false, true, true, CONV, EG>(lane, v, e, tq, outLine, co, egK2, egVal); break;
+	default: epilogue_tmem_t<R, K2LO, true, true, true, CONV, EG>(lane, v, e, tq, outLine, co, egK2, egVal); break;
 	}
 }
+template <int R, int K2LO, bool CONV>
+__device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co, int egK2, float& egVal) {
+	if (egK2 >= 0) epilogue_tmem_sel<R, K2LO, CONV, true>(lane, v, e, tq, outLine, co, egK2, egVal);
+	else epilogue_tmem_sel<R, K2LO, CONV, false>(lane, v, e, tq, outLine, co, egK2, egVal);
+}
+
 }  // namespace octb200
