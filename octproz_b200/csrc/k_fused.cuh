@@ -278,7 +278,9 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 						for (int i = 0; i < 8; ++i) f4[tig + 32 * R * i] = conv(w8[i]);
 					}
 				};
-				if (sh == 0) store8(cvt0); else store8(cvt);
+				/* measured on one box, old vs new library: N = 1024 0.2153 -> 0.2112 ms, but N = 2048 0.5042 -> 0.5105 ms -- the two-warp
+				 * kernel keeps the single path */
+				if (R == 1 && sh == 0) store8(cvt0); else store8(cvt);
 				/* the remaining HB + HA halo samples (Lanczos only) */
 				for (int q4 = N / 4 + tig; q4 < SE / 4; q4 += 32 * R) f4[q4] = cvt(s2[q4]);
 				if constexpr (SA == SA_CUBIC && !ROLL) {

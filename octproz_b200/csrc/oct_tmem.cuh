@@ -343,7 +343,7 @@ __device__ __forceinline__ void epilogue_tmem_sel(int lane, const float2 (&v)[32
 }
 template <int R, int K2LO, bool CONV>
 __device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co, int egK2, float& egVal) {
-	if (egK2 >= 0) epilogue_tmem_sel<R, K2LO, CONV, true>(lane, v, e, tq, outLine, co, egK2, egVal);
+	if (R == 2 || egK2 >= 0) epilogue_tmem_sel<R, K2LO, CONV, true>(lane, v, e, tq, outLine, co, egK2, egVal);      /* R = 2: one variant, see k_fused.cuh */
 	else epilogue_tmem_sel<R, K2LO, CONV, false>(lane, v, e, tq, outLine, co, egK2, egVal);
 }
 
