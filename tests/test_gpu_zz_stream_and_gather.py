@@ -1,0 +1,52 @@
+"""The two things the fused kernel's epilogue can do besides writing the float line -- the converted u16 line for the stream-to-host
+path (CONV kernels) and the en-face capture for the peer gather -- in the SAME launch: what every rank of the multi-GPU end-to-end
+loop runs (bench.py e2e leg at N > 1).  One rank is enough to exercise the kernel variant; the peer stores themselves are covered
+by tests/test_gpu_multi.py.  (Sorted last on purpose: it combines features the earlier files test one by one.)"""
+import copy
+
+import numpy as np
+import pytest
+
+from octproz_b200 import OctPipeline, _lib, benchmark_params, synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,bits,kw", [(1024, 12, {}), (1024, 12, dict(bscanFlip=True, fixedPatternNoiseRemoval=False)), (2048, 16, {})])
+def test_streaming_and_automatic_gather_in_one_launch(n, bits, kw):
+    import torch
+    from tests.test_gpu_multi import _window_tensor
+    a, b = 40, 4
+    q = benchmark_params(n, a, b, bits)
+    for k, v in kw.items():
+        setattr(q, k, v)
+    q.streamToHost = True
+    q.update_all_curves()
+    raw = np.ascontiguousarray(synth.make_volume(n, a, b, bits, resample=q.resampleCurve, dispersion=q.dispersionCurve))
+    s = [np.zeros((b, a, n // 2), np.uint16) for _ in range(2)]
+    got_cb = []
+    p = OctPipeline(fft_mode=_lib.FFT_FUSED)
+    assert p.initializeCuda(None, None, copy.deepcopy(q)), getattr(p, "_create_error", "")
+    p.cuda_registerStreamingBuffers(s[0], s[1], s[0].nbytes)
+    p.set_callbacks(streaming=lambda ptr: got_cb.append(ptr))
+    p.enface_gather_connect(p.enface_gather_init(0, 1, a * b, 0))
+    p.octCudaPipeline(raw); p.sync()                      # FPN determination happens here
+    dev = torch.device("cuda", 0)
+    for frame in (17, n // 2 - 1, 300):
+        p.enface_gather_auto(True, frame, 1, 0)
+        l0 = p.launch_count()
+        p.octCudaPipeline(raw)
+        launches = p.launch_count() - l0
+        ptr = p.enface_gather_wait(); p.sync()
+        gathered = _window_tensor(ptr, a * b, torch, dev).clone()
+        want = torch.empty(a * b, dtype=torch.float32, device=dev)
+        p.changeDisplayedEnFaceFrame(frame, 1, 0, want); p.sync()
+        vol = p.copy_output(0)
+        last = s[0] if got_cb[-1] == s[0].ctypes.data else s[1]
+        assert launches == 1, launches                    # compute + converted output + en-face capture + publish: one kernel
+        assert torch.equal(gathered, want), frame
+        assert np.array_equal(last, orc.float_to_output(vol, bits)), frame
+    p.enface_gather_close()
+    p.cuda_unregisterStreamingBuffers()
+    p.cleanupCuda()
