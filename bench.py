@@ -149,6 +149,15 @@ def cpu_reference_run(q, threads, bscans, repeats=1, calibrate=True):
                       f"(processor.tpp, FFTW-API substitute), {threads} thread(s)"}
 
 
+def cpu_single_thread(q, bscans=4):
+    """the reference's CPU path "as shipped" runs on one thread; a small sample is enough for a rate"""
+    try:
+        r = cpu_reference_run(q, 1, bscans, repeats=1, calibrate=False)
+        return {"value": r["mhz"], "unit": "MHz (1e6 A-scans/s)", "sample": r["sample"]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -194,7 +203,8 @@ def main():
                 "volumes_per_s": mhz * 1e6 / ascans_per_step, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(config, step=f"bounded sample: {t[0]['ascans']} A-scans per step"),
-                "cpu_baseline": {"value": mhz, "unit": "MHz (1e6 A-scans/s)", "cores": t[0]["threads"], "kind": t[0]["kind"], "sample": t[0]["sample"]},
+                "cpu_baseline": {"value": mhz, "unit": "MHz (1e6 A-scans/s)", "cores": t[0]["threads"], "kind": t[0]["kind"], "sample": t[0]["sample"],
+                                 "single_thread": cpu_single_thread(q)},
                 "e2e": {"value": mhz, "unit": "MHz (1e6 A-scans/s)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "host_cores": ncores}
         print(json.dumps(line), flush=True)
@@ -424,7 +434,8 @@ def main():
     if rank == 0 and world == 1:
         bscans = args.cpu_bscans or b            # one full volume per repeat: ~3 s of CPU work each
         c = cpu_reference_run(q, ncores, bscans, repeats=4)
-        cpu = {"value": c["mhz"], "unit": "MHz (1e6 A-scans/s)", "cores": c["threads"], "kind": c["kind"], "sample": c["sample"]}
+        cpu = {"value": c["mhz"], "unit": "MHz (1e6 A-scans/s)", "cores": c["threads"], "kind": c["kind"], "sample": c["sample"],
+               "single_thread": cpu_single_thread(q)}
 
     if dist is not None:
         p.sync(); torch.cuda.synchronize(); dist.barrier()       # peers have stopped writing into this rank's window
