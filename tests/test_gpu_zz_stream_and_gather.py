@@ -50,3 +50,32 @@ def test_streaming_and_automatic_gather_in_one_launch(n, bits, kw):
     p.enface_gather_close()
     p.cuda_unregisterStreamingBuffers()
     p.cleanupCuda()
+
+
+@pytest.mark.skipif(not orc.have_ref("libref_cuda.so"), reason="oracle/_ref/libref_cuda.so not built")
+@pytest.mark.parametrize("bits,kw", [(12, {}), (16, dict(signalGrayscaleMin=20.0, signalGrayscaleMax=70.0, signalMultiplicator=1.4)), (10, {})])
+def test_float_to_output_restatement_pinned_to_the_reference_kernel(bits, kw):
+    """the oracle's floatToOutput (and with it the fused conversion, which is tested bit-identical to it) against the reference's OWN
+    kernel: the reference streams its converted buffer to the host (cuda_code.cu:1357-1372); applying the restatement to the float
+    volume the same run produced must give exactly those containers -- including values saturated at both ends"""
+    import ctypes as C
+    n, a, b = 1024, 24, 2
+    q = benchmark_params(n, a, b, bits); q.fixedPatternNoiseRemoval = False; q.streamToHost = True
+    for k, v in kw.items():
+        setattr(q, k, v)
+    rc = orc.RefCuda(); rc.configure(q)
+    q.resampleCurve, q.dispersionCurve, q.windowCurve = rc.curves()
+    raw = synth.make_volume(n, a, b, bits, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+    h1 = np.ascontiguousarray(raw).copy(); h2 = h1.copy()
+    rc.init(h1, h2)
+    s1 = np.zeros((b, a, n // 2), np.uint16); s2 = np.zeros_like(s1)
+    rc.L.refcuda_register_streaming(s1.ctypes.data, s2.ctypes.data, C.c_size_t(s1.nbytes))
+    rc.process(h1)
+    rc.L.refcuda_sync()
+    vol = rc.output(0)
+    want = orc.float_to_output(vol, bits)
+    ok = np.array_equal(s1, want) or np.array_equal(s2, want)
+    rc.L.refcuda_unregister_streaming()
+    rc.cleanup()
+    assert ok, "oracle floatToOutput differs from the reference's kernel on the reference's own volume"
+    assert want.min() < want.max()
