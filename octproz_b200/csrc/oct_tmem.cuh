@@ -100,7 +100,23 @@ __device__ __forceinline__ void tmem_ld2_issue(uint32_t taddr, float (&r)[2]) {
 __device__ __forceinline__ void tmem_ld2_wait(float (&r)[2]) {
 	asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]) :: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&r)[32]) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+	             : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]),
+	               "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]),
+	               "=f"(r[23]), "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(float (&r)[32]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+	             : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]), "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]),
+	               "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]), "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]), "+f"(r[22]),
+	               "+f"(r[23]), "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]), "+f"(r[30]), "+f"(r[31]) :: "memory");
+}
 /* width picked by the array type */
+__device__ __forceinline__ void tmem_ldx_issue(uint32_t taddr, float (&r)[32]) { tmem_ld32_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ldx_issue(uint32_t taddr, float (&r)[16]) { tmem_ld16_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ldx_wait(float (&r)[32]) { tmem_ld32_wait(r); }
+__device__ __forceinline__ void tmem_ldx_wait(float (&r)[16]) { tmem_ld16_wait(r); }
 __device__ __forceinline__ void tmem_ldx_issue(uint32_t taddr, float (&r)[8]) { tmem_ld8_issue(taddr, r); }
 __device__ __forceinline__ void tmem_ldx_issue(uint32_t taddr, float (&r)[4]) { tmem_ld4_issue(taddr, r); }
 __device__ __forceinline__ void tmem_ldx_issue(uint32_t taddr, float (&r)[2]) { tmem_ld2_issue(taddr, r); }
@@ -252,9 +268,28 @@ template <int R>
 __device__ __forceinline__ void exchange_store_tmem(int lane, const float2 (&v)[32], float2* xbuf, uint32_t tq) {
 	using M = TmemMap<R>;
 	constexpr int X = OCT_XCHG_X, TW = X / 2, CH = 32 / TW;       /* twiddles per read, reads per line */
-	float t[2][X];
 	auto issue = [&](int c, float (&dst)[X]) { tmem_ldx_issue(tq + M::TW + X * c, dst); };
 	auto wait = [&](float (&dst)[X]) { tmem_ldx_wait(dst); };
+	if constexpr (X >= 16) {
+		/* wide reads, not double buffered: the twiddles of a whole half (or all) of the exchange at once, their registers are the ones
+		 * the stored values free up */
+		static_for<0, CH>([&](auto cc) {
+			constexpr int c = decltype(cc)::value;
+			float t1[X];
+			issue(c, t1);
+			wait(t1);
+			static_for<0, TW>([&](auto ic) {
+				constexpr int i = decltype(ic)::value;
+				constexpr int k1 = TW * c + i;
+				constexpr int r = bitrev5(k1);
+				float2 val = v[r];
+				if constexpr (k1 != 0) val = cmul(val, make_float2(t1[2 * i], t1[2 * i + 1]));
+				xbuf[k1 * XPITCH + lane] = val;
+			});
+		});
+		return;
+	}
+	float t[2][X];
 	issue(0, t[0]);
 	wait(t[0]);
 	static_for<0, CH>([&](auto cc) {
