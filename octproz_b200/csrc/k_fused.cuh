@@ -30,6 +30,13 @@ namespace octb200 {
 #ifndef OCT_RT_HALO
 #define OCT_RT_HALO 0
 #endif
+/* experiments for the two-warp kernels (tools/variant_sweep.sh): each of the two instruction cuts of the N = 1024 kernels on its own */
+#ifndef OCT_R2_NOSHIFT
+#define OCT_R2_NOSHIFT 0
+#endif
+#ifndef OCT_R2_EGVAR
+#define OCT_R2_EGVAR 0
+#endif
 #ifndef OCT_R1_THREADS
 #define OCT_R1_THREADS 512
 #endif
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 				};
 				/* measured on one box, old vs new library: N = 1024 0.2153 -> 0.2112 ms, but N = 2048 0.5042 -> 0.5105 ms -- the two-warp
 				 * kernel keeps the single path */
-				if (R == 1 && sh == 0) store8(cvt0); else store8(cvt);
+				if ((R == 1 || OCT_R2_NOSHIFT) && sh == 0) store8(cvt0); else store8(cvt);
 				/* the remaining HB + HA halo samples (Lanczos only) */
 				for (int q4 = N / 4 + tig; q4 < SE / 4; q4 += 32 * R) f4[q4] = cvt(s2[q4]);
 				if constexpr (SA == SA_CUBIC && !ROLL) {

@@ -21,10 +21,24 @@
 
 namespace octb200 {
 
+#ifndef OCT_R2_EGVAR
+#define OCT_R2_EGVAR 0
+#endif
+/* OCT_TW4 = 1 (experiment, not the default): every inter-pass twiddle is stored as four words (t.x, t.y, -t.y, t.x), the two operand
+ * pairs of the packed complex multiply, instead of two -- a half-pair negation is not a free operand modifier, so the two-word form
+ * costs one FADD per twiddle and line (31).  Same arithmetic, bit-identical results. */
+#ifndef OCT_TW4
+#define OCT_TW4 0
+#endif
 template <int R> struct TmemMap;
 /* per lane quadrant; for R = 2 a quadrant only holds the tables of ITS sub-sequence p = quadrant & 1 (warp w: p = w % 2, quadrant w % 4) */
+#if OCT_TW4
+template <> struct TmemMap<1> { static constexpr int LUT = 0, TW = 256, CTW = 384, MEAN = 384, PPBG = 416, ALLOC = 512; };
+template <> struct TmemMap<2> { static constexpr int LUT = 0, TW = 256, CTW = 384, MEAN = 448, PPBG = 480, ALLOC = 512; };
+#else
 template <> struct TmemMap<1> { static constexpr int LUT = 0, TW = 256, CTW = 320, MEAN = 320, PPBG = 352, ALLOC = 512; };
 template <> struct TmemMap<2> { static constexpr int LUT = 0, TW = 256, CTW = 320, MEAN = 384, PPBG = 416, ALLOC = 512; };
+#endif
 
 /* ---- raw tcgen05 wrappers (SASS: LDTM / STTM / UTCALLOC) ---- */
 __device__ __forceinline__ void tmem_alloc(uint32_t* smemResult, int cols) {
@@ -197,7 +211,12 @@ __device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int q
 		for (int u = 0; u < 4; ++u) {
 			const int i = base + u * parts;
 			if (i < 16) {
+#if OCT_TW4
+				tmem_st_f4(tq + M::TW + 8 * i, make_float4(t[u].x, t[u].y, -t[u].y, t[u].x));
+				tmem_st_f4(tq + M::TW + 8 * i + 4, make_float4(t[u].z, t[u].w, -t[u].w, t[u].z));
+#else
 				tmem_st_f4(tq + M::TW + 4 * i, t[u]);
+#endif
 				if constexpr (R == 2) tmem_st_f4(tq + M::CTW + 4 * i, c[u]);
 				if (fpn && i < 8) tmem_st_f4(tq + M::MEAN + 4 * i, m[u]);
 				if (a.epi.ppbg && i < 4) tmem_st_f4(tq + M::PPBG + 4 * i, g[u]);
@@ -267,7 +286,15 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 template <int R>
 __device__ __forceinline__ void exchange_store_tmem(int lane, const float2 (&v)[32], float2* xbuf, uint32_t tq) {
 	using M = TmemMap<R>;
-	constexpr int X = OCT_XCHG_X, TW = X / 2, CH = 32 / TW;       /* twiddles per read, reads per line */
+	constexpr int WPT = OCT_TW4 ? 4 : 2;                          /* words per twiddle */
+	constexpr int X = OCT_XCHG_X, TW = X / WPT, CH = 32 / TW;     /* registers per read, twiddles per read, reads per line */
+	auto twmul = [](float2 val, const float* w) {
+#if OCT_TW4
+		return pfma(make_float2(val.y, val.y), make_float2(w[2], w[3]), pmul(make_float2(val.x, val.x), make_float2(w[0], w[1])));
+#else
+		return cmul(val, make_float2(w[0], w[1]));
+#endif
+	};
 	auto issue = [&](int c, float (&dst)[X]) { tmem_ldx_issue(tq + M::TW + X * c, dst); };
 	auto wait = [&](float (&dst)[X]) { tmem_ldx_wait(dst); };
 	if constexpr (X >= 16) {
@@ -283,7 +310,7 @@ __device__ __forceinline__ void exchange_store_tmem(int lane, const float2 (&v)[
 				constexpr int k1 = TW * c + i;
 				constexpr int r = bitrev5(k1);
 				float2 val = v[r];
-				if constexpr (k1 != 0) val = cmul(val, make_float2(t1[2 * i], t1[2 * i + 1]));
+				if constexpr (k1 != 0) val = twmul(val, &t1[WPT * i]);
 				xbuf[k1 * XPITCH + lane] = val;
 			});
 		});
@@ -301,7 +328,7 @@ __device__ __forceinline__ void exchange_store_tmem(int lane, const float2 (&v)[
 			constexpr int k1 = TW * c + i;
 			constexpr int r = bitrev5(k1);
 			float2 val = v[r];
-			if constexpr (k1 != 0) val = cmul(val, make_float2(t[b][2 * i], t[b][2 * i + 1]));
+			if constexpr (k1 != 0) val = twmul(val, &t[b][WPT * i]);
 			xbuf[k1 * XPITCH + lane] = val;
 		});
 		if constexpr (c < CH - 1) wait(t[b ^ 1]);
@@ -378,7 +405,7 @@ __device__ __forceinline__ void epilogue_tmem_sel(int lane, const float2 (&v)[32
 }
 template <int R, int K2LO, bool CONV>
 __device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co, int egK2, float& egVal) {
-	if (R == 2 || egK2 >= 0) epilogue_tmem_sel<R, K2LO, CONV, true>(lane, v, e, tq, outLine, co, egK2, egVal);      /* R = 2: one variant, see k_fused.cuh */
+	if ((R == 2 && !OCT_R2_EGVAR) || egK2 >= 0) epilogue_tmem_sel<R, K2LO, CONV, true>(lane, v, e, tq, outLine, co, egK2, egVal);      /* R = 2: one variant, see k_fused.cuh */
 	else epilogue_tmem_sel<R, K2LO, CONV, false>(lane, v, e, tq, outLine, co, egK2, egVal);
 }
 

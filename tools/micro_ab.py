@@ -1,6 +1,6 @@
 """Smallest possible same-box A/B of two builds of liboctb200.so (no torch): device time of the chain re-run on the resident raw
 buffer (octCudaPipeline(NULL), cuda_code.cu:1400) and a hash of the output, so that a faster variant is also shown bit-identical.
-   OCTB200_LIB=<variant .so> python tools/micro_ab.py <tag>"""
+   OCTB200_LIB=<variant .so> python tools/micro_ab.py <tag> [1024|2048]"""
 import hashlib
 import json
 import os
@@ -14,9 +14,10 @@ from octproz_b200 import OctPipeline, _lib, benchmark_params, synth  # noqa: E40
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "default"
 t0 = time.time()
-n, a, b = 1024, 512, 256
-q = benchmark_params(n, a, b); q.update_all_curves()
-small = synth.make_volume(n, a, 4, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+a, b, bits = (512, 256, 12) if n == 1024 else (1024, 128, 16)
+q = benchmark_params(n, a, b, bits); q.update_all_curves()
+small = synth.make_volume(n, a, 4, bits, resample=q.resampleCurve, dispersion=q.dispersionCurve)
 raw = np.ascontiguousarray(np.tile(small, (b // 4, 1, 1)))
 p = OctPipeline(fft_mode=_lib.FFT_FUSED)
 assert p.initializeCuda(None, None, q), getattr(p, "_create_error", "")
@@ -31,9 +32,9 @@ for _ in range(iters):
 p.event_record(1)
 ms = p.event_elapsed_ms(0, 1) / iters
 out = p.copy_output(0)
-res = {"tag": tag, "ms_per_volume": ms, "MHz": a * b / ms / 1e3, "sha1_first_8_bscans": hashlib.sha1(out[:8].tobytes()).hexdigest(),
+res = {"tag": tag, "n": n, "ms_per_volume": ms, "MHz": a * b / ms / 1e3, "sha1_first_8_bscans": hashlib.sha1(out[:8].tobytes()).hexdigest(),
        "sha1_last_bscan": hashlib.sha1(out[-1].tobytes()).hexdigest(), "wall_s": round(time.time() - t0, 1)}
 print("MICRO_AB", json.dumps(res), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open(f"gpurun_out/micro_ab_{tag}.json", "w"))
+json.dump(res, open(f"gpurun_out/micro_ab_{tag}_N{n}.json", "w"))
 p.cleanupCuda()
