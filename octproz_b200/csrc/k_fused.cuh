@@ -37,6 +37,9 @@ namespace octb200 {
 #ifndef OCT_R2_EGVAR
 #define OCT_R2_EGVAR 0
 #endif
+#ifndef OCT_CVT_I2F
+#define OCT_CVT_I2F 0
+#endif
 #ifndef OCT_R1_THREADS
 #define OCT_R1_THREADS 512
 #endif
@@ -264,7 +267,15 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 				};
 				/* without the bitshift (the usual case) the shift and mask are identities: one uniform branch per line saves two ALU
 				 * instructions per 32-bit word (32 of the ~1230 per line) */
+#if OCT_CVT_I2F
+				/* experiment: one conversion-pipe instruction per sample (I2F.U16 on a register half) instead of PRMT + FADD */
+				auto cvt0 = [](uint2 w) {
+					return make_float4((float)(unsigned short)(w.x & 0xFFFFu), (float)(unsigned short)(w.x >> 16),
+					                   (float)(unsigned short)(w.y & 0xFFFFu), (float)(unsigned short)(w.y >> 16));
+				};
+#else
 				auto cvt0 = [](uint2 w) { return make_float4(u16lo_to_float(w.x), u16hi_to_float(w.x), u16lo_to_float(w.y), u16hi_to_float(w.y)); };
+#endif
 				/* first N samples of the slot: 8 quads per thread, all loads in flight before the first conversion */
 				uint2 w8[8];
 #pragma unroll

@@ -5,7 +5,7 @@
 #   bash tools/variant_sweep.sh build
 #   gpurun --timeout 300 -- 'bash tools/variant_sweep.sh run'
 # Static instruction counts of the N = 1024 benchmark kernel (common part of the loop, default = 1085): x32 1022, tw4 1041,
-# tw4+x32 1001.
+# tw4+x32 1001, i2f 1052.
 set -e
 cd "$(dirname "$0")/.."
 declare -A V=(
@@ -14,6 +14,8 @@ declare -A V=(
   [tw4]="-DOCT_TW4=1"
   [tw4x32]="-DOCT_TW4=1 -DOCT_XCHG_X=32"
   [tw4x32w20]="-DOCT_TW4=1 -DOCT_XCHG_X=32 -DOCT_R1_THREADS=640"
+  [i2f]="-DOCT_CVT_I2F=1"
+  [all]="-DOCT_TW4=1 -DOCT_XCHG_X=32 -DOCT_CVT_I2F=1"
   [r2noshift]="-DOCT_R2_NOSHIFT=1"
   [r2egvar]="-DOCT_R2_EGVAR=1"
 )
