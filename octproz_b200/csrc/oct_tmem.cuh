@@ -24,6 +24,9 @@ namespace octb200 {
 #ifndef OCT_R2_EGVAR
 #define OCT_R2_EGVAR 0
 #endif
+#ifndef OCT_EPI_PAIR
+#define OCT_EPI_PAIR 0
+#endif
 /* OCT_TW4 = 1 (experiment, not the default): every inter-pass twiddle is stored as four words (t.x, t.y, -t.y, t.x), the two operand
  * pairs of the packed complex multiply, instead of two -- a half-pair negation is not a free operand modifier, so the two-word form
  * costs one FADD per twiddle and line (31).  Same arithmetic, bit-identical results. */
@@ -371,6 +374,32 @@ __device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32],
 		float m[8], bgv[4];
 		if constexpr (FPN) tmem_ld8(tq + M::MEAN + 8 * g, m);
 		if constexpr (PPBG) tmem_ld4(tq + M::PPBG + 4 * g, bgv);
+#if OCT_EPI_PAIR
+		/* experiment: the final scale FMA of two outputs as one packed instruction (same FMA per half, bit-identical) */
+		static_for<0, 2>([&](auto hc) {
+			constexpr int h = decltype(hc)::value;
+			float tr[2];
+			static_for<0, 2>([&](auto ic) {
+				constexpr int i = 2 * h + decltype(ic)::value;
+				constexpr int r = bitrev5(K2LO + 4 * g + i);
+				float2 d = v[r];
+				if constexpr (FPN) d = csub(d, make_float2(m[2 * i], m[2 * i + 1]));
+				const float pw = fmaf(d.x, d.x, d.y * d.y);
+				tr[decltype(ic)::value] = LOG ? oct_lg2(pw) : oct_sqrt(pw);
+			});
+			const float2 o2 = pfma(make_float2(tr[0], tr[1]), make_float2(sA, sA), make_float2(sB, sB));
+			static_for<0, 2>([&](auto ic) {
+				constexpr int i = 2 * h + decltype(ic)::value;
+				constexpr int k2 = K2LO + 4 * g + i;
+				const int z = lane + 32 * k2;
+				float o = decltype(ic)::value ? o2.y : o2.x;
+				if constexpr (PPBG) o = saturate01(o - fmaf(bw, bgv[i], bo));
+				outLine[z] = o;
+				if constexpr (CONV) co.line[z] = (unsigned short)__float_as_uint(__fmaf_rz(__saturatef(o), co.scale, 8388608.0f));
+				if constexpr (EG) { if (k2 == egK2) egVal = o; }
+			});
+		});
+#else
 		static_for<0, 4>([&](auto ic) {
 			constexpr int i = decltype(ic)::value;
 			constexpr int k2 = K2LO + 4 * g + i;
@@ -385,6 +414,7 @@ __device__ __forceinline__ void epilogue_tmem_t(int lane, const float2 (&v)[32],
 			if constexpr (CONV) co.line[z] = (unsigned short)__float_as_uint(__fmaf_rz(__saturatef(o), co.scale, 8388608.0f));
 			if constexpr (EG) { if (k2 == egK2) egVal = o; }   /* uniform compare: the displayed en-face bin stays in a register */
 		});
+#endif
 	});
 }
 /* runtime flags -> one uniform branch per line instead of several per output.  EG (the en-face gather keeps one output per line in a

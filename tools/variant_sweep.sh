@@ -15,7 +15,8 @@ declare -A V=(
   [tw4x32]="-DOCT_TW4=1 -DOCT_XCHG_X=32"
   [tw4x32w20]="-DOCT_TW4=1 -DOCT_XCHG_X=32 -DOCT_R1_THREADS=640"
   [i2f]="-DOCT_CVT_I2F=1"
-  [all]="-DOCT_TW4=1 -DOCT_XCHG_X=32 -DOCT_CVT_I2F=1"
+  [epipair]="-DOCT_EPI_PAIR=1"
+  [all]="-DOCT_TW4=1 -DOCT_XCHG_X=32 -DOCT_CVT_I2F=1 -DOCT_EPI_PAIR=1"
   [r2noshift]="-DOCT_R2_NOSHIFT=1"
   [r2egvar]="-DOCT_R2_EGVAR=1"
 )
