@@ -1,0 +1,343 @@
+/*
+ * octb200_host.hpp -- the host side ABOVE the C ABI (include/octb200.h) in the reference's own language, without Qt.
+ *
+ * OCTproZ is a C++/Qt application; Qt is not available where this repository is built, so the classes a maintainer meets on the
+ * path are mirrored here in plain C++17 with the reference's names, members and call order:
+ *
+ *   AcquisitionParams / AcquisitionBuffer   octproz_devkit/src/acquisitionparameter.h:31-37, acquisitionbuffer.h:43-68, .cpp:43-76
+ *   AcquisitionSystem                        octproz_devkit/src/acquisitionsystem.h:58-73 (startAcquisition / stopAcquisition, public
+ *                                            `buffer`, `params`, `acqusitionRunning` -- the reference's spelling; the Qt signals
+ *                                            acquisitionStarted / acquisitionStopped are std::function members)
+ *   VirtualOCTSystem                         octproz_plugins/octproz-virtual-oct-system/src/virtualoctsystem.cpp:59-224
+ *   OctPipeline                              the kernels.h entry points (kernels.h:63-84) as methods over an octb200 handle
+ *   Processing                               octproz/src/processing.cpp:124-229 (block the buffers, initializeCuda, poll the double
+ *                                            buffer, octCudaPipeline, release the buffer, per-second statistics :194-207)
+ *
+ * Header only.  Processing is a template over the pipeline type so that the handshake can be exercised on a machine without a
+ * GPU against a stand-in (tests/host/host_mirror_test.cpp); the product type is OctPipeline, which has no CPU fallback.
+ * In a real OCTproZ build none of this is needed: integration/octproz_kernels_adapter.cpp re-exports the kernels.h names and the
+ * Qt classes stay byte-for-byte what they are.
+ */
+#ifndef OCTB200_HOST_HPP
+#define OCTB200_HOST_HPP
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "octb200.h"
+
+namespace octb200 {
+namespace host {
+
+/* acquisitionparameter.h:31-37 */
+struct AcquisitionParams {
+	unsigned int samplesPerLine = 0;
+	unsigned int ascansPerBscan = 0;
+	unsigned int bscansPerBuffer = 0;
+	unsigned int buffersPerVolume = 0;
+	unsigned int bitDepth = 0;
+};
+
+/* acquisitionbuffer.{h,cpp}: bufferCnt 128-byte aligned host buffers + ready flags.  The reference's flags are plain bools polled by
+ * two threads; here they are atomics with release / acquire so that the handshake is defined behaviour. */
+class AcquisitionBuffer {
+public:
+	std::vector<void*> bufferArray;
+	std::unique_ptr<std::atomic<bool>[]> bufferReadyArray;
+	std::atomic<int> currIndex{-1};
+	int bufferCnt = 0;
+	size_t bytesPerBuffer = 0;
+
+	AcquisitionBuffer() = default;
+	AcquisitionBuffer(const AcquisitionBuffer&) = delete;
+	AcquisitionBuffer& operator=(const AcquisitionBuffer&) = delete;
+	~AcquisitionBuffer() { releaseMemory(); }
+
+	bool allocateMemory(unsigned int count, size_t bytes) {            /* acquisitionbuffer.cpp:43-63 */
+		releaseMemory();
+		bufferReadyArray.reset(new std::atomic<bool>[count]);
+		for (unsigned int i = 0; i < count; ++i) {
+			void* p = nullptr;
+			if (posix_memalign(&p, 128, bytes ? bytes : 128) != 0) { releaseMemory(); return false; }
+			std::memset(p, 0, bytes);
+			bufferArray.push_back(p);
+			bufferReadyArray[i].store(false, std::memory_order_relaxed);
+		}
+		bufferCnt = (int)count;
+		bytesPerBuffer = bytes;
+		currIndex.store(-1);
+		return true;
+	}
+	void releaseMemory() {                                              /* acquisitionbuffer.cpp:65-76 */
+		for (void* p : bufferArray) std::free(p);
+		bufferArray.clear();
+		bufferReadyArray.reset();
+		bufferCnt = 0;
+		bytesPerBuffer = 0;
+		currIndex.store(-1);
+	}
+	bool ready(int i) const { return bufferReadyArray[i].load(std::memory_order_acquire); }
+	void setReady(int i, bool v) { bufferReadyArray[i].store(v, std::memory_order_release); }
+};
+
+/* acquisitionsystem.h:58-73 */
+class AcquisitionSystem {
+public:
+	AcquisitionBuffer* buffer;
+	AcquisitionParams params;
+	std::atomic<bool> acqusitionRunning{false};                        /* sic */
+	std::function<void(AcquisitionSystem*)> acquisitionStarted;        /* signal acquisitionStarted(AcquisitionSystem*) */
+	std::function<void()> acquisitionStopped;                          /* signal acquisitionStopped() */
+
+	AcquisitionSystem() : buffer(new AcquisitionBuffer()) {}
+	virtual ~AcquisitionSystem() { delete buffer; }
+	virtual void startAcquisition() = 0;
+	virtual void stopAcquisition() { acqusitionRunning.store(false); }
+};
+
+/* virtualoctsystem.cpp: headerless little-endian raw file replayed into a two-slot buffer.  Settings = virtualoctsystemsettingsdialog.h:27-38. */
+class VirtualOCTSystem : public AcquisitionSystem {
+public:
+	std::string filePath;
+	int buffersFromFile = 2;
+	unsigned int bscanOffset = 0;
+	int waitTimeUs = 0;
+	bool syncWithProcessing = true;
+	std::atomic<long long> buffersDelivered{0};
+
+	VirtualOCTSystem(const std::string& file, unsigned bitDepth, unsigned width, unsigned height, unsigned depth, unsigned buffersPerVolume = 1)
+	    : filePath(file) {
+		params.samplesPerLine = width; params.ascansPerBscan = height; params.bscansPerBuffer = depth;
+		params.buffersPerVolume = buffersPerVolume; params.bitDepth = bitDepth;
+	}
+
+	size_t bytesOf(size_t samples) const { return samples * (size_t)std::ceil((double)params.bitDepth / 8.0); }   /* virtualoctsystem.cpp:124 */
+
+	bool init() {                                                       /* virtualoctsystem.cpp:112-131 */
+		FILE* f = std::fopen(filePath.c_str(), "rb");
+		if (!f) return false;
+		std::fclose(f);
+		return buffer->allocateMemory(2, bytesOf((size_t)params.samplesPerLine * params.ascansPerBscan * params.bscansPerBuffer));
+	}
+
+	void startAcquisition() override {                                  /* virtualoctsystem.cpp:143-224 */
+		if (!init()) { if (acquisitionStopped) acquisitionStopped(); return; }
+		const size_t nBytes = buffer->bytesPerBuffer;
+		const size_t offset = bytesOf((size_t)bscanOffset * params.samplesPerLine * params.ascansPerBscan);          /* :167 */
+		FILE* f = std::fopen(filePath.c_str(), "rb");
+		if (!f) { if (acquisitionStopped) acquisitionStopped(); return; }
+		auto readAt = [&](size_t off, void* dst) {
+			if (std::fseek(f, (long)off, SEEK_SET) == 0) { const size_t got = std::fread(dst, 1, nBytes, f); (void)got; }
+		};
+		readAt(offset, buffer->bufferArray[0]);
+		readAt(offset + (buffersFromFile == 2 ? nBytes : 0), buffer->bufferArray[1]);                                  /* :175-179 */
+		std::fclose(f);
+		acqusitionRunning.store(true);
+		buffer->currIndex.store(1);
+		if (acquisitionStarted) acquisitionStarted(this);
+		while (acqusitionRunning.load()) {                              /* :196-223 */
+			while (syncWithProcessing && buffer->ready(buffer->currIndex.load()) && acqusitionRunning.load()) std::this_thread::yield();
+			const int nxt = (buffer->currIndex.load() + 1) % 2;
+			buffer->currIndex.store(nxt);
+			if (!buffer->ready(nxt)) { buffer->setReady(nxt, true); buffersDelivered.fetch_add(1); }
+			if (waitTimeUs > 0) std::this_thread::sleep_for(std::chrono::microseconds(waitTimeUs));
+		}
+		if (acquisitionStopped) acquisitionStopped();
+	}
+};
+
+/* The processing block of OctAlgorithmParameters as the C ABI carries it, plus the three host LUTs (octalgorithmparameters.h:108-166). */
+struct OctAlgorithmParameters {
+	octb200_params p;
+	std::vector<float> resampleCurve, dispersionCurve, windowCurve, postProcessBackground;
+	float c[4] = {0, 0, 0, 0}, d[4] = {0, 0, 0, 0};
+	int window = OCTB200_WIN_HANNING;
+	float windowCenter = 0.5f, windowFillFactor = 0.95f;
+
+	OctAlgorithmParameters() { octb200_default_params(&p); }
+
+	/* updateResampleCurve / updateDispersionCurve / updateWindowCurve (octalgorithmparameters.cpp:141-249) */
+	bool updateCurves(unsigned int samplesPerLine) {
+		const int n = (int)samplesPerLine;
+		resampleCurve.resize(n); dispersionCurve.resize(n); windowCurve.resize(n);
+		return octb200_make_resample_curve(n, c[0], c[1], c[2], c[3], resampleCurve.data()) == OCTB200_OK &&
+		       octb200_make_dispersion_curve(n, d[0], d[1], d[2], d[3], dispersionCurve.data()) == OCTB200_OK &&
+		       octb200_make_window_curve(window, windowCenter, windowFillFactor, n, windowCurve.data()) == OCTB200_OK;
+	}
+
+	/* the published benchmark settings (performance/v180/.../20250504_octproz_settings.ini:17-67) */
+	static OctAlgorithmParameters benchmark(unsigned int samplesPerLine) {
+		OctAlgorithmParameters q;
+		q.p.signalLogScaling = 1; q.p.signalGrayscaleMin = -30.0f; q.p.signalGrayscaleMax = 100.0f; q.p.signalMultiplicator = 1.0f; q.p.signalAddend = 0.0f;
+		q.p.resampling = 1; q.p.resamplingInterpolation = OCTB200_INTERP_CUBIC;
+		const float s = (float)((double)samplesPerLine / 1024.0);
+		q.c[0] = 0.535239f; q.c[1] = (float)(871.817574 * s); q.c[2] = (float)(-170.633784 * s); q.c[3] = (float)(97.249716 * s);
+		q.p.dispersionCompensation = 1; q.d[0] = 0.0f; q.d[1] = 97.0f; q.d[2] = -96.625f; q.d[3] = -0.375f;
+		q.p.windowing = 1; q.window = OCTB200_WIN_HANNING; q.windowFillFactor = 0.95f; q.windowCenter = 0.5f;
+		q.p.fixedPatternNoiseRemoval = 1; q.p.bscansForNoiseDetermination = 1;
+		q.updateCurves(samplesPerLine);
+		return q;
+	}
+};
+
+/* kernels.h:63-84 over one octb200 handle.  Every failure throws std::runtime_error with octb200_last_error(): loud, no fallback. */
+class OctPipeline {
+public:
+	explicit OctPipeline(int fftMode = OCTB200_FFT_AUTO, int device = -1) : fftMode_(fftMode), device_(device) {}
+	OctPipeline(const OctPipeline&) = delete;
+	OctPipeline& operator=(const OctPipeline&) = delete;
+	~OctPipeline() { cleanupCuda(); }
+
+	/* initializeCuda(void* h_buffer1, void* h_buffer2, OctAlgorithmParameters*) -- kernels.h:63, cuda_code.cu:1067-1162 */
+	bool initializeCuda(void* hBuffer1, void* hBuffer2, const AcquisitionParams& acq, OctAlgorithmParameters* params) {
+		cleanupCuda();
+		octb200_config cfg;
+		std::memset(&cfg, 0, sizeof(cfg));
+		cfg.samplesPerLine = acq.samplesPerLine; cfg.ascansPerBscan = acq.ascansPerBscan; cfg.bscansPerBuffer = acq.bscansPerBuffer;
+		cfg.buffersPerVolume = acq.buffersPerVolume ? acq.buffersPerVolume : 1; cfg.bitDepth = acq.bitDepth;
+		cfg.device = device_; cfg.fftMode = fftMode_;
+		if (octb200_create(&cfg, &h_) != OCTB200_OK) { lastError_ = octb200_last_error(nullptr); h_ = nullptr; return false; }
+		acq_ = acq; params_ = params;
+		if (hBuffer1 && hBuffer2) check(octb200_register_host_buffers(h_, hBuffer1, hBuffer2), "register_host_buffers");
+		pushParams(true);
+		return true;
+	}
+	/* octCudaPipeline(void* h_inputSignal) -- kernels.h:64, cuda_code.cu:1389-1605 */
+	void octCudaPipeline(void* hInputSignal) {
+		pushParams(false);
+		check(octb200_process_host(h_, hInputSignal), "process_host");
+	}
+	/* cleanupCuda() -- kernels.h:65, cuda_code.cu:1164-1212 */
+	void cleanupCuda() {
+		if (h_) { octb200_destroy(h_); h_ = nullptr; }
+	}
+	void sync() { check(octb200_sync(h_), "sync"); }
+	void copyOutput(float* host, unsigned bufferNrInVolume = 0) { check(octb200_copy_output(h_, host, bufferNrInVolume), "copy_output"); }
+	unsigned long long launchCount() const { return h_ ? (unsigned long long)octb200_launch_count(h_) : 0ULL; }
+	octb200_pipeline* handle() { return h_; }
+	const std::string& lastError() const { return lastError_; }
+
+	/* the *Updated edge triggers of the reference (cuda_code.cu:1433-1445): callers flip these after changing a curve */
+	bool resamplingUpdated = false, dispersionUpdated = false, windowUpdated = false, postProcessBackgroundUpdated = false;
+
+private:
+	void check(int rc, const char* what) {
+		if (rc != OCTB200_OK) {
+			lastError_ = std::string(what) + " failed (" + std::to_string(rc) + "): " + (octb200_last_error(h_) ? octb200_last_error(h_) : "");
+			throw std::runtime_error(lastError_);
+		}
+	}
+	void pushParams(bool forceCurves) {
+		OctAlgorithmParameters& q = *params_;
+		check(octb200_set_params(h_, &q.p), "set_params");
+		const int n = (int)acq_.samplesPerLine;
+		if (q.p.resampling && (forceCurves || resamplingUpdated)) { check(octb200_set_resample_curve(h_, q.resampleCurve.data(), n), "set_resample_curve"); resamplingUpdated = false; }
+		if (q.p.dispersionCompensation && (forceCurves || dispersionUpdated)) { check(octb200_set_dispersion_curve(h_, q.dispersionCurve.data(), n), "set_dispersion_curve"); dispersionUpdated = false; }
+		if (q.p.windowing && (forceCurves || windowUpdated)) { check(octb200_set_window_curve(h_, q.windowCurve.data(), n), "set_window_curve"); windowUpdated = false; }
+		if (q.p.postProcessBackgroundRemoval && postProcessBackgroundUpdated && !q.postProcessBackground.empty()) {
+			check(octb200_set_postprocess_background(h_, q.postProcessBackground.data(), (int)q.postProcessBackground.size()), "set_postprocess_background");
+			postProcessBackgroundUpdated = false;
+		}
+		/* edge triggers are consumed by the pipeline (cuda_code.cu:1524,1561) */
+		q.p.redetermineFixedPatternNoise = 0;
+		q.p.postProcessBackgroundRecordingRequested = 0;
+	}
+
+	int fftMode_, device_;
+	octb200_pipeline* h_ = nullptr;
+	AcquisitionParams acq_;
+	OctAlgorithmParameters* params_ = nullptr;
+	std::string lastError_;
+};
+
+/* processing.cpp:194-207: what the sidebar shows */
+struct ProcessingStats {
+	double buffersPerSecond = 0, volumesPerSecond = 0, bscansPerSecond = 0, ascansPerSecond = 0, bufferSizeMB = 0, dataThroughputMBs = 0;
+	long long processedBuffers = 0;
+};
+
+/* Processing::slot_start (processing.cpp:136-229).  Pipeline needs initializeCuda(h1, h2, acq, params*), octCudaPipeline(h), sync(), cleanupCuda(). */
+template <class Pipeline>
+class Processing {
+public:
+	Processing(Pipeline* pipeline, OctAlgorithmParameters* octParams) : pipeline_(pipeline), octParams_(octParams) {}
+
+	/* signal rawData(void*, bitDepth, samplesPerLine, ascansPerBscan, bscansPerBuffer, buffersPerVolume, currentBufferNr) (processing.h:110) */
+	std::function<void(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned)> rawData;
+	ProcessingStats stats;
+
+	/* maxBuffers > 0: headless runs stop the acquisition after that many processed buffers (the GUI's Stop button) */
+	bool slot_start(AcquisitionSystem* system, long long maxBuffers = 0) {
+		AcquisitionBuffer* buffer = system->buffer;
+		for (int i = 0; i < buffer->bufferCnt; ++i) buffer->setReady(i, true);                  /* blockBuffersForAcquisitionSystem :124-128 */
+		const AcquisitionParams& a = system->params;
+		if (buffer->bufferCnt < 2 || !pipeline_->initializeCuda(buffer->bufferArray[0], buffer->bufferArray[1], a, octParams_)) {      /* :151 */
+			for (int i = 0; i < buffer->bufferCnt; ++i) buffer->setReady(i, false);
+			system->stopAcquisition();                                                            /* initializationFailed -> slot_stop (octprozapp.cpp:54) */
+			return false;
+		}
+		const unsigned perVolume = a.buffersPerVolume ? a.buffersPerVolume : 1;
+		unsigned currentBufferNr = perVolume - 1;
+		for (int i = 0; i < buffer->bufferCnt; ++i) buffer->setReady(i, false);                 /* unblock :130-134 */
+		const auto t0 = std::chrono::steady_clock::now();
+		long long n = 0;
+		while (system->acqusitionRunning.load()) {                                               /* :176-218 */
+			const int pos = buffer->currIndex.load();
+			if (pos >= 0 && buffer->ready(pos)) {
+				currentBufferNr = (currentBufferNr + 1) % perVolume;
+				if (rawData) rawData(buffer->bufferArray[pos], a.bitDepth, a.samplesPerLine, a.ascansPerBscan, a.bscansPerBuffer, perVolume, currentBufferNr);
+				pipeline_->octCudaPipeline(buffer->bufferArray[pos]);                           /* :187 */
+				buffer->setReady(pos, false);                                                    /* :191 */
+				++n;
+				if (maxBuffers > 0 && n >= maxBuffers) system->stopAcquisition();
+			} else {
+				std::this_thread::yield();
+			}
+		}
+		pipeline_->sync();
+		const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		const double bps = dt > 0 ? (double)n / dt : 0.0;
+		stats.processedBuffers = n;
+		stats.buffersPerSecond = bps; stats.volumesPerSecond = bps / perVolume;                 /* :198-201 */
+		stats.bscansPerSecond = bps * a.bscansPerBuffer; stats.ascansPerSecond = stats.bscansPerSecond * a.ascansPerBscan;
+		stats.bufferSizeMB = (double)buffer->bytesPerBuffer / 1048576.0; stats.dataThroughputMBs = bps * stats.bufferSizeMB;
+		return true;
+	}
+
+private:
+	Pipeline* pipeline_;
+	OctAlgorithmParameters* octParams_;
+};
+
+/* run `buffers` buffers of a raw file through `pipeline` with the reference's thread structure (acquisition thread + processing loop) */
+template <class Pipeline>
+ProcessingStats replay(VirtualOCTSystem& vos, Pipeline& pipeline, OctAlgorithmParameters& params, long long buffers, bool* ok = nullptr) {
+	Processing<Pipeline> proc(&pipeline, &params);
+	std::atomic<int> state{0};          /* 1 = started, 2 = stopped before starting (file missing) */
+	vos.acquisitionStarted = [&](AcquisitionSystem*) { state.store(1); };
+	vos.acquisitionStopped = [&]() { int expected = 0; state.compare_exchange_strong(expected, 2); };
+	std::thread producer([&] { vos.startAcquisition(); });
+	while (state.load() == 0) std::this_thread::yield();
+	bool good = false;
+	if (state.load() == 1) good = proc.slot_start(&vos, buffers);
+	vos.stopAcquisition();
+	producer.join();
+	if (ok) *ok = good;
+	return proc.stats;
+}
+
+}  // namespace host
+}  // namespace octb200
+
+#endif /* OCTB200_HOST_HPP */
