@@ -12,6 +12,8 @@
  *   OctPipeline                              the kernels.h entry points (kernels.h:63-84) as methods over an octb200 handle
  *   Processing                               octproz/src/processing.cpp:124-229 (block the buffers, initializeCuda, poll the double
  *                                            buffer, octCudaPipeline, release the buffer, per-second statistics :194-207)
+ *   DispersionEstimationEngine               octproz-dispersion-estimator-extension/src/dispersionestimationengine.cpp:21-158 (the
+ *                                            search; every sweep is one octb200_dispersion_sweep call instead of n CPU passes)
  *
  * Header only.  Processing is a template over the pipeline type so that the handshake can be exercised on a machine without a
  * GPU against a stand-in (tests/host/host_mirror_test.cpp); the product type is OctPipeline, which has no CPU fallback.
@@ -21,6 +23,7 @@
 #ifndef OCTB200_HOST_HPP
 #define OCTB200_HOST_HPP
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -336,6 +339,145 @@ ProcessingStats replay(VirtualOCTSystem& vos, Pipeline& pipeline, OctAlgorithmPa
 	if (ok) *ok = good;
 	return proc.stats;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------------
+ * Dispersion estimator (octproz-dispersion-estimator-extension): DispersionEstimationEngine::startDispersionEstimation
+ * (src/dispersionestimationengine.cpp:21-116) with the reference's search semantics -- d2 sweep with d3 = 0, then d3 at the best d2,
+ * strict '<' from a best metric of 0, step |end - start| / n, the two plotted A-scans, d1 = -(d2 + d3).  The reference re-runs its
+ * CPU path once per trial value (processDispersionMetric, :118-158); here a sweep is ONE call of `Sweep` -- for the product
+ * PipelineSweep, i.e. octb200_dispersion_sweep: all trials in one launch of the fused kernel plus one metric kernel.
+ * Sweep: std::vector<float> operator()(const void* raw, unsigned lines, const std::vector<float>& coeffs, std::vector<float>* ascans)
+ *        coeffs = four floats per trial (d0 d1 d2 d3), ascans = NULL or [trials][lines][N/2], returns one metric per trial
+ * ------------------------------------------------------------------------------------------------------------------------------- */
+struct DispersionEstimatorParameters {                                  /* src/dispersionestimatorparameters.h:58-76 (GUI-only fields omitted) */
+	int numberOfCenterAscans = 10;
+	bool useLinearAscans = true;
+	int numberOfAscanSamplesToIgnore = 0;
+	bool autoCalcD1 = false;
+	int sharpnessMetric = OCTB200_METRIC_SUM_ABOVE_THRESHOLD;
+	float metricThreshold = 0.0f;
+	double d2start = -100.0, d2end = 100.0, d3start = -100.0, d3end = 100.0;
+	int numberOfDispersionSamples = 100;
+};
+
+/* the window the estimator's processing path applies whatever the main window setting is (octprocessor/processor.tpp:126-133, T = float) */
+inline std::vector<float> cpuPathWindow(unsigned int samplesPerSpectrum) {
+	std::vector<float> w(samplesPerSpectrum);
+	const float factor = static_cast<float>(2.0 * 3.14159265358979323846 / (samplesPerSpectrum - 1));
+	for (size_t i = 0; i < samplesPerSpectrum; ++i) w[i] = static_cast<float>(0.5) * (1 - std::cos(factor * i));
+	return w;
+}
+
+template <class Sweep>
+class DispersionEstimationEngine {
+public:
+	DispersionEstimatorParameters params;
+	double bestD2 = 0, bestD3 = 0, bestMetricValueD2 = 0, bestMetricValueD3 = 0, calculatedD1 = 0;
+	std::vector<std::pair<double, float>> metricsD2, metricsD3;         /* (trial value, metric): what the extension plots */
+	std::vector<float> ascanWithoutDispersionCompensation, ascanWithBestDispersion;
+
+	/* d0, d1: the main settings' dispersion coefficients, kept while d2 / d3 are searched (processorcontroller.cpp:59-66) */
+	DispersionEstimationEngine(Sweep sweep, float d0, float d1) : sweep_(sweep), d0_(d0), d1_(d1) {}
+	void setParams(const DispersionEstimatorParameters& p) { params = p; }
+
+	void startDispersionEstimation(const void* frameBuffer, unsigned int bitDepth, unsigned int samplesPerLine, unsigned int linesPerFrame) {
+		const unsigned int centerAscans = std::min(static_cast<unsigned int>(params.numberOfCenterAscans), linesPerFrame);      /* :37 */
+		unsigned int offsetAscans = 0;
+		if (centerAscans < linesPerFrame) offsetAscans = (linesPerFrame - centerAscans) / 2;                                   /* :42-47 */
+		const size_t bytesPerSample = static_cast<size_t>(std::ceil(static_cast<double>(bitDepth) / 8.0));
+		const size_t lineSizeBytes = samplesPerLine * bytesPerSample;
+		const char* rawData = static_cast<const char*>(frameBuffer) + offsetAscans * lineSizeBytes;                            /* :50-57 */
+
+		const int n = params.numberOfDispersionSamples;
+		const double stepSizeD2 = std::fabs(params.d2end - params.d2start) / static_cast<double>(n);                           /* :69 */
+		const double stepSizeD3 = std::fabs(params.d3end - params.d3start) / static_cast<double>(n);                           /* :70 */
+
+		/* d2, with d3 = 0 (:78-82) */
+		std::vector<double> trial(n);
+		{ double d = params.d2start; for (int i = 0; i < n; ++i) { trial[i] = d; d += stepSizeD2; } }
+		std::vector<float> m = sweep_(rawData, centerAscans, coeffs(trial, true, 0.0), nullptr);
+		bestD2 = 0; bestMetricValueD2 = 0; metricsD2.clear();
+		for (int i = 0; i < n; ++i) {
+			if (bestMetricValueD2 < m[i]) { bestMetricValueD2 = m[i]; bestD2 = trial[i]; }                                     /* :140-143, strict */
+			metricsD2.emplace_back(trial[i], m[i]);
+		}
+		/* d3, at the best d2 (:85-90) */
+		{ double d = params.d3start; for (int i = 0; i < n; ++i) { trial[i] = d; d += stepSizeD3; } }
+		m = sweep_(rawData, centerAscans, coeffs(trial, false, bestD2), nullptr);
+		bestD3 = 0; bestMetricValueD3 = 0; metricsD3.clear();
+		for (int i = 0; i < n; ++i) {
+			if (bestMetricValueD3 < m[i]) { bestMetricValueD3 = m[i]; bestD3 = trial[i]; }                                     /* :147-150 */
+			metricsD3.emplace_back(trial[i], m[i]);
+		}
+		/* the two A-scans the GUI plots (:93-96; processFirstLineOnly :160-192 applies the center offset a second time inside the
+		   already extracted block -- with centerAscans lines in the block that offset is 0) */
+		std::vector<float> ascans;
+		const std::vector<float> two = { d0_, d1_, 0.0f, 0.0f, d0_, d1_, static_cast<float>(bestD2), static_cast<float>(bestD3) };
+		sweep_(rawData, 1u, two, &ascans);
+		const size_t half = samplesPerLine / 2;
+		ascanWithoutDispersionCompensation.assign(ascans.begin(), ascans.begin() + half);
+		ascanWithBestDispersion.assign(ascans.begin() + half, ascans.begin() + 2 * half);
+		if (params.autoCalcD1) calculatedD1 = -(bestD2 + bestD3);                                                              /* :101 */
+	}
+
+private:
+	std::vector<float> coeffs(const std::vector<double>& trial, bool isD2, double other) const {
+		std::vector<float> c;
+		c.reserve(trial.size() * 4);
+		for (double t : trial) {
+			c.push_back(d0_); c.push_back(d1_);
+			c.push_back(static_cast<float>(isD2 ? t : other)); c.push_back(static_cast<float>(isD2 ? other : t));
+		}
+		return c;
+	}
+	Sweep sweep_;
+	float d0_, d1_;
+};
+
+/* The product sweep: octb200_dispersion_sweep on an initialised OctPipeline.  The estimator's processing path differs from the main one
+ * in three settings, applied for the lifetime of this object and restored afterwards: its own Hanning window (cpuPathWindow), no
+ * bitshift, and -- a quirk of the reference reproduced on purpose -- a rolling-average window of 10 whatever the settings say
+ * (processorcontroller.cpp:116 passes the setting into the constructor's `windowSize` slot, processor.h:26). */
+class PipelineSweep {
+public:
+	PipelineSweep(OctPipeline& pipe, OctAlgorithmParameters& q, unsigned int samplesPerLine, const DispersionEstimatorParameters& prm)
+	    : pipe_(pipe), q_(q), n_(samplesPerLine), prm_(prm), savedParams_(q.p), savedWindow_(q.windowCurve) {
+		q_.p.bitshift = 0;
+		q_.p.rollingAverageWindowSize = 10;
+		q_.windowCurve = cpuPathWindow(samplesPerLine);
+		apply();
+	}
+	~PipelineSweep() {
+		q_.p = savedParams_;
+		q_.windowCurve = savedWindow_;
+		try { apply(); } catch (...) {}
+	}
+	std::vector<float> operator()(const void* raw, unsigned int lines, const std::vector<float>& coeffs, std::vector<float>* ascans) {
+		octb200_sweep_config c;
+		std::memset(&c, 0, sizeof(c));
+		c.lines = lines; c.trials = static_cast<uint32_t>(coeffs.size() / 4); c.metric = prm_.sharpnessMetric; c.metricThreshold = prm_.metricThreshold;
+		c.samplesToIgnore = prm_.numberOfAscanSamplesToIgnore; c.logScale = prm_.useLinearAscans ? 0 : 1;
+		c.logMin = q_.p.signalGrayscaleMin; c.logMax = q_.p.signalGrayscaleMax; c.logCoeff = q_.p.signalMultiplicator; c.logAddend = q_.p.signalAddend;
+		std::vector<float> metrics(c.trials);
+		if (ascans) ascans->assign(static_cast<size_t>(c.trials) * lines * (n_ / 2), 0.0f);
+		const int rc = octb200_dispersion_sweep(pipe_.handle(), raw, &c, coeffs.data(), metrics.data(), ascans ? ascans->data() : nullptr);
+		if (rc != OCTB200_OK) throw std::runtime_error(std::string("octb200_dispersion_sweep failed: ") + octb200_last_error(pipe_.handle()));
+		return metrics;
+	}
+
+private:
+	void apply() {
+		if (octb200_set_params(pipe_.handle(), &q_.p) != OCTB200_OK) throw std::runtime_error("set_params failed");
+		if (q_.p.windowing && octb200_set_window_curve(pipe_.handle(), q_.windowCurve.data(), static_cast<int>(n_)) != OCTB200_OK)
+			throw std::runtime_error("set_window_curve failed");
+	}
+	OctPipeline& pipe_;
+	OctAlgorithmParameters& q_;
+	unsigned int n_;
+	DispersionEstimatorParameters prm_;
+	octb200_params savedParams_;
+	std::vector<float> savedWindow_;
+};
 
 }  // namespace host
 }  // namespace octb200

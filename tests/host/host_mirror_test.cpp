@@ -123,6 +123,57 @@ int main(int argc, char** argv) {
 		CHECK(!p.initializeCuda(nullptr, nullptr, acq, &q));
 		CHECK(p.lastError().find("geometry") != std::string::npos);
 	}
+	/* dispersion estimator search (dispersionestimationengine.cpp:21-116) against a synthetic metric with a known optimum */
+	{
+		struct FakeSweep {
+			int* calls; std::vector<unsigned>* linesSeen; const void** rawSeen;
+			std::vector<float> operator()(const void* raw, unsigned lines, const std::vector<float>& c, std::vector<float>* ascans) {
+				++*calls; linesSeen->push_back(lines); *rawSeen = raw;
+				std::vector<float> m(c.size() / 4);
+				for (size_t t = 0; t < m.size(); ++t) {
+					const float d2 = c[4 * t + 2], d3 = c[4 * t + 3];
+					m[t] = 1000.0f - (d2 - 30.0f) * (d2 - 30.0f) - 2.0f * (d3 + 8.0f) * (d3 + 8.0f);     /* maximum at d2 = 30, d3 = -8 */
+				}
+				if (ascans) ascans->assign(m.size() * lines * 32, 1.5f);
+				return m;
+			}
+		};
+		int calls = 0; std::vector<unsigned> linesSeen; const void* rawSeen = nullptr;
+		DispersionEstimationEngine<FakeSweep> eng(FakeSweep{&calls, &linesSeen, &rawSeen}, 0.0f, 97.0f);
+		DispersionEstimatorParameters prm;
+		prm.numberOfCenterAscans = 10; prm.numberOfDispersionSamples = 100; prm.d2start = -100; prm.d2end = 100; prm.d3start = -20; prm.d3end = 20; prm.autoCalcD1 = true;
+		eng.setParams(prm);
+		std::vector<unsigned short> frame(64 * 50, 7);
+		eng.startDispersionEstimation(frame.data(), 12, 64, 50);
+		CHECK(calls == 3 && linesSeen[0] == 10 && linesSeen[1] == 10 && linesSeen[2] == 1);                      /* d2 sweep, d3 sweep, the two plotted A-scans */
+		CHECK(rawSeen == reinterpret_cast<const char*>(frame.data()) + (size_t)20 * 64 * 2);                     /* center block: offset (50 - 10) / 2 lines */
+		CHECK(std::fabs(eng.bestD2 - 30.0) < 1e-9 && std::fabs(eng.bestD3 - (-8.0)) < 1e-9);                     /* both on the trial grids (step 2 and 0.4) */
+		CHECK(eng.metricsD2.size() == 100 && eng.metricsD3.size() == 100 && eng.metricsD2[0].first == -100.0);
+		CHECK(std::fabs(eng.metricsD2[99].first - 98.0) < 1e-9);                                                  /* start + 99 steps: the end value itself is never tried */
+		CHECK(std::fabs(eng.calculatedD1 - (-22.0)) < 1e-9);
+		CHECK(eng.ascanWithBestDispersion.size() == 32 && eng.ascanWithoutDispersionCompensation.size() == 32);
+		/* quirk of the reference kept: "best" starts at a metric of 0 with a strict '<' -- a metric that is never positive selects nothing */
+		struct NegSweep {
+			std::vector<float> operator()(const void*, unsigned lines, const std::vector<float>& c, std::vector<float>* a) {
+				if (a) a->assign(c.size() / 4 * lines * 32, 0.0f);
+				return std::vector<float>(c.size() / 4, -1.0f);
+			}
+		};
+		DispersionEstimationEngine<NegSweep> neg(NegSweep{}, 0.0f, 0.0f);
+		neg.setParams(prm);
+		neg.startDispersionEstimation(frame.data(), 12, 64, 50);
+		CHECK(neg.bestD2 == 0.0 && neg.bestD3 == 0.0 && neg.bestMetricValueD2 == 0.0);
+		/* fewer lines than center A-scans: the whole frame, no offset (:37-47) */
+		calls = 0; linesSeen.clear();
+		eng.startDispersionEstimation(frame.data(), 12, 64, 4);
+		CHECK(linesSeen[0] == 4 && rawSeen == frame.data());
+	}
+	/* the estimator path's own window (processor.tpp:126-133 with T = float) */
+	{
+		std::vector<float> w = cpuPathWindow(1024);
+		CHECK(w.size() == 1024 && w[0] == 0.0f && std::fabs(w[1023]) < 1e-6f && std::fabs(w[511] - 1.0f) < 1e-5f);
+		if (argc > 2) { FILE* f = std::fopen(argv[2], "wb"); CHECK(f); std::fwrite(w.data(), 4, w.size(), f); std::fclose(f); }
+	}
 	std::puts("host mirror ok");
 	return 0;
 }

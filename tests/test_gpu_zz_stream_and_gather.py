@@ -112,3 +112,28 @@ def test_cpp_replay_matches_the_python_mirror(tmp_path):
         p.cleanupCuda()
     assert any(abs(res["output_sum"] - want) <= 1e-6 * abs(want) + 1e-3 for want in candidates), (res["output_sum"], candidates)
     assert res["launches"] >= 6
+
+
+def test_cpp_dispersion_engine_reproduces_the_reference_search(tmp_path):
+    """examples/estimate_dispersion_main.cpp (the C++ DispersionEstimationEngine of include/octb200_host.hpp over
+    octb200_dispersion_sweep) on the golden frame: the same best d2 / d3 / d1 as the search that ran every trial through the
+    reference's CPU path and metric code (tests/golden/estimator.npz), with two sweeps + the two plotted A-scans = 3 sweep calls"""
+    import json
+    import os
+    import subprocess
+
+    from tests.test_host_mirror import build
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "estimator.npz"))
+    raw = np.ascontiguousarray(g["raw"]).astype(np.uint16)
+    lines, n = raw.shape
+    path = str(tmp_path / "frame.raw")
+    raw.tofile(path)
+    exe = str(tmp_path / "estimate")
+    build("examples/estimate_dispersion_main.cpp", exe)
+    r = subprocess.run([exe, path, str(n), str(lines), "12", "-160", "0", "-40", "40", "16", str(lines)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    want_d2, want_d3, want_d1 = (float(x) for x in g["search_log0"])
+    assert (res["bestD2"], res["bestD3"]) == (want_d2, want_d3), (res, g["search_log0"])
+    assert abs(res["calculatedD1"] - want_d1) < 1e-9
+    assert res["bestMetricValueD2"] > 0 and res["bestMetricValueD3"] >= res["bestMetricValueD2"] * 0.999

@@ -20,9 +20,14 @@ def build(src, exe, extra=()):
 def test_handshake_against_a_stand_in_pipeline(tmp_path):
     exe = str(tmp_path / "host_mirror_test")
     build("tests/host/host_mirror_test.cpp", exe)
-    r = subprocess.run([exe, str(tmp_path / "replay.raw")], capture_output=True, text=True, timeout=120)
+    r = subprocess.run([exe, str(tmp_path / "replay.raw"), str(tmp_path / "window.f32")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert "host mirror ok" in r.stdout
+    # the C++ and the Python mirror of the estimator path's window agree (to the last ulp or one: cosf vs numpy's float32 cos)
+    import numpy as np
+    from octproz_b200.dispersion_estimator import cpu_path_window
+    w = np.fromfile(str(tmp_path / "window.f32"), np.float32)
+    assert w.shape == (1024,) and np.allclose(w, cpu_path_window(1024), rtol=0, atol=2e-7)
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="no g++")
