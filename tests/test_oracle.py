@@ -237,3 +237,47 @@ def test_oracle_against_reference_cuda_golden_vectors(path):
     lanczos = case == "lanczos"          # the reference's Lanczos weights come from __sinf (fast-math); error floor ~1e-3 of the median amplitude
     assert_parity(out, g["out"], q, atol_frac=2e-2 if lanczos else 1e-4, saturated=bool(q.postProcessBackgroundRemoval),
                   max_frac_outside=1e-4, what=name, atol_abs=floor)
+
+
+def test_float_to_output_known_answers_and_special_values():
+    """floatToOutput (cuda_code.cu:943-967): (container)((double)saturate(x) * (2^bits - 1)), i.e. truncation of the exact product"""
+    below_one = np.nextafter(np.float32(1.0), np.float32(0.0))
+    x = np.array([0.0, -0.0, 1.0, below_one, 0.5, -3.0, 7.0, np.nan, np.inf, -np.inf, 1.0 / 4095.0, 2047.5 / 4095.0], np.float32)
+    got = orc.float_to_output(x, 12)
+    third = int(np.floor(float(np.float32(1.0 / 4095.0)) * 4095.0))        # 1/4095 is not representable: 0 or 1 depending on its rounding
+    half = int(np.floor(float(np.float32(2047.5 / 4095.0)) * 4095.0))
+    assert got.dtype == np.uint16
+    assert got.tolist() == [0, 0, 4095, 4094, 2047, 0, 4095, 0, 4095, 0, third, half]
+    assert orc.float_to_output(np.array([1.0, below_one, 0.5], np.float32), 8).tolist() == [255, 254, 127]
+    assert orc.float_to_output(np.array([1.0, below_one, 0.25], np.float32), 10).tolist() == [1023, 1022, 255]
+    assert orc.float_to_output(np.array([1.0, below_one, 0.25], np.float32), 16).tolist() == [65535, 65534, 16383]
+    assert orc.float_to_output(np.array([1.0, 0.5], np.float32), 24).dtype == np.uint32
+
+
+def test_round_toward_zero_fma_identity_behind_the_fused_conversion():
+    """The fused kernel converts with ONE fp32 FMA rounded toward zero: low 16 bits of RZ(sat(x) * K + 2^23) (oct_tmem.cuh).  Checked here in
+    exact rational arithmetic: for every fp32 s in [0, 1] and K in {1023, 4095, 65535}, RZ32(s * K + 2^23) - 2^23 == floor(s * K), which is
+    what the reference's double-precision product truncates to.  (The GPU tests check the kernel itself bit for bit.)"""
+    from fractions import Fraction
+
+    def rz32(v: Fraction) -> Fraction:          # round a positive rational toward zero onto the fp32 grid
+        e = v.numerator.bit_length() - v.denominator.bit_length()
+        if Fraction(2) ** e > v:
+            e -= 1
+        ulp = Fraction(2) ** (e - 23)
+        return (v // ulp) * ulp
+
+    rng = np.random.default_rng(5)
+    samples = np.concatenate([rng.random(3000, dtype=np.float32), np.float32(1.0) - rng.random(500, dtype=np.float32) * np.float32(1e-4),
+                              rng.random(500, dtype=np.float32) * np.float32(1e-3),
+                              np.array([0.0, 1.0, np.nextafter(np.float32(1), np.float32(0)), 0.5, 1e-30, 1e-45], np.float32)])
+    for K in (1023, 4095, 65535):
+        ks = np.arange(1, K + 1, max(1, K // 257), dtype=np.float64) / K                 # values right at the integer boundaries k / K ...
+        edge = np.concatenate([ks.astype(np.float32), np.nextafter(ks.astype(np.float32), np.float32(0)), np.nextafter(ks.astype(np.float32), np.float32(2))])
+        for s in np.concatenate([samples, edge[edge <= 1.0]]):
+            exact = Fraction(float(s)) * K
+            fused = rz32(exact + 2 ** 23) - 2 ** 23
+            assert fused == exact.numerator // exact.denominator, (float(s), K)
+        want = orc.float_to_output(samples, {1023: 10, 4095: 12, 65535: 16}[K])
+        mine = np.array([int(Fraction(float(s)) * K) for s in samples], np.uint16)
+        assert np.array_equal(want, mine)
