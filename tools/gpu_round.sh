@@ -13,6 +13,10 @@ if [ -z "$quick" ]; then
 timeout 200 python bench.py --separate-conversion --no-packed --steps 300 --cpu-bscans 8 > $out/${tag}_bench_sepconv.json 2>> $out/${tag}_bench_ours.err
 timeout 200 python bench.py --no-numa --no-packed --steps 200 --cpu-bscans 8 > $out/${tag}_bench_nonuma.json 2>> $out/${tag}_bench_ours.err
 timeout 300 python bench.py --workload 2048x1024x128-16bit --no-packed --steps 300 --cpu-bscans 8 > $out/${tag}_bench_ours_2048.json 2>> $out/${tag}_bench_ours.err
+timeout 300 python bench.py --workload 2048x1024x512-16bit-config4 --no-packed --steps 60 --cpu-bscans 16 > $out/${tag}_bench_config4.json 2>> $out/${tag}_bench_ours.err
+timeout 200 python bench.py --mode cufft --no-packed --steps 300 --cpu-bscans 8 > $out/${tag}_bench_cufft.json 2>> $out/${tag}_bench_ours.err
+timeout 200 python bench.py --mode split --no-packed --steps 300 --cpu-bscans 8 > $out/${tag}_bench_split.json 2>> $out/${tag}_bench_ours.err
+timeout 120 python tools/gpu_check.py display > $out/${tag}_display.log 2>&1
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench_ours.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bench_steps3.csv python bench.py --steps 3 --warmup 1 --no-packed --cpu-bscans 8 > $out/${tag}_bench_under_ncu.log 2>&1
 fi
