@@ -179,6 +179,81 @@ struct OctAlgorithmParameters {
 		       octb200_make_window_curve(window, windowCenter, windowFillFactor, n, windowCurve.data()) == OCTB200_OK;
 	}
 
+	/* Settings file of the reference (QSettings INI): the [processing] keys of octproz/src/sidebar.h:58-94, the
+	 * [Virtual%20OCT%20System] keys of virtualoctsystemsettingsdialog.h:27-38 and [streaming].  Missing keys keep
+	 * the defaults of the reference's settings code.  acq / vos receive the acquisition geometry and the replay settings when given. */
+	struct VirtualOctSettings { std::string filePath; int buffersFromFile = 2; unsigned int bscanOffset = 0; int waitTimeUs = 0; bool syncWithProcessing = true; };
+	static bool fromIni(const std::string& path, OctAlgorithmParameters* q, AcquisitionParams* acq = nullptr, VirtualOctSettings* vos = nullptr) {
+		FILE* f = std::fopen(path.c_str(), "r");
+		if (!f) return false;
+		std::string section;
+		char line[4096];
+		auto trim = [](std::string t) {
+			const char* ws = " \t\r\n";
+			const size_t a = t.find_first_not_of(ws);
+			if (a == std::string::npos) return std::string();
+			return t.substr(a, t.find_last_not_of(ws) - a + 1);
+		};
+		auto truth = [](const std::string& v) { return v == "true" || v == "1" || v == "True"; };
+		octb200_params& p = q->p;
+		while (std::fgets(line, sizeof(line), f)) {
+			const std::string t = trim(line);
+			if (t.empty() || t[0] == ';' || t[0] == '#') continue;
+			if (t[0] == '[') { section = t.substr(1, t.find(']') - 1); continue; }
+			const size_t eq = t.find('=');
+			if (eq == std::string::npos) continue;
+			const std::string k = trim(t.substr(0, eq)), v = trim(t.substr(eq + 1));
+			const double num = std::atof(v.c_str());
+			if (section == "processing") {
+				if (k == "bitshift") p.bitshift = truth(v);
+				else if (k == "flip_bscans") p.bscanFlip = truth(v);
+				else if (k == "log") p.signalLogScaling = truth(v);
+				else if (k == "sinusoidal_scan_correction") p.sinusoidalScanCorrection = truth(v);
+				else if (k == "max") p.signalGrayscaleMax = (float)num;
+				else if (k == "min") p.signalGrayscaleMin = (float)num;
+				else if (k == "coeff") p.signalMultiplicator = (float)num;
+				else if (k == "addend") p.signalAddend = (float)num;
+				else if (k == "background_removal") p.backgroundRemoval = truth(v);
+				else if (k == "background_removal_window_size") p.rollingAverageWindowSize = (int)num;
+				else if (k == "resampling") p.resampling = truth(v);
+				else if (k == "resampling_interpolation") p.resamplingInterpolation = (int)num;
+				else if (k.rfind("resampling_c", 0) == 0 && k.size() == 13) q->c[k[12] - '0'] = (float)num;
+				else if (k == "dispersion_compensation") p.dispersionCompensation = truth(v);
+				else if (k.rfind("dispersion_compensation_d", 0) == 0 && k.size() == 26) q->d[k[25] - '0'] = (float)num;
+				else if (k == "windowing") p.windowing = truth(v);
+				else if (k == "window_type") q->window = (int)num;
+				else if (k == "window_fill_factor") q->windowFillFactor = (float)num;
+				else if (k == "window_center_position") q->windowCenter = (float)num;
+				else if (k == "fixed_pattern_removal") p.fixedPatternNoiseRemoval = truth(v);
+				else if (k == "fixed_pattern_removal_continuously") p.continuousFixedPatternNoiseDetermination = truth(v);
+				else if (k == "fixed_pattern_removal_bscans") p.bscansForNoiseDetermination = (uint32_t)num;
+				else if (k == "post_processing_background_removal") p.postProcessBackgroundRemoval = truth(v);
+				else if (k == "post_processing_background_removal_weight") p.postProcessBackgroundWeight = (float)num;
+				else if (k == "post_processing_background_removal_offset") p.postProcessBackgroundOffset = (float)num;
+			} else if (section == "Virtual%20OCT%20System" || section == "Virtual OCT System") {
+				if (acq) {
+					if (k == "bit_depth") acq->bitDepth = (unsigned)num;
+					else if (k == "width") acq->samplesPerLine = (unsigned)num;
+					else if (k == "height") acq->ascansPerBscan = (unsigned)num;
+					else if (k == "depth") acq->bscansPerBuffer = (unsigned)num;
+					else if (k == "buffers_per_volume") acq->buffersPerVolume = (unsigned)num;
+				}
+				if (vos) {
+					if (k == "file_path") vos->filePath = v;
+					else if (k == "buffers_from_file") vos->buffersFromFile = (int)num;
+					else if (k == "bscan_offset") vos->bscanOffset = (unsigned)num;
+					else if (k == "wait_time") vos->waitTimeUs = (int)num;
+					else if (k == "sync_with_processing") vos->syncWithProcessing = truth(v);
+				}
+			} else if (section == "streaming") {
+				if (k == "streaming_enabled") p.streamToHost = truth(v);
+				else if (k == "streaming_skip") p.streamingBuffersToSkip = (uint32_t)num;
+			}
+		}
+		std::fclose(f);
+		return true;
+	}
+
 	/* the published benchmark settings (performance/v180/.../20250504_octproz_settings.ini:17-67) */
 	static OctAlgorithmParameters benchmark(unsigned int samplesPerLine) {
 		OctAlgorithmParameters q;

@@ -174,6 +174,28 @@ int main(int argc, char** argv) {
 		CHECK(w.size() == 1024 && w[0] == 0.0f && std::fabs(w[1023]) < 1e-6f && std::fabs(w[511] - 1.0f) < 1e-5f);
 		if (argc > 2) { FILE* f = std::fopen(argv[2], "wb"); CHECK(f); std::fwrite(w.data(), 4, w.size(), f); std::fclose(f); }
 	}
+	/* settings INI (QSettings vocabulary of the reference): argv[3] = a settings file, fields echoed for tests/test_host_mirror.py */
+	if (argc > 3) {
+		OctAlgorithmParameters q;
+		AcquisitionParams acq;
+		OctAlgorithmParameters::VirtualOctSettings vs;
+		CHECK(OctAlgorithmParameters::fromIni(argv[3], &q, &acq, &vs));
+		CHECK(!OctAlgorithmParameters::fromIni(std::string(argv[3]) + ".missing", &q));
+		std::printf("INI {\"bitshift\": %d, \"bscanFlip\": %d, \"signalLogScaling\": %d, \"sinusoidalScanCorrection\": %d, \"signalGrayscaleMin\": %.9g, "
+		            "\"signalGrayscaleMax\": %.9g, \"signalMultiplicator\": %.9g, \"signalAddend\": %.9g, \"backgroundRemoval\": %d, "
+		            "\"rollingAverageWindowSize\": %d, \"resampling\": %d, \"resamplingInterpolation\": %d, \"c\": [%.9g, %.9g, %.9g, %.9g], "
+		            "\"dispersionCompensation\": %d, \"d\": [%.9g, %.9g, %.9g, %.9g], \"windowing\": %d, \"window\": %d, \"windowFillFactor\": %.9g, "
+		            "\"windowCenter\": %.9g, \"fixedPatternNoiseRemoval\": %d, \"continuousFixedPatternNoiseDetermination\": %d, "
+		            "\"bscansForNoiseDetermination\": %u, \"postProcessBackgroundRemoval\": %d, \"postProcessBackgroundWeight\": %.9g, "
+		            "\"postProcessBackgroundOffset\": %.9g, \"streamToHost\": %d, \"streamingBuffersToSkip\": %u, \"bitDepth\": %u, \"samplesPerLine\": %u, "
+		            "\"ascansPerBscan\": %u, \"bscansPerBuffer\": %u, \"buffersPerVolume\": %u, \"buffersFromFile\": %d, \"bscanOffset\": %u, \"syncWithProcessing\": %d}\n",
+		            q.p.bitshift, q.p.bscanFlip, q.p.signalLogScaling, q.p.sinusoidalScanCorrection, q.p.signalGrayscaleMin, q.p.signalGrayscaleMax,
+		            q.p.signalMultiplicator, q.p.signalAddend, q.p.backgroundRemoval, q.p.rollingAverageWindowSize, q.p.resampling, q.p.resamplingInterpolation,
+		            q.c[0], q.c[1], q.c[2], q.c[3], q.p.dispersionCompensation, q.d[0], q.d[1], q.d[2], q.d[3], q.p.windowing, q.window, q.windowFillFactor,
+		            q.windowCenter, q.p.fixedPatternNoiseRemoval, q.p.continuousFixedPatternNoiseDetermination, q.p.bscansForNoiseDetermination,
+		            q.p.postProcessBackgroundRemoval, q.p.postProcessBackgroundWeight, q.p.postProcessBackgroundOffset, q.p.streamToHost, q.p.streamingBuffersToSkip,
+		            acq.bitDepth, acq.samplesPerLine, acq.ascansPerBscan, acq.bscansPerBuffer, acq.buffersPerVolume, vs.buffersFromFile, vs.bscanOffset, (int)vs.syncWithProcessing);
+	}
 	std::puts("host mirror ok");
 	return 0;
 }
