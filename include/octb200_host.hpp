@@ -12,6 +12,7 @@
  *   OctPipeline                              the kernels.h entry points (kernels.h:63-84) as methods over an octb200 handle
  *   Processing                               octproz/src/processing.cpp:124-229 (block the buffers, initializeCuda, poll the double
  *                                            buffer, octCudaPipeline, release the buffer, per-second statistics :194-207)
+ *   Recorder                                 octproz/src/recorder.cpp:99-152 (N buffers into one headerless file)
  *   DispersionEstimationEngine               octproz-dispersion-estimator-extension/src/dispersionestimationengine.cpp:21-158 (the
  *                                            search; every sweep is one octb200_dispersion_sweep call instead of n CPU passes)
  *
@@ -396,6 +397,33 @@ public:
 private:
 	Pipeline* pipeline_;
 	OctAlgorithmParameters* octParams_;
+};
+
+/* Recorder::slot_record (octproz/src/recorder.cpp:99-152): append `buffersToRecord` buffers (raw or processed, whatever the caller
+ * connects) to ONE headerless little-endian file, then stop -- the format the Virtual OCT System replays (docs/docs/faq.md:5). */
+class Recorder {
+public:
+	Recorder(const std::string& path, size_t bytesPerBuffer, unsigned int buffersToRecord)
+	    : bytesPerBuffer_(bytesPerBuffer), buffersToRecord_(buffersToRecord), f_(std::fopen(path.c_str(), "wb")) {}
+	Recorder(const Recorder&) = delete;
+	Recorder& operator=(const Recorder&) = delete;
+	~Recorder() { close(); }
+	bool isOpen() const { return f_ != nullptr; }
+	unsigned int recordedBuffers() const { return recorded_; }
+	bool finished() const { return recorded_ >= buffersToRecord_; }
+	/* returns false once the requested number of buffers has been written (recorder.cpp:124-131: recording finished) */
+	bool record(const void* buffer) {
+		if (!f_ || finished()) return false;
+		if (std::fwrite(buffer, 1, bytesPerBuffer_, f_) != bytesPerBuffer_) { close(); return false; }
+		if (++recorded_ == buffersToRecord_) close();
+		return true;
+	}
+	void close() { if (f_) { std::fclose(f_); f_ = nullptr; } }
+
+private:
+	size_t bytesPerBuffer_;
+	unsigned int buffersToRecord_, recorded_ = 0;
+	FILE* f_;
 };
 
 /* run `buffers` buffers of a raw file through `pipeline` with the reference's thread structure (acquisition thread + processing loop) */

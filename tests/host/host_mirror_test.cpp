@@ -123,6 +123,32 @@ int main(int argc, char** argv) {
 		CHECK(!p.initializeCuda(nullptr, nullptr, acq, &q));
 		CHECK(p.lastError().find("geometry") != std::string::npos);
 	}
+	/* Recorder: the raw buffers seen by Processing (signal rawData, processing.h:110) recorded into one headerless file that replays identically */
+	{
+		const std::string rec = path + ".rec";
+		VirtualOCTSystem vos(path, 12, n, a, b, 1);
+		FakePipeline fp;
+		OctAlgorithmParameters q;
+		Recorder recorder(rec, (size_t)n * a * b * 2, 3);
+		CHECK(recorder.isOpen());
+		Processing<FakePipeline> proc(&fp, &q);
+		proc.rawData = [&](void* buf, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned) { recorder.record(buf); };
+		std::atomic<bool> started{false};
+		vos.acquisitionStarted = [&](AcquisitionSystem*) { started.store(true); };
+		std::thread producer([&] { vos.startAcquisition(); });
+		while (!started.load()) std::this_thread::yield();
+		CHECK(proc.slot_start(&vos, 5));
+		vos.stopAcquisition();
+		producer.join();
+		CHECK(recorder.finished() && recorder.recordedBuffers() == 3 && !recorder.record(vos.buffer->bufferArray[0]));
+		FILE* f = std::fopen(rec.c_str(), "rb");
+		CHECK(f);
+		std::vector<unsigned short> back((size_t)n * a * b * 3);
+		CHECK(std::fread(back.data(), 2, back.size(), f) == back.size() && std::fgetc(f) == EOF);
+		std::fclose(f);
+		for (int k = 0; k < 3; ++k) CHECK(back[(size_t)k * n * a * b] == fp.firstSample[k]);                     /* the buffers that were processed, in order */
+	}
+
 	/* dispersion estimator search (dispersionestimationengine.cpp:21-116) against a synthetic metric with a known optimum */
 	{
 		struct FakeSweep {
