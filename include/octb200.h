@@ -88,7 +88,10 @@ typedef struct {
 	                               first B-scan, so "flip every even B-scan" (cuda_code.cu:795) keeps its parity */
 	uint32_t inputPacking;      /* OCTB200_PACK_*: how the raw buffer stores its samples */
 	uint32_t flags;             /* OCTB200_FLAG_* */
-	uint32_t reserved[1];
+	uint32_t bscansInUnshardedBuffer; /* multi-GPU shards: B-scans per buffer of the un-sharded acquisition (0 = bscanIndexBase +
+	                               bscansPerBuffer).  Only used by the B-scan flip: with an ODD number of B-scans per buffer the
+	                               reference never flips the last one (cuda_bscanFlip covers samplesPerBuffer/4 elements,
+	                               cuda_code.cu:794-805,1547), and only the shard that holds it can know that */
 } octb200_config;
 
 /* the [processing] block of OctAlgorithmParameters (octalgorithmparameters.h:108-166, 195-199) */
@@ -215,14 +218,22 @@ OCTB200_API int octb200_float_to_output(octb200_pipeline* p, uint32_t bufferNrIn
      init    : allocate this rank's window for a volume of `globalLines` A-scans, this shard starting at line `lineOffset`
                (= first B-scan of the shard * ascansPerBscan); returns the window's IPC handle in handleOut[64]
      connect : handles = world * 64 bytes, rank-major; opens every peer window
-     gather  : enqueue extraction + peer stores + flag publication on the compute stream (double-buffered by sequence number:
-               a frame stays valid until the second-next gather)
+     gather  : enqueue extraction + peer stores + flag publication on the compute stream, then the consumer side for the same
+               sequence number: wait for ALL ranks' slabs, copy the assembled frame into this rank's private display frame and
+               acknowledge to every producer.  Frame buffers in the windows are double-buffered by sequence number; a producer only
+               overwrites a buffer after every rank has acknowledged the frame it held (flow control in the kernels' prologue), so a
+               rank that runs ahead can never tear a frame a slower rank is still reading.  COLLECTIVE: every rank must issue the
+               same sequence of gathers; a rank that stops gathering stalls its peers two gathers later -- for at most 10 s per
+               launch: every device-side wait has a time-out that is counted (status) instead of hanging
      auto    : from now on EVERY octb200_process_* call also gathers frame (frameNr, frames, function) of the buffer it produced.
                When one depth frame is displayed and the slab is final after the fused kernel (single-slab volume, no sinusoidal
-               correction, no background recording) the extraction and the peer stores happen inside that kernel's epilogue -- compute and collective
-               in one launch; otherwise the stand-alone gather kernel is appended to the chain
-     wait    : enqueue, on the compute stream, the wait for the latest sequence number of ALL ranks; *dFrame = device pointer
-               of the assembled frame [globalLines] floats, reference order disp[(E-1)-i]
+               correction, no background recording) the extraction and the peer stores happen inside that kernel's epilogue, spread
+               over the whole kernel (a line group stores the values of up to 8 neighbouring lines with one coalesced store per
+               rank; no end-of-kernel push, no grid-wide barrier) -- compute and collective in one launch; otherwise the stand-alone
+               gather kernel is appended to the chain
+     wait    : *dFrame = device pointer of this rank's display frame [globalLines] floats, reference order disp[(E-1)-i]; valid
+               (stream ordered on the compute stream) until the next gather.  The consumer kernel was already enqueued by gather
+     status  : sequence number of the latest gather and the number of time-outs so far (0 / 0 in a healthy run); synchronises
      close   : release (collective in spirit: call after a barrier, peers must have stopped gathering) */
 #define OCTB200_IPC_HANDLE_BYTES 64
 OCTB200_API int octb200_enface_gather_init(octb200_pipeline* p, int rank, int world, uint32_t globalLines, uint32_t lineOffset, void* handleOut);
@@ -230,6 +241,7 @@ OCTB200_API int octb200_enface_gather_connect(octb200_pipeline* p, const void* h
 OCTB200_API int octb200_enface_gather(octb200_pipeline* p, uint32_t frameNr, uint32_t displayFunctionFrames, int displayFunction);
 OCTB200_API int octb200_enface_gather_auto(octb200_pipeline* p, int enable, uint32_t frameNr, uint32_t displayFunctionFrames, int displayFunction);
 OCTB200_API int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame);
+OCTB200_API int octb200_enface_gather_status(octb200_pipeline* p, uint32_t* sequence, uint32_t* ackTimeouts, uint32_t* arrivalTimeouts);
 OCTB200_API int octb200_enface_gather_close(octb200_pipeline* p);
 
 /* ---------- dispersion-estimator sweep (octproz-dispersion-estimator-extension) ----------

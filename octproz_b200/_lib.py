@@ -27,7 +27,7 @@ SYMBOLS = [
     "octb200_volume_u8", "octb200_float_to_output", "octb200_compute_stream", "octb200_event_record",
     "octb200_event_elapsed_ms", "octb200_launch_count", "octb200_time_kernel",
     "octb200_enface_gather_init", "octb200_enface_gather_connect", "octb200_enface_gather", "octb200_enface_gather_wait",
-    "octb200_enface_gather_close", "octb200_enface_gather_auto", "octb200_dispersion_sweep",
+    "octb200_enface_gather_close", "octb200_enface_gather_auto", "octb200_enface_gather_status", "octb200_dispersion_sweep",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -42,7 +42,7 @@ class Config(C.Structure):
     _fields_ = [("samplesPerLine", C.c_uint32), ("ascansPerBscan", C.c_uint32), ("bscansPerBuffer", C.c_uint32),
                 ("buffersPerVolume", C.c_uint32), ("bitDepth", C.c_uint32), ("device", C.c_int32),
                 ("rawSlots", C.c_int32), ("fftMode", C.c_int32), ("bscanIndexBase", C.c_uint32),
-                ("inputPacking", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32 * 1)]
+                ("inputPacking", C.c_uint32), ("flags", C.c_uint32), ("bscansInUnshardedBuffer", C.c_uint32)]
 
 
 class Params(C.Structure):
@@ -131,6 +131,7 @@ def load() -> C.CDLL:
     lib.octb200_enface_gather.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int]
     lib.octb200_enface_gather_auto.argtypes = [P, C.c_int, C.c_uint32, C.c_uint32, C.c_int]
     lib.octb200_enface_gather_wait.argtypes = [P, C.POINTER(C.c_void_p)]
+    lib.octb200_enface_gather_status.argtypes = [P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.octb200_enface_gather_close.argtypes = [P]
     lib.octb200_dispersion_sweep.argtypes = [P, C.c_void_p, C.POINTER(SweepConfig), C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) oct_post_kernel(const PostArgs a, int vec
 	const int lane = threadIdx.x & 31, warpsPerBlock = blockDim.x >> 5;
 	for (int line = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); line < a.lines; line += gridDim.x * warpsPerBlock) {
 		int b = line / a.A, al = line - b * a.A;
-		if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u) al = a.A - 1 - al;
+		if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u && (unsigned)b + a.bscanBase < a.flipEnd) al = a.A - 1 - al;
 		const float2* in = a.in + (size_t)line * a.N;
 		float* out = a.out + ((size_t)b * a.A + al) * H;
 		if (vec) {
@@ -414,10 +414,19 @@ cudaError_t launch_enface_frame(float* disp, const float* vol, unsigned W, unsig
 /* ---- en-face extraction fused with its all-gather over peer memory (multi-GPU shards) ----
  * Same per-line arithmetic as enface_frame_kernel (cuda_code.cu:884-912); instead of a local frame + ncclAllGather every
  * value is stored straight into the frame window of EVERY rank (P2P stores over NVLink / NVSwitch; the own rank is a plain
- * store).  The last CTA to finish publishes `seq` in each rank's flag word for this rank (release, system scope); readers
- * wait with enface_wait_kernel (acquire, system scope). */
+ * store).  Protocol as in the fused kernel (oct_device.cuh GatherDev): acknowledgements of the frame buffer being overwritten are
+ * awaited first, the last CTA to finish publishes `seq` in each rank's arrived[] word for this rank (release, system scope). */
 
 __global__ void __launch_bounds__(256) enface_gather_kernel(const EnfaceGatherArgs a) {
+	if (a.world > 1 && a.seq >= 3u) {
+		if (threadIdx.x == 0) {
+			const unsigned* acks = a.flags[a.rank] + OCT_GATHER_ACK;
+			bool ok = true;
+			for (int c = 0; c < a.world; ++c) ok = gather_spin_ge(acks + c, a.seq - 2u) && ok;
+			if (!ok) atomicAdd(a.status, 1u);
+		}
+		__syncthreads();
+	}
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < a.E) {
 		float val;
@@ -438,29 +447,53 @@ __global__ void __launch_bounds__(256) enface_gather_kernel(const EnfaceGatherAr
 #pragma unroll 1
 		for (int r = 0; r < a.world; ++r) a.frames[r][dst] = val;
 	}
-	__threadfence_system();
 	__syncthreads();
 	if (threadIdx.x == 0) {
+		__threadfence_system();
 		const unsigned done = atomicAdd(a.counter, 1u);
 		if (done == gridDim.x - 1) {
 			*a.counter = 0;                                             /* next launch is stream ordered behind this one */
 			__threadfence_system();
 #pragma unroll 1
-			for (int r = 0; r < a.world; ++r) st_relaxed_sys_u32(a.flags[r] + a.rank, a.seq);
+			for (int r = 0; r < a.world; ++r) st_relaxed_sys_u32(a.flags[r] + OCT_GATHER_ARRIVED + a.rank, a.seq);
 		}
 	}
 }
-__global__ void enface_wait_kernel(const unsigned* flags, int world, unsigned seq) {
-	if ((int)threadIdx.x < world) {
-		while ((int)(ld_acquire_sys_u32(flags + threadIdx.x) - seq) < 0) __nanosleep(200);
+/* consumer side: wait until every rank's slab of frame `seq` has arrived, copy the frame out of the window into this rank's private
+ * display frame (what the GL widget's PBO is in the reference), and only then acknowledge `seq` to every producer -- the producers
+ * check that acknowledgement before they overwrite this frame buffer two gathers later (flow control: a rank that runs ahead can
+ * never tear a frame a slower rank is still reading). */
+__global__ void __launch_bounds__(256) enface_consume_kernel(const EnfaceConsumeArgs a) {
+	if ((int)threadIdx.x < a.world) {
+		if (!gather_spin_ge(a.window + OCT_GATHER_ARRIVED + threadIdx.x, a.seq) && blockIdx.x == 0) atomicAdd(a.status + 1, 1u);
+	}
+	__syncthreads();
+	const unsigned quads = a.Eglobal >> 2;
+	const float4* src4 = reinterpret_cast<const float4*>(a.frame);
+	float4* dst4 = reinterpret_cast<float4*>(a.display);
+	for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) dst4[q] = __ldcg(src4 + q);
+	for (unsigned i = (quads << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < a.Eglobal; i += gridDim.x * blockDim.x) a.display[i] = __ldcg(a.frame + i);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const unsigned done = atomicAdd(a.counter, 1u);
+		if (done == gridDim.x - 1) {
+			*a.counter = 0;
+			__threadfence_system();
+#pragma unroll 1
+			for (int r = 0; r < a.world; ++r) st_relaxed_sys_u32(a.peerHeaders[r] + OCT_GATHER_ACK + a.rank, a.seq);
+		}
 	}
 }
 cudaError_t launch_enface_gather(const EnfaceGatherArgs& a, cudaStream_t st) {
 	enface_gather_kernel<<<(a.E + 255) / 256, 256, 0, st>>>(a);
 	return cudaGetLastError();
 }
-cudaError_t launch_enface_wait(const unsigned* flags, int world, unsigned seq, cudaStream_t st) {
-	enface_wait_kernel<<<1, 32, 0, st>>>(flags, world, seq);
+cudaError_t launch_enface_consume(const EnfaceConsumeArgs& a, int smCount, cudaStream_t st) {
+	int blocks = (int)((a.Eglobal / 4 + 255) / 256);
+	if (blocks > smCount) blocks = smCount;
+	if (blocks < 1) blocks = 1;
+	enface_consume_kernel<<<blocks, 256, 0, st>>>(a);
 	return cudaGetLastError();
 }
 

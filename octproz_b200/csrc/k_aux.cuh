@@ -30,6 +30,7 @@ struct PostArgs {
 	int lines, N, A;
 	int flip;
 	unsigned bscanBase;
+	unsigned flipEnd;       /* see FusedArgs::flipEnd */
 };
 
 /* en-face extraction + all-gather over peer memory */
@@ -38,14 +39,26 @@ struct EnfaceGatherArgs {
 	unsigned* flags[OCT_MAX_PEERS];    /* flag words of every rank; word [rank] is written by this rank */
 	const float* vol;
 	unsigned* counter;                 /* local CTA completion counter (zero between launches) */
+	unsigned* status;                  /* local time-out counters (GatherDev::status) */
 	unsigned W, E;                     /* depth bins per line, local lines */
 	unsigned frameNr, nFrames; int fn;
 	unsigned Eglobal, offset;          /* lines of the whole (sharded) volume, first line of this shard */
 	int world, rank;
 	unsigned seq;
 };
+/* consumer side of the gather: wait for all slabs of frame `seq`, copy the frame out, acknowledge to every producer */
+struct EnfaceConsumeArgs {
+	unsigned* peerHeaders[OCT_MAX_PEERS];   /* window header of every rank (ack[] at word OCT_GATHER_ACK) */
+	const unsigned* window;                 /* this rank's window header (arrived[] at word 0) */
+	const float* frame;                     /* frame buffer of this sequence number in this rank's window */
+	float* display;                         /* private copy handed to the caller */
+	unsigned* counter;                      /* local CTA completion counter of the consume kernel */
+	unsigned* status;
+	unsigned Eglobal, seq;
+	int world, rank;
+};
 cudaError_t launch_enface_gather(const EnfaceGatherArgs& a, cudaStream_t st);
-cudaError_t launch_enface_wait(const unsigned* flags, int world, unsigned seq, cudaStream_t st);
+cudaError_t launch_enface_consume(const EnfaceConsumeArgs& a, int smCount, cudaStream_t st);
 
 cudaError_t launch_sweep_metric(float* metrics, const float* data, int trials, int lines, int H, int metric, float thr, int ignore, cudaStream_t st);
 cudaError_t launch_unpack12(uint16_t* out, const void* in, long long octets, int smCount, cudaStream_t st);

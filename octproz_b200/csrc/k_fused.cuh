@@ -32,7 +32,7 @@ namespace octb200 {
 #endif
 /* experiments for the two-warp kernels (tools/variant_sweep.sh): each of the two instruction cuts of the N = 1024 kernels on its own */
 #ifndef OCT_R2_NOSHIFT
-#define OCT_R2_NOSHIFT 0
+#define OCT_R2_NOSHIFT 1
 #endif
 #ifndef OCT_R2_EGVAR
 #define OCT_R2_EGVAR 0
@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 #if OCT_TMEM_LUT
 	uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(smem + L.offW);
 	if (warp == 0) tmem_alloc(tmemBaseSlot, TmemMap<R>::ALLOC);
+	/* multi-GPU en-face gather: every consumer has released the frame buffer this launch overwrites (flow control, oct_device.cuh) */
+	if (a.eg.world > 1 && threadIdx.x == blockDim.x - 1) gather_wait_acks(a.eg);
 	tmem_fence_before_sync();
 	__syncthreads();
 	tmem_fence_after_sync();
@@ -198,8 +200,12 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	/* R = 2, 4-tap stage, no rolling mean: the float slot is split by sample parity (see sample_taps4_x2) */
 	constexpr bool SPLIT = (src_is_raw(SRC)) && stage_a_splits_slot(R, SA, ROLL);
 
+	/* line schedule: group g of G works through blocks of LB consecutive lines, block q = g, g + G, g + 2G, ...  LB = 1 is the plain
+	 * strided walk; a larger block lets the en-face gather store LB neighbouring values at once (oct_device.cuh GatherDev) */
 	const int G = gridDim.x * groupsPerCta;
-	const int g0 = blockIdx.x * groupsPerCta + grp;
+	const int LB = a.lineBlock > 1 ? a.lineBlock : 1;
+	const int blockStep = (G - 1) * LB + 1;            /* from the last line of a block to the first line of the group's next block */
+	const int g0 = (blockIdx.x * groupsPerCta + grp) * LB;
 
 	if constexpr (src_is_raw(SRC)) {
 		if (tig == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -216,8 +222,10 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 #endif
 	/* en-face gather fused into the epilogue: k2 index of the displayed depth bin (bin = lane + 32 k2), -1 = off */
 	const int egK2 = (a.eg.world > 0) ? (int)(a.eg.frameNr >> 5) : -1;
-	int it = 0;
-	for (int gline = g0; gline < a.lines; gline += G, ++it) {
+	int it = 0, jb = 0;                /* jb: position inside the current block */
+	float egKeep = 0.f;                /* lane j: en-face value of line j of the current block */
+	for (int gline = g0; gline < a.lines; ++it) {
+		const int glineNext = gline + ((jb + 1 == LB) ? blockStep : 1);
 		float2 v[32];
 
 		if constexpr (src_is_raw(SRC)) {
@@ -296,8 +304,8 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 						for (int i = 0; i < 8; ++i) f4[tig + 32 * R * i] = conv(w8[i]);
 					}
 				};
-				/* measured on one box, old vs new library: N = 1024 0.2153 -> 0.2112 ms, but N = 2048 0.5042 -> 0.5105 ms -- the two-warp
-				 * kernel keeps the single path */
+				/* N = 1024: 0.2153 -> 0.2112 ms (round 1).  N = 2048: within the run-to-run noise of the two-warp kernel (round 1: 0.5042 -> 0.5105 ms;
+				 * round 2 sweep, profiles/r02a_variant_sweep.txt: 0.5040 -> 0.4991 ms); on since round 2 (OCT_R2_NOSHIFT) */
 				if ((R == 1 || OCT_R2_NOSHIFT) && sh == 0) store8(cvt0); else store8(cvt);
 				/* the remaining HB + HA halo samples (Lanczos only) */
 				for (int q4 = N / 4 + tig; q4 < SE / 4; q4 += 32 * R) f4[q4] = cvt(s2[q4]);
@@ -324,7 +332,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			}
 			group_sync<R>(barId);
 			/* raw slot consumed: refill it with the next line of this group */
-			if (tig == 0 && gline + G < a.lines) issue_line_load<R, SA == SA_LANCZOS, SRC == SRC_RAW12P>(a, gline + G, slot, bar);
+			if (tig == 0 && glineNext < a.lines) issue_line_load<R, SA == SA_LANCZOS, SRC == SRC_RAW12P>(a, glineNext, slot, bar);
 			if constexpr (ROLL) {
 				const int W = a.W;
 				for (int q = tig; q < SE; q += 32 * R) {
@@ -386,7 +394,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			if (R == 1 || p == 0) epilogue_complex<0>(lane, v, o); else epilogue_complex<16>(lane, v, o);
 		} else {
 			int b = gline / a.A, al = gline - b * a.A;
-			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u) al = a.A - 1 - al;
+			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u && (unsigned)b + a.bscanBase < a.flipEnd) al = a.A - 1 - al;
 			float* o = a.out + (size_t)blockIdx.y * a.trialOutStride + ((size_t)b * a.A + al) * H;
 #if OCT_TMEM_LUT
 			float egVal = 0.f;
@@ -394,13 +402,24 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			co.line = CONV ? a.convOut + ((size_t)b * a.A + al) * H : nullptr;
 			co.scale = a.convScale;
 			if (R == 1 || p == 0) epilogue_tmem<R, 0, CONV>(lane, v, a.epi, tq, o, co, egK2, egVal); else epilogue_tmem<R, 16, CONV>(lane, v, a.epi, tq, o, co, egK2, egVal);
-			if (egK2 >= 0 && (R == 1 || p == (egK2 >> 4)) && lane == (int)(a.eg.frameNr & 31u)) gather_store(a.eg, (unsigned)(b * a.A + al), egVal);
+			if (egK2 >= 0 && (R == 1 || p == (egK2 >> 4))) {
+				/* the value sits in lane frameNr % 32; lane jb keeps it until the block is complete, then lanes 0 .. jb store the block's
+				 * neighbouring values into every rank's frame (flip is an A-scan permutation inside a B-scan: a flipped line is stored alone) */
+				const float val = __shfl_sync(0xffffffffu, egVal, (int)(a.eg.frameNr & 31u));
+				if (a.flip) gather_store_block(a.eg, (unsigned)(b * a.A + al), 1, lane, val);
+				else {
+					if (lane == jb) egKeep = val;
+					if (jb + 1 == LB || glineNext >= a.lines) gather_store_block(a.eg, (unsigned)(gline - jb), jb + 1, lane, egKeep);
+				}
+			}
 #else
 			static_assert(!CONV, "the converted output is written by the tensor-memory epilogue only (OCT_TMEM_LUT = 1)");
 			if (R == 1 || p == 0) epilogue_scaled<0>(lane, v, a.epi, sMean, sPpbg, o); else epilogue_scaled<16>(lane, v, a.epi, sMean, sPpbg, o);
 #endif
 		}
 		group_sync<R>(barId);              /* tile / slot reads finished before the next line's conversion overwrites them */
+		gline = glineNext;
+		jb = (jb + 1 == LB) ? 0 : jb + 1;
 	}
 #if OCT_TMEM_LUT
 	tmem_fence_before_sync();
@@ -409,7 +428,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 #else
 	__syncthreads();
 #endif
-	if (a.eg.world > 0) gather_push_and_publish(a.eg, (unsigned)a.lines);
+	if (a.eg.world > 0) gather_publish(a.eg);      /* behind the CTA-wide barrier above */
 
 }
 

@@ -51,16 +51,27 @@ __device__ __forceinline__ float u16hi_to_float(uint32_t w) { return __uint_as_f
 
 /* ---------------- en-face gather over peer memory, fused into the epilogue (multi-GPU shards) ----------------
  * world > 0: the lane that finalises depth bin frameNr of a line (updateDisplayedEnFaceFrame with one frame, cuda_code.cu:909)
- * keeps that output value in a register and writes it into this rank's frame window; at the end of the SAME kernel all CTAs
- * push the finished slab into the frame window of every other rank (coalesced P2P stores over NVLink) and the last one
- * publishes `seq` in every rank's flag word (release, system scope).  See k_aux.cu enface_gather_kernel for the
- * stand-alone form used for multi-frame averages / MIP and when later passes (sinusoidal correction, background recording)
- * still change the slab. */
+ * keeps that output value in a register; a line group works through blocks of `lineBlock` CONSECUTIVE lines, so after a block its
+ * warp holds lineBlock neighbouring en-face values and stores them -- one coalesced 4*lineBlock-byte store per rank -- straight into
+ * the frame window of EVERY rank (peer-mapped pointers: P2P stores over NVLink / NVSwitch; the own rank is a plain store).  The
+ * stores are spread over the whole kernel, there is no end-of-kernel push and no grid barrier: a CTA that has finished its lines
+ * fences once at system scope and bumps a counter; the last one publishes `seq` in every rank's "arrived" word for this rank.
+ *
+ * Window of a rank (octb200.cu EnfaceGather): [64 words arrived[producer]] [64 words ack[consumer]] ... [frame 0] [frame 1].
+ * Frames are double-buffered by sequence parity.  Flow control: before a producer stores frame `seq` into a peer's window that
+ * peer must have consumed frame seq - 2 (same parity): the consumer's enface_consume_kernel (k_aux.cu) waits for all arrived[]
+ * words, copies the frame into its private display buffer and THEN writes ack[consumer] = seq into every producer's window; a
+ * producer checks its own (local) ack words in the kernel prologue.  Every spin has a time-out (status word), never a hang.
+ * See k_aux.cu enface_gather_kernel for the stand-alone form used for multi-frame averages / MIP and when later passes
+ * (sinusoidal correction, background recording) still change the slab. */
 constexpr int OCT_MAX_PEERS = 16;
+constexpr int OCT_GATHER_ARRIVED = 0, OCT_GATHER_ACK = 64, OCT_GATHER_HEADER_BYTES = 1024;
+constexpr unsigned long long OCT_GATHER_TIMEOUT_NS = 10ull * 1000ull * 1000ull * 1000ull;
 struct GatherDev {
-	float* frames[OCT_MAX_PEERS];
-	unsigned* flags[OCT_MAX_PEERS];
-	unsigned* counter;
+	float* frames[OCT_MAX_PEERS];      /* frame window (parity of seq) of every rank */
+	unsigned* flags[OCT_MAX_PEERS];    /* header of every rank's window: arrived[] at word 0, ack[] at word 64 */
+	unsigned* counter;                 /* local CTA completion counter (zero between launches) */
+	unsigned* status;                  /* local: [0] = time-outs waiting for acknowledgements, [1] = time-outs waiting for arrivals */
 	unsigned Eglobal, offset, seq;
 	unsigned frameNr, nFrames;
 	int fn;
@@ -72,51 +83,46 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) { as
 __device__ __forceinline__ void st_relaxed_sys_u32(unsigned* p, unsigned v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-/* phase 1 (per line, by the one lane that holds the depth bin): the en-face value goes into THIS rank's own frame window */
-__device__ __forceinline__ void gather_store(const GatherDev& g, unsigned line, float val) {
-	g.frames[g.rank][(g.Eglobal - 1u) - (g.offset + line)] = val;
+/* spin until *word >= want (sequence numbers, wrap-safe) or the time-out; returns false on time-out */
+__device__ __forceinline__ bool gather_spin_ge(const unsigned* word, unsigned want) {
+	if ((int)(ld_acquire_sys_u32(word) - want) >= 0) return true;
+	const unsigned long long t0 = global_timer_ns();
+	while ((int)(ld_acquire_sys_u32(word) - want) < 0) {
+		__nanosleep(100);
+		if (global_timer_ns() - t0 > OCT_GATHER_TIMEOUT_NS) return false;
+	}
+	return true;
 }
-/* phase 2 (end of the kernel, all CTAs): once every CTA has finished its lines (grid barrier on g.counter -- the grid is one
- * persistent CTA per SM, all resident), each CTA pushes its share of this rank's slab to every peer with coalesced 16-byte
- * stores over NVLink; the last CTA to finish the push publishes `seq` in every rank's flag word.  Scattered 4-byte peer stores
- * straight from the epilogue cost 34 us per volume at 8 GPUs; the bulk push costs a few. */
-__device__ __forceinline__ void gather_push_and_publish(const GatherDev& g, unsigned E) {
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		atomicAdd(g.counter, 1u);
-		while (ld_acquire_gpu_u32(g.counter) < gridDim.x) __nanosleep(64);
+/* producer prologue (one thread per CTA): every consumer has released the frame buffer this launch is about to overwrite */
+__device__ __forceinline__ void gather_wait_acks(const GatherDev& g) {
+	if (g.world < 2 || g.seq < 3u) return;
+	const unsigned* acks = g.flags[g.rank] + OCT_GATHER_ACK;
+	bool ok = true;
+	for (int c = 0; c < g.world; ++c) ok = gather_spin_ge(acks + c, g.seq - 2u) && ok;
+	if (!ok) atomicAdd(g.status, 1u);
+}
+/* after a block of `cnt` consecutive lines starting at `firstLine`: lanes 0 .. cnt-1 hold their en-face values */
+__device__ __forceinline__ void gather_store_block(const GatherDev& g, unsigned firstLine, int cnt, int lane, float val) {
+	if (lane < cnt) {
+		const unsigned idx = (g.Eglobal - 1u) - (g.offset + firstLine + (unsigned)lane);      /* the reference writes the frame reversed (cuda_code.cu:909) */
+#pragma unroll 1
+		for (int r = 0; r < g.world; ++r) g.frames[r][idx] = val;
 	}
-	__syncthreads();
-	if (g.world > 1) {
-		const unsigned lo = g.Eglobal - g.offset - E;                       /* this rank's slab inside the (reversed) frame */
-		const float* src = g.frames[g.rank] + lo;
-		/* head / tail so that the body is 16-byte aligned in every window (windows are 256-byte aligned) */
-		const unsigned head = ((4u - (lo & 3u)) & 3u) < E ? ((4u - (lo & 3u)) & 3u) : E;
-		const unsigned quads = (E - head) >> 2, tail = head + (quads << 2);
-		const unsigned per = (quads + gridDim.x - 1) / gridDim.x;
-		const unsigned q0 = blockIdx.x * per, q1 = (q0 + per < quads) ? q0 + per : quads;
-		for (int r = 0; r < g.world; ++r) {
-			if (r == g.rank) continue;
-			float* dst = g.frames[r] + lo;
-			for (unsigned q = q0 + threadIdx.x; q < q1; q += blockDim.x)
-				reinterpret_cast<float4*>(dst + head)[q] = __ldcg(reinterpret_cast<const float4*>(src + head) + q);
-			if (blockIdx.x == 0) {
-				for (unsigned i = threadIdx.x; i < head; i += blockDim.x) dst[i] = __ldcg(src + i);
-				for (unsigned i = tail + threadIdx.x; i < E; i += blockDim.x) dst[i] = __ldcg(src + i);
-			}
-		}
-	}
-	__syncthreads();
+}
+/* end of the kernel, after a CTA-wide barrier: one system-scope fence per CTA orders the peer stores of all its threads (fence
+ * cumulativity through the barrier); the last CTA to arrive publishes `seq` in every rank's arrived[] word for this rank.  No CTA
+ * waits for another one, so nothing here depends on the CTAs being co-resident. */
+__device__ __forceinline__ void gather_publish(const GatherDev& g) {
 	if (threadIdx.x == 0) {
-		__threadfence_system();      /* one system-scope fence after the CTA barrier orders the peer stores of all its threads (fence cumulativity) */
+		__threadfence_system();
 		const unsigned done = atomicAdd(g.counter, 1u);
-		if (done == 2u * gridDim.x - 1u) {
-			*g.counter = 0;              /* every CTA has left the spin above: safe to rearm for the next launch (stream ordered) */
+		if (done == gridDim.x * gridDim.y - 1u) {
+			*g.counter = 0;              /* the next launch is stream ordered behind this one */
 			__threadfence_system();
 #pragma unroll 1
-			for (int r = 0; r < g.world; ++r) st_relaxed_sys_u32(g.flags[r] + g.rank, g.seq);
+			for (int r = 0; r < g.world; ++r) st_relaxed_sys_u32(g.flags[r] + OCT_GATHER_ARRIVED + g.rank, g.seq);
 		}
 	}
 }
@@ -142,6 +148,9 @@ struct FusedArgs {
 	int W;
 	int HB, HA;
 	GatherDev eg;            /* eg.world == 0: no en-face gather in this launch */
+	int lineBlock;           /* a line group works through blocks of this many consecutive lines (1, 2, 4, 8; 0 = 1); see GatherDev */
+	unsigned flipEnd;        /* B-scans with (index + bscanBase) >= flipEnd are never flipped: with an odd number of B-scans the reference's
+	                            cuda_bscanFlip leaves the last one alone (cuda_code.cu:794-805 runs over samplesPerBuffer/4 elements) */
 	/* dispersion sweep (gridDim.y = trials): trial t = blockIdx.y processes the SAME lines with its own stage LUT and writes its own output slab */
 	int trials;              /* 0 / 1: plain launch */
 	int trialLutStride;      /* float4 elements between the LUT images of consecutive trials */

@@ -27,21 +27,40 @@ namespace octb200 {
 #ifndef OCT_EPI_PAIR
 #define OCT_EPI_PAIR 0
 #endif
-/* OCT_TW4 = 1 (experiment, not the default): every inter-pass twiddle is stored as four words (t.x, t.y, -t.y, t.x), the two operand
- * pairs of the packed complex multiply, instead of two -- a half-pair negation is not a free operand modifier, so the two-word form
- * costs one FADD per twiddle and line (31).  Same arithmetic, bit-identical results. */
-#ifndef OCT_TW4
-#define OCT_TW4 0
+/* Inter-pass twiddle layout and read width, per line-group size R (measured on one B200 box, tools/variant_sweep.sh,
+ * profiles/r02a_variant_sweep.txt; every variant is bit-identical, same output hash):
+ *   TW4  : every inter-pass twiddle is stored as four words (t.x, t.y, -t.y, t.x), the two operand pairs of the packed complex multiply,
+ *          instead of two -- a half-pair negation is not a free operand modifier, so the two-word form costs one FADD per twiddle and
+ *          line (31).  Same arithmetic bit for bit.
+ *   XCHG : registers per tensor-memory read of the exchange phase.  8 = double-buffered x8 reads (ptxas hoists them and copies the
+ *          still-live tuple out of the way: 66 MOV per line); 32 = two single-buffered x32 reads whose destination registers are the
+ *          ones the stored values free up (MOV 74 -> 23 per line).
+ *   N = 1024 (R = 1): TW4 + x32 0.2114 -> 0.2042 ms per 1024x512x256 volume (tw4 alone 0.2072, x32 alone 0.2094).
+ *   N = 2048 (R = 2): x32 costs the two-warp kernel 1.5-4 % (0.504 -> 0.512-0.524 ms per 2048x1024x128 buffer); tw4 alone 0.4998. */
+#ifndef OCT_R1_TW4
+#define OCT_R1_TW4 1
 #endif
+#ifndef OCT_R2_TW4
+#define OCT_R2_TW4 1
+#endif
+#ifndef OCT_R1_XCHG_X
+#define OCT_R1_XCHG_X 32
+#endif
+#ifndef OCT_R2_XCHG_X
+#define OCT_R2_XCHG_X 8
+#endif
+template <int R> struct XchgCfg {
+	static constexpr bool TW4 = (R == 1) ? (OCT_R1_TW4 != 0) : (OCT_R2_TW4 != 0);
+	static constexpr int X = (R == 1) ? OCT_R1_XCHG_X : OCT_R2_XCHG_X;
+};
 template <int R> struct TmemMap;
 /* per lane quadrant; for R = 2 a quadrant only holds the tables of ITS sub-sequence p = quadrant & 1 (warp w: p = w % 2, quadrant w % 4) */
-#if OCT_TW4
-template <> struct TmemMap<1> { static constexpr int LUT = 0, TW = 256, CTW = 384, MEAN = 384, PPBG = 416, ALLOC = 512; };
-template <> struct TmemMap<2> { static constexpr int LUT = 0, TW = 256, CTW = 384, MEAN = 448, PPBG = 480, ALLOC = 512; };
-#else
-template <> struct TmemMap<1> { static constexpr int LUT = 0, TW = 256, CTW = 320, MEAN = 320, PPBG = 352, ALLOC = 512; };
-template <> struct TmemMap<2> { static constexpr int LUT = 0, TW = 256, CTW = 320, MEAN = 384, PPBG = 416, ALLOC = 512; };
-#endif
+template <> struct TmemMap<1> {
+	static constexpr int LUT = 0, TW = 256, CTW = XchgCfg<1>::TW4 ? 384 : 320, MEAN = CTW, PPBG = MEAN + 32, ALLOC = 512;
+};
+template <> struct TmemMap<2> {
+	static constexpr int LUT = 0, TW = 256, CTW = XchgCfg<2>::TW4 ? 384 : 320, MEAN = CTW + 64, PPBG = MEAN + 32, ALLOC = 512;
+};
 
 /* ---- raw tcgen05 wrappers (SASS: LDTM / STTM / UTCALLOC) ---- */
 __device__ __forceinline__ void tmem_alloc(uint32_t* smemResult, int cols) {
@@ -214,12 +233,12 @@ __device__ __forceinline__ void tmem_fill(uint32_t tq /* quadrant base */, int q
 		for (int u = 0; u < 4; ++u) {
 			const int i = base + u * parts;
 			if (i < 16) {
-#if OCT_TW4
-				tmem_st_f4(tq + M::TW + 8 * i, make_float4(t[u].x, t[u].y, -t[u].y, t[u].x));
-				tmem_st_f4(tq + M::TW + 8 * i + 4, make_float4(t[u].z, t[u].w, -t[u].w, t[u].z));
-#else
-				tmem_st_f4(tq + M::TW + 4 * i, t[u]);
-#endif
+				if constexpr (XchgCfg<R>::TW4) {
+					tmem_st_f4(tq + M::TW + 8 * i, make_float4(t[u].x, t[u].y, -t[u].y, t[u].x));
+					tmem_st_f4(tq + M::TW + 8 * i + 4, make_float4(t[u].z, t[u].w, -t[u].w, t[u].z));
+				} else {
+					tmem_st_f4(tq + M::TW + 4 * i, t[u]);
+				}
 				if constexpr (R == 2) tmem_st_f4(tq + M::CTW + 4 * i, c[u]);
 				if (fpn && i < 8) tmem_st_f4(tq + M::MEAN + 4 * i, m[u]);
 				if (a.epi.ppbg && i < 4) tmem_st_f4(tq + M::PPBG + 4 * i, g[u]);
@@ -280,23 +299,17 @@ __device__ __forceinline__ void stage_a_tmem(int lane, int p, const float* f, in
 }
 
 /* ---- inter-pass twiddle + transpose store, twiddles from TMEM (cf. exchange_store): w^{k1 lane} at columns TW + 2 k1 ----
- * OCT_XCHG_X = registers per tensor-memory read (8: four twiddles, 4: two, 2: one).  The read of chunk c+1 is in flight while
- * chunk c is multiplied and stored.  ptxas hoists these reads for latency and, when the destination tuple is still live, copies the
- * old values out of it: the wider the tuple, the more MOVs (x8: 66 per line). */
-#ifndef OCT_XCHG_X
-#define OCT_XCHG_X 8
-#endif
+ * XchgCfg<R>::X = registers per tensor-memory read (see the top of this file).  With X = 8 the read of chunk c+1 is in flight while
+ * chunk c is multiplied and stored. */
 template <int R>
 __device__ __forceinline__ void exchange_store_tmem(int lane, const float2 (&v)[32], float2* xbuf, uint32_t tq) {
 	using M = TmemMap<R>;
-	constexpr int WPT = OCT_TW4 ? 4 : 2;                          /* words per twiddle */
-	constexpr int X = OCT_XCHG_X, TW = X / WPT, CH = 32 / TW;     /* registers per read, twiddles per read, reads per line */
+	constexpr bool TW4 = XchgCfg<R>::TW4;
+	constexpr int WPT = TW4 ? 4 : 2;                              /* words per twiddle */
+	constexpr int X = XchgCfg<R>::X, TW = X / WPT, CH = 32 / TW;  /* registers per read, twiddles per read, reads per line */
 	auto twmul = [](float2 val, const float* w) {
-#if OCT_TW4
-		return pfma(make_float2(val.y, val.y), make_float2(w[2], w[3]), pmul(make_float2(val.x, val.x), make_float2(w[0], w[1])));
-#else
-		return cmul(val, make_float2(w[0], w[1]));
-#endif
+		if constexpr (TW4) return pfma(make_float2(val.y, val.y), make_float2(w[2], w[3]), pmul(make_float2(val.x, val.x), make_float2(w[0], w[1])));
+		else return cmul(val, make_float2(w[0], w[1]));
 	};
 	auto issue = [&](int c, float (&dst)[X]) { tmem_ldx_issue(tq + M::TW + X * c, dst); };
 	auto wait = [&](float (&dst)[X]) { tmem_ldx_wait(dst); };

@@ -111,16 +111,17 @@ struct octb200_pipeline {
 	float* dSweepPhase = nullptr; float2* dSweepPhasor = nullptr; size_t sweepPhaseElems = 0;
 	float* dSweepMetric = nullptr; size_t sweepMetricElems = 0;
 
-	/* en-face gather over peer memory (multi-GPU shards): local window = [64 flag words][frame 0][frame 1] */
+	/* en-face gather over peer memory (multi-GPU shards): local window = [1 KiB header: arrived[], ack[]][frame 0][frame 1] (oct_device.cuh) */
 	struct EnfaceGather {
 		int world = 0, rank = 0;
-		unsigned Eglobal = 0, offset = 0, seq = 0;
+		unsigned Eglobal = 0, offset = 0, seq = 0, consumedSeq = 0;
 		unsigned char* window = nullptr;
 		size_t frameStride = 0;
 		unsigned char* peerBase[OCT_MAX_PEERS] = {};
 		bool opened[OCT_MAX_PEERS] = {};
 		bool connected = false;
-		unsigned* counter = nullptr;
+		unsigned* counter = nullptr;       /* [0] producer kernels, [1] consume kernel, [2..3] status (time-outs: acks, arrivals) */
+		float* display = nullptr;          /* private copy of the last consumed frame */
 		bool autoOn = false;               /* every process call also gathers the en-face frame */
 		unsigned autoFrame = 0, autoFrames = 1; int autoFn = 0;
 	} eg;
@@ -257,6 +258,14 @@ int ensure_fpn_scratch(octb200_pipeline* p, size_t elems) {
 	return rc;
 }
 
+/* cuda_bscanFlip runs over samplesPerBuffer/4 output elements (cuda_code.cu:794-805, launch :1547): with an odd number of B-scans
+   per buffer the last (even-indexed) B-scan is only visited in its lower half and never swapped.  B-scan indices at or beyond this
+   bound are not flipped; shards pass the B-scan count of the un-sharded buffer (octb200_config.bscansInUnshardedBuffer). */
+unsigned flip_end(const octb200_pipeline* p) {
+	const unsigned total = p->cfg.bscansInUnshardedBuffer ? p->cfg.bscansInUnshardedBuffer : p->cfg.bscanIndexBase + (unsigned)p->B;
+	return total & ~1u;
+}
+
 FusedArgs fused_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, int lines) {
 	FusedArgs a{};
 	a.raw = static_cast<const uint16_t*>(dRaw);
@@ -264,8 +273,9 @@ FusedArgs fused_args(const octb200_pipeline* p, const Stage& st, const void* dRa
 	a.lutB = p->dLutB; a.tw = p->dTw; a.ctw = p->dCtw;
 	a.meanLine = p->dMeanLine; a.ppbg = p->dPpbg;
 	a.totalSamples = p->S; a.lines = lines; a.A = p->A;
-	a.flip = p->prm.bscanFlip; a.bscanBase = p->cfg.bscanIndexBase;
+	a.flip = p->prm.bscanFlip; a.bscanBase = p->cfg.bscanIndexBase; a.flipEnd = flip_end(p);
 	a.shiftBits = p->prm.bitshift ? 4 : 0; a.W = st.W; a.HB = st.HB; a.HA = st.HA;
+	a.lineBlock = 1;
 	return a;
 }
 PreArgs pre_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, int lines) {
@@ -280,16 +290,16 @@ PreArgs pre_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, i
 	return a;
 }
 
-/* next en-face gather of this handle: sequence number, frame window of that parity on every rank, flag words */
+/* next en-face gather of this handle: sequence number, frame window of that parity on every rank, header words */
 GatherDev next_gather(octb200_pipeline* p, unsigned frameNr, unsigned nFrames, int fn) {
 	auto& g = p->eg;
 	GatherDev d{};
 	g.seq++;
 	for (int r = 0; r < g.world; ++r) {
-		d.frames[r] = reinterpret_cast<float*>(g.peerBase[r] + 256 + (size_t)(g.seq & 1u) * g.frameStride);
+		d.frames[r] = reinterpret_cast<float*>(g.peerBase[r] + OCT_GATHER_HEADER_BYTES + (size_t)(g.seq & 1u) * g.frameStride);
 		d.flags[r] = reinterpret_cast<unsigned*>(g.peerBase[r]);
 	}
-	d.counter = g.counter; d.Eglobal = g.Eglobal; d.offset = g.offset; d.seq = g.seq;
+	d.counter = g.counter; d.status = g.counter + 2; d.Eglobal = g.Eglobal; d.offset = g.offset; d.seq = g.seq;
 	d.frameNr = (frameNr >= (unsigned)p->H) ? 0u : frameNr;          /* cuda_code.cu:1302 */
 	d.nFrames = nFrames < 1 ? 1u : nFrames; d.fn = fn; d.world = g.world; d.rank = g.rank;
 	return d;
@@ -297,11 +307,42 @@ GatherDev next_gather(octb200_pipeline* p, unsigned frameNr, unsigned nFrames, i
 cudaError_t launch_gather_standalone(octb200_pipeline* p, const GatherDev& d) {
 	EnfaceGatherArgs a{};
 	for (int r = 0; r < d.world; ++r) { a.frames[r] = d.frames[r]; a.flags[r] = d.flags[r]; }
-	a.vol = p->dVolume; a.counter = d.counter;
+	a.vol = p->dVolume; a.counter = d.counter; a.status = d.status;
 	a.W = (unsigned)p->H; a.E = (unsigned)(p->A * p->B * p->V);
 	a.frameNr = d.frameNr; a.nFrames = d.nFrames; a.fn = d.fn;
 	a.Eglobal = d.Eglobal; a.offset = d.offset; a.world = d.world; a.rank = d.rank; a.seq = d.seq;
 	return launch_enface_gather(a, p->sCompute);
+}
+/* consumer side of the latest gather (once per sequence number): wait for every rank's slab, copy the frame into the private display
+   frame, acknowledge to every producer.  Enqueued right behind every gather: a rank consumes each frame it takes part in, so the
+   producers' flow-control wait (two gathers later) is normally satisfied long before they look. */
+cudaError_t consume_gather(octb200_pipeline* p) {
+	auto& g = p->eg;
+	if (g.consumedSeq == g.seq) return cudaSuccess;
+	EnfaceConsumeArgs a{};
+	for (int r = 0; r < g.world; ++r) a.peerHeaders[r] = reinterpret_cast<unsigned*>(g.peerBase[r]);
+	a.window = reinterpret_cast<const unsigned*>(g.window);
+	a.frame = reinterpret_cast<const float*>(g.window + OCT_GATHER_HEADER_BYTES + (size_t)(g.seq & 1u) * g.frameStride);
+	a.display = g.display; a.counter = g.counter + 1; a.status = g.counter + 2;
+	a.Eglobal = g.Eglobal; a.seq = g.seq; a.world = g.world; a.rank = g.rank;
+	cudaError_t e = launch_enface_consume(a, p->smCount, p->sCompute);
+	if (e == cudaSuccess) { g.consumedSeq = g.seq; p->launches++; }
+	return e;
+}
+
+/* a line group of the fused kernel works through blocks of this many consecutive lines when the en-face gather is fused into its
+   epilogue (one coalesced peer store per block and rank): the largest of 8, 4, 2, 1 that does not add a round to the slowest group */
+int gather_line_block(const octb200_pipeline* p, const Stage& st, int src, int lines) {
+	int grid = 0, threads = 0, smem = 0;
+	fused_launch_shape(p->R, st.sa, st.roll, src, st.HB, st.HA, p->smCount, lines, &grid, &threads, &smem);
+	const int G = grid * (threads / 32 / p->R);
+	if (G < 1) return 1;
+	const int rounds = (lines + G - 1) / G;
+	for (int lb = 8; lb > 1; lb >>= 1) {
+		const int blocks = (lines + lb - 1) / lb;
+		if (((blocks + G - 1) / G) * lb == rounds) return lb;
+	}
+	return 1;
 }
 
 /* the whole per-buffer chain on the compute stream; dRaw is device memory */
@@ -384,7 +425,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		PostArgs po{};
 		po.in = p->dFft; po.out = mainOut; po.meanLine = p->dMeanLine; po.ppbg = p->dPpbg;
 		po.epi = epi_for(p, fpn, ppbgFoldMain); po.lines = p->lines; po.N = p->N; po.A = p->A;
-		po.flip = q.bscanFlip; po.bscanBase = p->cfg.bscanIndexBase;
+		po.flip = q.bscanFlip; po.bscanBase = p->cfg.bscanIndexBase; po.flipEnd = flip_end(p);
 		CK(p, launch_post(po, p->smCount, p->sCompute)); p->launches++;
 	} else {
 		const int src = (mode == OCTB200_FFT_FUSED) ? rawSrc : SRC_CPLX;
@@ -403,6 +444,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		/* automatic en-face gather: fused into this kernel's epilogue when the slab is final after it */
 		if (p->eg.autoOn && p->eg.connected && !sinus && !ppbgRecord && p->V == 1 && p->eg.autoFrames <= 1) {
 			fa.eg = next_gather(p, p->eg.autoFrame, p->eg.autoFrames, p->eg.autoFn);
+			fa.lineBlock = gather_line_block(p, st, src, p->lines);
 			gatherDone = true;
 		}
 		if (convFused) {
@@ -434,6 +476,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		const GatherDev d = next_gather(p, p->eg.autoFrame, p->eg.autoFrames, p->eg.autoFn);
 		CK(p, launch_gather_standalone(p, d)); p->launches++;
 	}
+	if (p->eg.autoOn && p->eg.connected) CK(p, consume_gather(p));
 
 	/* ---- streaming to the host (cuda_code.cu:1357-1386,1595-1604) ---- */
 	const bool wantFloat = q.streamFloatToHost && p->hostFloat[0] && p->hostFloat[1];
@@ -748,12 +791,21 @@ int octb200_set_callbacks(octb200_pipeline* p, octb200_host_callback s, octb200_
 }
 
 /* ---------- hot path ---------- */
+/* after every chain that read internal raw slot `s` -- also a re-run on the resident buffer and a chain that failed half way: the next
+   upload into that slot waits for the kernels enqueued so far */
+static int chain_on_slot(octb200_pipeline* p, int s) {
+	const int rc = run_chain(p, p->dRaw[s]);
+	const cudaError_t e = cudaEventRecord(p->evRawFree[s], p->sCompute);
+	if (rc) return rc;
+	CK(p, e);
+	return OCTB200_OK;
+}
 int octb200_process_host(octb200_pipeline* p, const void* hRaw) {
 	if (!p) return OCTB200_ERR_INVALID;
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	if (!hRaw) {
 		if (p->slot < 0 && !p->lastDeviceRaw) return fail(p, OCTB200_ERR_NOT_READY, "no buffer has been uploaded yet");
-		return run_chain(p, p->slot >= 0 ? p->dRaw[p->slot] : p->lastDeviceRaw);
+		return p->slot >= 0 ? chain_on_slot(p, p->slot) : run_chain(p, p->lastDeviceRaw);
 	}
 	const int s = (p->slot + 1) % (int)p->dRaw.size();
 	const size_t bytes = p->inBytes;
@@ -762,9 +814,8 @@ int octb200_process_host(octb200_pipeline* p, const void* hRaw) {
 	CK(p, cudaEventRecord(p->evRawReady[s], p->sH2D));
 	CK(p, cudaStreamWaitEvent(p->sCompute, p->evRawReady[s], 0));
 	p->slot = s;
-	int rc = run_chain(p, p->dRaw[s]);
+	int rc = chain_on_slot(p, s);
 	if (rc) return rc;
-	CK(p, cudaEventRecord(p->evRawFree[s], p->sCompute));
 	/* the producer may overwrite hRaw as soon as we return (processing.cpp:191) -- same contract as cuda_code.cu:1416-1419 */
 	CK(p, cudaEventSynchronize(p->evRawReady[s]));
 	return OCTB200_OK;
@@ -774,7 +825,8 @@ int octb200_process_device(octb200_pipeline* p, const void* dRaw) {
 	if (!p) return OCTB200_ERR_INVALID;
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	if (!dRaw) {
-		dRaw = p->lastDeviceRaw ? p->lastDeviceRaw : (p->slot >= 0 ? p->dRaw[p->slot] : nullptr);
+		if (!p->lastDeviceRaw && p->slot >= 0) return chain_on_slot(p, p->slot);     /* re-run on the internal slot the last upload filled */
+		dRaw = p->lastDeviceRaw;
 		if (!dRaw) return fail(p, OCTB200_ERR_NOT_READY, "no device buffer to re-process");
 	}
 	if (reinterpret_cast<uintptr_t>(dRaw) & 15) return fail(p, OCTB200_ERR_INVALID, "device raw pointer must be 16-byte aligned");
@@ -848,10 +900,11 @@ int octb200_enface_gather_init(octb200_pipeline* p, int rank, int world, uint32_
 	if ((unsigned long long)lineOffset + E > globalLines) return fail(p, OCTB200_ERR_INVALID, "shard [%u, %u) exceeds the %u lines of the volume", lineOffset, lineOffset + E, globalLines);
 	octb200_enface_gather_close(p);
 	auto& g = p->eg;
-	g.world = world; g.rank = rank; g.Eglobal = globalLines; g.offset = lineOffset; g.seq = 0;
+	g.world = world; g.rank = rank; g.Eglobal = globalLines; g.offset = lineOffset; g.seq = 0; g.consumedSeq = 0;
 	g.frameStride = ((size_t)globalLines * sizeof(float) + 255) / 256 * 256;
-	{ int rc = dalloc(p, &g.window, 256 + 2 * g.frameStride); if (rc) return rc; }
-	{ int rc = dalloc(p, &g.counter, 1); if (rc) return rc; }
+	{ int rc = dalloc(p, &g.window, OCT_GATHER_HEADER_BYTES + 2 * g.frameStride); if (rc) return rc; }
+	{ int rc = dalloc(p, &g.counter, 4); if (rc) return rc; }
+	{ int rc = dalloc(p, &g.display, (size_t)globalLines + 4); if (rc) return rc; }
 	cudaIpcMemHandle_t h;
 	CK(p, cudaIpcGetMemHandle(&h, g.window));
 	static_assert(sizeof(h) == OCTB200_IPC_HANDLE_BYTES, "ipc handle size");
@@ -879,6 +932,7 @@ int octb200_enface_gather(octb200_pipeline* p, uint32_t frameNr, uint32_t nFrame
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	const GatherDev d = next_gather(p, frameNr, nFrames, fn);
 	CK(p, launch_gather_standalone(p, d)); p->launches++;
+	CK(p, consume_gather(p));
 	return OCTB200_OK;
 }
 int octb200_enface_gather_auto(octb200_pipeline* p, int enable, uint32_t frameNr, uint32_t nFrames, int fn) {
@@ -890,9 +944,19 @@ int octb200_enface_gather_auto(octb200_pipeline* p, int enable, uint32_t frameNr
 int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame) {
 	if (!p || !p->eg.connected || p->eg.seq == 0) return fail(p, OCTB200_ERR_NOT_READY, "no en-face gather issued");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
-	auto& g = p->eg;
-	CK(p, launch_enface_wait(reinterpret_cast<const unsigned*>(g.window), g.world, g.seq, p->sCompute)); p->launches++;
-	if (dFrame) *dFrame = reinterpret_cast<float*>(g.window + 256 + (size_t)(g.seq & 1u) * g.frameStride);
+	CK(p, consume_gather(p));          /* already enqueued behind the gather itself; a no-op then */
+	if (dFrame) *dFrame = p->eg.display;
+	return OCTB200_OK;
+}
+int octb200_enface_gather_status(octb200_pipeline* p, uint32_t* sequence, uint32_t* ackTimeouts, uint32_t* arrivalTimeouts) {
+	if (!p || !p->eg.counter) return fail(p, OCTB200_ERR_NOT_READY, "enface_gather_init first");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	unsigned st[2] = { 0, 0 };
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	CK(p, cudaMemcpy(st, p->eg.counter + 2, sizeof(st), cudaMemcpyDeviceToHost));
+	if (sequence) *sequence = p->eg.seq;
+	if (ackTimeouts) *ackTimeouts = st[0];
+	if (arrivalTimeouts) *arrivalTimeouts = st[1];
 	return OCTB200_OK;
 }
 int octb200_enface_gather_close(octb200_pipeline* p) {
@@ -905,8 +969,8 @@ int octb200_enface_gather_close(octb200_pipeline* p) {
 		if (g.opened[r] && g.peerBase[r]) cudaIpcCloseMemHandle(g.peerBase[r]);
 		g.opened[r] = false; g.peerBase[r] = nullptr;
 	}
-	dfree(g.window); dfree(g.counter);
-	g.connected = false; g.world = 0; g.seq = 0; g.autoOn = false;
+	dfree(g.window); dfree(g.counter); dfree(g.display);
+	g.connected = false; g.world = 0; g.seq = 0; g.consumedSeq = 0; g.autoOn = false;
 	return OCTB200_OK;
 }
 

@@ -30,16 +30,27 @@ def _ptr(x) -> int:
     raise TypeError(f"cannot take the address of {type(x)}")
 
 
+def device_copy(dst, src_ptr: int, nbytes: int) -> None:
+    """copy `nbytes` from a raw device address (e.g. the frame octb200_enface_gather_wait returns) into a torch CUDA tensor"""
+    import torch
+    rt = torch.cuda.cudart()
+    err = rt.cudaMemcpy(int(dst.data_ptr()), int(src_ptr), int(nbytes), 3)     # cudaMemcpyDeviceToDevice
+    if int(err) != 0:
+        raise _lib.Octb200Error(f"cudaMemcpy failed: {err}")
+
+
 class OctPipeline:
     def __init__(self, fft_mode: int = _lib.FFT_AUTO, device: int = -1, raw_slots: int = 2, bscan_index_base: int = 0,
-                 input_packing: int = _lib.PACK_CONTAINER, flags: int = 0):
+                 input_packing: int = _lib.PACK_CONTAINER, flags: int = 0, bscans_in_unsharded_buffer: int = 0):
         """input_packing = PACK_12P: the raw buffers hold 12-bit samples packed two per three bytes (octproz_b200.packing.pack12),
-        an extension over the reference's container formats.  flags: _lib.FLAG_* (octb200_config.flags)"""
+        an extension over the reference's container formats.  flags: _lib.FLAG_* (octb200_config.flags).
+        bscans_in_unsharded_buffer: shards only -- B-scans per buffer of the un-sharded acquisition (octb200_config, B-scan flip)"""
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self._fft_mode, self._device, self._raw_slots, self._bscan_base = fft_mode, device, raw_slots, bscan_index_base
         self._packing = input_packing
         self._flags = flags
+        self._unsharded = bscans_in_unsharded_buffer
         self.params: OctAlgorithmParameters | None = None
         self._callbacks = None
 
@@ -63,7 +74,7 @@ class OctPipeline:
         (numpy arrays or None); they are pinned like the reference does (cuda_code.cu:1135-1136)."""
         cfg = _lib.Config(int(params.samplesPerLine), int(params.ascansPerBscan), int(params.bscansPerBuffer),
                           int(params.buffersPerVolume), int(params.bitDepth), int(self._device), int(self._raw_slots),
-                          int(self._fft_mode), int(self._bscan_base), int(self._packing), int(self._flags))
+                          int(self._fft_mode), int(self._bscan_base), int(self._packing), int(self._flags), int(self._unsharded))
         rc = self._lib.octb200_create(C.byref(cfg), C.byref(self._h))
         if rc != _lib.OK:
             self._h = C.c_void_p()
@@ -164,8 +175,15 @@ class OctPipeline:
         """every octCudaPipeline / process_device call also gathers this frame (inside the fused kernel's epilogue when possible)"""
         self._ck(self._lib.octb200_enface_gather_auto(self._h, int(enable), frameNr, displayFunctionFrames, displayFunction), "enface_gather_auto")
 
+    def enface_gather_status(self) -> dict:
+        """sequence number of the latest gather and the device-side time-out counters (0 / 0 in a healthy run); synchronises"""
+        seq, a, b = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._ck(self._lib.octb200_enface_gather_status(self._h, C.byref(seq), C.byref(a), C.byref(b)), "enface_gather_status")
+        return {"sequence": int(seq.value), "ack_timeouts": int(a.value), "arrival_timeouts": int(b.value)}
+
     def enface_gather_wait(self) -> int:
-        """enqueue the wait for all ranks' slabs of the latest gather; returns the device address of the assembled frame"""
+        """device address of this rank's display frame: the latest gathered frame, consumed (all ranks' slabs waited for, copied out of
+        the window, acknowledged) by the kernel that every gather enqueues behind itself"""
         out = C.c_void_p()
         self._ck(self._lib.octb200_enface_gather_wait(self._h, C.byref(out)), "enface_gather_wait")
         return int(out.value or 0)

@@ -39,8 +39,12 @@ class ShardedPipeline:
         self.local.bscansPerBuffer = self.count
         if pipeline_factory is None:
             from .pipeline import OctPipeline
-            pipeline_factory = lambda base: OctPipeline(fft_mode=fft_mode, device=device, bscan_index_base=base)  # noqa: E731
-        self.pipe = pipeline_factory(self.start % 2)
+            total = int(params.bscansPerBuffer)
+            pipeline_factory = lambda base: OctPipeline(fft_mode=fft_mode, device=device, bscan_index_base=base,  # noqa: E731
+                                                        bscans_in_unsharded_buffer=total)
+        # the index of the shard's first B-scan in the un-sharded buffer: flip parity AND the reference's "last B-scan of an odd buffer
+        # is never flipped" (cuda_code.cu:794-805) are decided on un-sharded indices
+        self.pipe = pipeline_factory(self.start)
         self._fpn_shared = False
 
     def initialize(self, h1=None, h2=None) -> bool:
@@ -70,8 +74,13 @@ class ShardedPipeline:
 
     def process_host(self, h_raw_local) -> None:
         q = self.local
-        need_share = bool(q.fixedPatternNoiseRemoval) and self.world > 1 and self.dist is not None and \
-            (not self._fpn_shared or q.continuousFixedPatternNoiseDetermination or q.redetermineFixedPatternNoise)
+        fpn = bool(q.fixedPatternNoiseRemoval) and self.world > 1 and self.dist is not None
+        need_share = fpn and (not self._fpn_shared or q.continuousFixedPatternNoiseDetermination or q.redetermineFixedPatternNoise)
+        if fpn:
+            _, count0 = shard_bounds(int(self.full.bscansPerBuffer), self.world, 0)
+            if int(q.bscansForNoiseDetermination) > count0:
+                raise ValueError(f"bscansForNoiseDetermination = {q.bscansForNoiseDetermination} exceeds rank 0's shard ({count0} B-scans): the "
+                                 "fixed-pattern-noise line is determined from the FIRST B-scans of the buffer (cuda_code.cu:1520-1522)")
         if need_share:
             # rank 0 owns the first B-scans of the buffer (cuda_code.cu:1520): it runs first, then the line is shared
             if self.rank == 0:
@@ -79,7 +88,15 @@ class ShardedPipeline:
             self._broadcast_fpn()
             self._fpn_shared = True
             if self.rank != 0 and self.count:
-                self.pipe.octCudaPipeline(h_raw_local)
+                # the other ranks USE the broadcast line: with the determination flags still set their pipeline would re-determine
+                # it from their own shard (run_chain, cuda_code.cu:1521) and overwrite it
+                cont, q.continuousFixedPatternNoiseDetermination = q.continuousFixedPatternNoiseDetermination, False
+                q.redetermineFixedPatternNoise = False
+                try:
+                    self.pipe.octCudaPipeline(h_raw_local)
+                finally:
+                    q.continuousFixedPatternNoiseDetermination = cont
+            q.redetermineFixedPatternNoise = False
         elif self.count:
             self.pipe.octCudaPipeline(h_raw_local)
 

@@ -145,6 +145,23 @@ def test_fpn_minimum_variance_segment_and_half_line_subtraction():
     assert np.allclose(out.reshape(a * b, n // 2), np.abs(Y[:, : n // 2]) / (n / 2), rtol=1e-5, atol=1e-7)
 
 
+def emulate_reference_bscan_flip(vol):
+    """cuda_bscanFlip thread by thread (cuda_code.cu:787-807, launched at :1547 with halfSamplesInVolume = samplesPerBuffer/4):
+    in-place swaps, every (index, mirrorIndex) pair is touched by exactly one thread"""
+    b, a, h = vol.shape
+    out = vol.copy().reshape(-1)
+    samples_per_bscan = h * a
+    for index0 in range((2 * h * a * b) // 4):
+        bscan = (index0 // samples_per_bscan) * 2
+        index = bscan * samples_per_bscan + index0 % samples_per_bscan
+        sample = index % samples_per_bscan
+        ascan = sample // h
+        mirror = bscan * samples_per_bscan + ((a - 1) - ascan) * h + sample % h
+        if ascan >= a // 2:
+            out[mirror], out[index] = out[index], out[mirror]
+    return out.reshape(b, a, h)
+
+
 def test_flip_even_bscans_and_sinusoidal_last_line():
     n, a, b = 64, 6, 3
     q = plain(n, a, b)
@@ -152,7 +169,14 @@ def test_flip_even_bscans_and_sinusoidal_last_line():
     base, _, _ = orc.process(q, raw)
     q.bscanFlip = True
     flipped, _, _ = orc.process(q, raw)
-    assert np.array_equal(flipped[0], base[0, ::-1]) and np.array_equal(flipped[1], base[1]) and np.array_equal(flipped[2], base[2, ::-1])
+    # odd number of B-scans: the reference's kernel covers samplesPerBuffer/4 elements, so the LAST even B-scan stays as it is
+    assert np.array_equal(flipped[0], base[0, ::-1]) and np.array_equal(flipped[1], base[1]) and np.array_equal(flipped[2], base[2])
+    for bb, aa in ((1, 6), (3, 6), (4, 6), (5, 5), (3, 5), (2, 7)):
+        qq = plain(n, aa, bb); rr = synth.make_volume(n, aa, bb, 12)
+        plain_out, _, _ = orc.process(qq, rr)
+        qq.bscanFlip = True
+        got, _, _ = orc.process(qq, rr)
+        assert np.array_equal(got, emulate_reference_bscan_flip(plain_out)), (bb, aa)
     q.sinusoidalScanCorrection = True
     sc, _, _ = orc.process(q, raw)
     curve = orc.sinusoidal_curve(a).astype(np.float64)

@@ -31,8 +31,8 @@ def test_shard_bounds_cover_and_balance():
 class OracleEngine:
     """stand-in for OctPipeline (TEST ONLY): same methods, arithmetic by the oracle"""
 
-    def __init__(self, base):
-        self.base, self.ml, self.q, self.out = base, None, None, None
+    def __init__(self, base, total):
+        self.base, self.total, self.ml, self.q, self.out = base, total, None, None, None
 
     def initializeCuda(self, h1, h2, q):
         self.q = q
@@ -48,13 +48,16 @@ class OracleEngine:
         q = copy.deepcopy(self.q)
         flip = q.bscanFlip
         q.bscanFlip = False
-        determine = q.fixedPatternNoiseRemoval and self.ml is None
-        out, ml, _ = orc.process(q, raw, mean_line=self.ml, determine_fpn=determine)
+        # run_chain's rule (octb200.cu, cuda_code.cu:1521): determine when nothing is known yet, always in continuous mode, or on request
+        determine = bool(q.fixedPatternNoiseRemoval) and (self.ml is None or bool(q.continuousFixedPatternNoiseDetermination) or
+                                                          bool(q.redetermineFixedPatternNoise))
+        out, ml, _ = orc.process(q, raw, mean_line=None if determine else self.ml, determine_fpn=determine)
         if determine:
             self.ml = ml
-        if flip:                                  # flip B-scans whose index in the UN-SHARDED buffer is even
+        if flip:                                  # flip B-scans whose index in the UN-SHARDED buffer is even -- except the last one of an odd buffer
             for b in range(out.shape[0]):
-                if (b + self.base) % 2 == 0:
+                g = b + self.base
+                if g % 2 == 0 and g < (self.total & ~1):
                     out[b] = out[b, ::-1].copy()
         self.out = out
 
@@ -76,20 +79,20 @@ class OracleEngine:
         self.gather["connected"] = False
 
 
-def _worker(rank, world, port, raw, q, ref, ref_enface, errs):
+def _worker(rank, world, port, raw, q, ref, ref_enface, errs, raw2=None, ref2=None):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        sp = ShardedPipeline(q, rank, world, dist=dist, pipeline_factory=lambda base: OracleEngine(base))
+        sp = ShardedPipeline(q, rank, world, dist=dist, pipeline_factory=lambda base: OracleEngine(base, int(q.bscansPerBuffer)))
         assert sp.initialize()
         sp.process_host(sp.local_slice(raw))
         sp.sync()
         lo, cnt = sp.start, sp.count
-        assert np.allclose(sp.pipe.out, ref[lo:lo + cnt], rtol=0, atol=2e-6), f"rank {rank}: shard differs from the un-sharded result"
+        assert np.allclose(sp.pipe.out, ref[lo:lo + cnt], rtol=0, atol=2e-5), f"rank {rank}: shard differs from the un-sharded result"
         h = q.samplesPerLine // 2
         extract = lambda f, nf, fn: torch.from_numpy(orc.enface_frame(sp.pipe.out, h, q.ascansPerBscan, cnt, f, nf, fn))  # noqa: E731
         full = sp.enface(17, 1, 0, extract)
-        assert np.allclose(full.numpy(), ref_enface, rtol=0, atol=2e-6), f"rank {rank}: en-face gather order"
+        assert np.allclose(full.numpy(), ref_enface, rtol=0, atol=2e-5), f"rank {rank}: en-face gather order"
         # 3-D volume view: u8 texture [depth][B-scan][A-scan] of the whole volume assembled from the per-rank slabs
         # (cuda_code.cu:928-940); voxel values encode their global coordinates so the order is checked exactly
         zz, yy, xx = np.meshgrid(np.arange(h), np.arange(q.bscansPerBuffer), np.arange(q.ascansPerBscan), indexing="ij")
@@ -102,6 +105,13 @@ def _worker(rank, world, port, raw, q, ref, ref_enface, errs):
         assert g["connected"] and g["global_lines"] == q.ascansPerBscan * q.bscansPerBuffer and g["line_offset"] == q.ascansPerBscan * lo
         sp.close_enface_peers()
         assert not g["connected"]
+        if raw2 is not None:
+            # a second, different buffer: with continuous determination the line must again come from the FIRST B-scans of the whole
+            # buffer (rank 0's shard), not from each rank's own shard
+            sp.process_host(sp.local_slice(raw2))
+            sp.sync()
+            # 5e-5: the broadcast line is fp32 (as in the product); a line re-determined from the rank's own shard is off by > 1e-2
+            assert np.allclose(sp.pipe.out, ref2[lo:lo + cnt], rtol=0, atol=5e-5), f"rank {rank}: second buffer differs from the un-sharded result"
         dist.barrier()
         dist.destroy_process_group()
     except Exception as e:  # noqa: BLE001
@@ -118,10 +128,14 @@ def test_two_ranks_match_unsharded(bscans):
     raw = synth.make_volume(n, a, bscans, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
     ref, _, _ = orc.process(q, raw)
     ref_enface = orc.enface_frame(ref, n // 2, a, bscans, 17, 1, 0)
+    _run_two_ranks((raw, q, ref, ref_enface))
+
+
+def _run_two_ranks(args):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     errs = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, raw, q, ref, ref_enface, errs)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port) + tuple(args[:4]) + (errs,) + tuple(args[4:])) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -130,3 +144,38 @@ def test_two_ranks_match_unsharded(bscans):
     while not errs.empty():
         msgs.append(errs.get())
     assert not msgs and all(p.exitcode == 0 for p in procs), msgs
+
+
+@pytest.mark.parametrize("mode", ["continuous", "redetermine"])
+def test_two_ranks_share_the_fpn_line_on_every_determination(mode):
+    """continuousFixedPatternNoiseDetermination / redetermineFixedPatternNoise: rank 0 determines from the first B-scans of the WHOLE
+    buffer and broadcasts; the other ranks must not re-determine the line from their own shard (cuda_code.cu:1520-1522)"""
+    n, a, bscans = 256, 18, 4
+    q = benchmark_params(n, a, bscans)
+    q.bscansForNoiseDetermination = 1
+    q.continuousFixedPatternNoiseDetermination = mode == "continuous"
+    q.update_all_curves()
+    raw = synth.make_volume(n, a, bscans, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
+    # a different buffer whose SECOND half (rank 1's shard) carries a fixed pattern of its own: a line determined from that shard would
+    # remove it, the line of the first B-scans of the buffer must not
+    raw2 = np.ascontiguousarray(raw[::-1]).astype(np.float64) / 2 + 100
+    raw2[bscans // 2:] += 300.0 * np.cos(2 * np.pi * 40 * np.arange(n) / n)
+    raw2 = np.clip(np.rint(raw2), 0, 4095).astype(raw.dtype)
+    ref, ml1, _ = orc.process(q, raw)
+    if mode == "continuous":
+        ref2, _, _ = orc.process(q, raw2)
+    else:
+        ref2, _, _ = orc.process(q, raw2, mean_line=ml1, determine_fpn=False)       # determined once: buffer 2 uses the line of buffer 1
+    ref_enface = orc.enface_frame(ref, n // 2, a, bscans, 17, 1, 0)
+    _run_two_ranks((raw, q, ref, ref_enface, raw2, ref2))
+
+
+def test_fpn_height_must_fit_rank0():
+    q = benchmark_params(256, 10, 4); q.bscansForNoiseDetermination = 3
+
+    class FakeDist:
+        pass
+    sp = ShardedPipeline(q, 0, 2, dist=FakeDist(), pipeline_factory=lambda base: OracleEngine(base, 4))
+    assert sp.initialize()
+    with pytest.raises(ValueError, match="exceeds rank 0"):
+        sp.process_host(np.zeros((2, 10, 256), np.uint16))

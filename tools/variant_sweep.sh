@@ -4,26 +4,24 @@
 # is faster must also be bit-identical).  Step 1 runs here (no GPU, ~3 min per variant), step 2 on the box:
 #   bash tools/variant_sweep.sh build
 #   gpurun --timeout 300 -- 'bash tools/variant_sweep.sh run'
-# Static instruction counts of the N = 1024 benchmark kernel (common part of the loop, default = 1085): x32 1022, tw4 1041,
-# tw4+x32 1001, i2f 1052.
+# Round-2 result (profiles/r02a_variant_sweep.txt): TW4 + x32 reads became the N = 1024 default (0.2114 -> 0.2042 ms), TW4 + the
+# no-shift conversion the N = 2048 default; what is listed below is each remaining switch on its own against the new default.
 set -e
 cd "$(dirname "$0")/.."
 declare -A V=(
-  [x32]="-DOCT_XCHG_X=32"
-  [x16]="-DOCT_XCHG_X=16"
-  [tw4]="-DOCT_TW4=1"
-  [tw4x32]="-DOCT_TW4=1 -DOCT_XCHG_X=32"
-  [tw4x32w20]="-DOCT_TW4=1 -DOCT_XCHG_X=32 -DOCT_R1_THREADS=640"
-  [i2f]="-DOCT_CVT_I2F=1"
-  [epipair]="-DOCT_EPI_PAIR=1"
-  [all]="-DOCT_TW4=1 -DOCT_XCHG_X=32 -DOCT_CVT_I2F=1 -DOCT_EPI_PAIR=1"
-  [r2noshift]="-DOCT_R2_NOSHIFT=1"
+  [r1old]="-DOCT_R1_TW4=0 -DOCT_R1_XCHG_X=8 -DOCT_R2_TW4=0 -DOCT_R2_NOSHIFT=0"
+  [r1i2f]="-DOCT_CVT_I2F=1"
+  [r1epi]="-DOCT_EPI_PAIR=1"
+  [r1w20]="-DOCT_R1_THREADS=640"
+  [r2x16]="-DOCT_R2_XCHG_X=16"
+  [r2tw2]="-DOCT_R2_TW4=0"
   [r2egvar]="-DOCT_R2_EGVAR=1"
 )
 case "$1" in
   build)
-    for t in "${!V[@]}"; do echo "== $t: ${V[$t]}"; make -s -C octproz_b200/csrc variant TAG=$t DEFS="${V[$t]}" 2>&1 | grep -v deprecated || true
-      grep -h "spill" octproz_b200/variants/obj_$t/k_fused_r1.ptxas.log | sort | uniq -c | head -3; done ;;
+    specs=(); for t in "${!V[@]}"; do specs+=("$t:${V[$t]}"); done
+    ONLY_OBJS="k_fused_r1 k_fused_r2 k_fused_r1_conv k_fused_r2_conv k_fused_p12 k_fused_p12_conv" tools/variant_build_parallel.sh "${specs[@]}"
+    rm -rf octproz_b200/variants/obj_* ;;
   run)
     python tools/micro_ab.py default 1024; python tools/micro_ab.py default 2048
     for t in "${!V[@]}"; do
