@@ -153,6 +153,11 @@ OCTB200_API int octb200_get_postprocess_background(octb200_pipeline* p, float* b
    broadcast rank 0's line; set marks the line as determined (cuda_code.cu:1523). */
 OCTB200_API int octb200_get_fpn_mean_line(octb200_pipeline* p, float* reIm, int n);
 OCTB200_API int octb200_set_fpn_mean_line(octb200_pipeline* p, const float* reIm, int n);
+/* diagnostics of the last determination (getMinimumVarianceMean, cuda_code.cu:523-565, keeps per bin the mean of the segment with the
+   smallest single-pass fp32 variance; at bins dominated by a constant term that minimum is decided by round-off): for the first
+   `bins` (<= samplesPerLine/2) depth bins the NINE candidate segments, stats[(s * bins + z) * 4 + {0,1,2,3}] = { mean.re, mean.im,
+   variance as computed (sumXX / L - |mean|^2 in fp32), mean power sumXX / L }; *segmentLength = L = height / 9.  Synchronises. */
+OCTB200_API int octb200_get_fpn_segment_stats(octb200_pipeline* p, float* stats, int bins, int* segmentLength);
 
 /* curve generators = OctAlgorithmParameters::update*Curve (octalgorithmparameters.cpp:141-249),
    Polynomial (polynomial.cpp:108-145), WindowFunction (windowfunction.cpp:121-253),

@@ -23,6 +23,7 @@
 
 #include <cuda_runtime_api.h>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #ifdef OCTB200_WITH_GL
 #include <cuda_gl_interop.h>
@@ -36,6 +37,39 @@ OctAlgorithmParameters* g_params = nullptr;
 bool g_initialized = false;
 #ifdef OCTB200_WITH_GL
 cudaGraphicsResource* g_glBscan = nullptr; cudaGraphicsResource* g_glEnFace = nullptr; cudaGraphicsResource* g_glVolume = nullptr;
+uint8_t* g_volStage = nullptr; size_t g_volStageBytes = 0;      /* linear u8 image of the GL_R8 3-D texture: [N/2][Btot][A] */
+
+/* updateVolumeDisplayBuffer (cuda_code.cu:1310-1355): the reference writes the voxels of the current buffer through a surface object,
+   one byte per thread; here octb200_volume_u8 writes the slab into a linear staging image with a tiled transpose and one
+   cudaMemcpy3DAsync moves that slab (x = all A-scans, y = the B-scans of this buffer, z = all depths) into the mapped array */
+void update_volume_view(const OctAlgorithmParameters* q, cudaStream_t st) {
+	if (!g_glVolume) return;
+	const size_t A = q->ascansPerBscan, B = q->bscansPerBuffer, Btot = B * q->buffersPerVolume, H = q->samplesPerLine / 2;
+	const size_t bytes = A * Btot * H;
+	if (g_volStageBytes != bytes) {
+		if (g_volStage) cudaFree(g_volStage);
+		g_volStage = nullptr; g_volStageBytes = 0;
+		if (cudaMalloc((void**)&g_volStage, bytes) != cudaSuccess) { printf("Cuda: volume view staging buffer allocation failed\n"); return; }
+		cudaMemsetAsync(g_volStage, 0, bytes, st);
+		g_volStageBytes = bytes;
+	}
+	const unsigned nr = octb200_current_buffer_nr(g_p);
+	if (octb200_volume_u8(g_p, nr, g_volStage) != OCTB200_OK) { printf("Cuda error: %s\n", octb200_last_error(g_p)); return; }
+	cudaArray_t arr = nullptr;
+	if (cudaGraphicsMapResources(1, &g_glVolume, st) != cudaSuccess) return;                     /* cuda_map3dTexture, cuda_code.cu:1669-1680 */
+	if (cudaGraphicsSubResourceGetMappedArray(&arr, g_glVolume, 0, 0) == cudaSuccess && arr) {
+		cudaMemcpy3DParms c;
+		std::memset(&c, 0, sizeof(c));
+		c.srcPtr = make_cudaPitchedPtr(g_volStage, A, A, Btot);
+		c.srcPos = make_cudaPos(0, nr * B, 0);
+		c.dstArray = arr;
+		c.dstPos = make_cudaPos(0, nr * B, 0);
+		c.extent = make_cudaExtent(A, B, H);
+		c.kind = cudaMemcpyDeviceToDevice;
+		if (cudaMemcpy3DAsync(&c, st) != cudaSuccess) printf("Cuda: volume view copy failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+	}
+	cudaGraphicsUnmapResources(1, &g_glVolume, st);
+}
 #endif
 
 void on_background(void* hostLine) {
@@ -135,7 +169,7 @@ extern "C" void octCudaPipeline(void* h_inputSignal) {
 	};
 	if (q->bscanViewEnabled) { if (float* d = mapped(g_glBscan)) { octb200_bscan_frame(g_p, q->frameNr, q->functionFramesBscan, q->displayFunctionBscan, d); cudaGraphicsUnmapResources(1, &g_glBscan, st); } }
 	if (q->enFaceViewEnabled) { if (float* d = mapped(g_glEnFace)) { octb200_enface_frame(g_p, q->frameNrEnFaceView, q->functionFramesEnFaceView, q->displayFunctionEnFaceView, d); cudaGraphicsUnmapResources(1, &g_glEnFace, st); } }
-	/* volume view: octb200_volume_u8 into a staging buffer + cudaMemcpy3DAsync into the mapped GL_R8 array */
+	if (q->volumeViewEnabled) update_volume_view(q, st);                                          /* cuda_code.cu:1579-1582 */
 #endif
 }
 
@@ -147,6 +181,9 @@ extern "C" void cleanupCuda() {
 	if (g_initialized) {                                                                          /* cuda_code.cu:1194-1212 */
 		octb200_destroy(g_p);
 		g_p = nullptr; g_initialized = false; d_processedBuffer = nullptr;
+#ifdef OCTB200_WITH_GL
+		if (g_volStage) { cudaFree(g_volStage); g_volStage = nullptr; g_volStageBytes = 0; }
+#endif
 	}
 }
 
@@ -202,4 +239,5 @@ extern "C" void changeDisplayedEnFaceFrame(unsigned int frameNr, unsigned int di
 
 /* harness hook (not part of kernels.h): FPN line of the adapter-owned pipeline */
 extern "C" int octb200_adapter_get_mean_line(float* reIm, int n) { return g_p ? octb200_get_fpn_mean_line(g_p, reIm, n) : -1; }
+extern "C" int octb200_adapter_get_fpn_segment_stats(float* stats, int bins, int* segmentLength) { return g_p ? octb200_get_fpn_segment_stats(g_p, stats, bins, segmentLength) : -1; }
 extern "C" int octb200_adapter_sync() { return g_p ? octb200_sync(g_p) : -1; }

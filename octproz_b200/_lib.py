@@ -17,7 +17,7 @@ SYMBOLS = [
     "octb200_create", "octb200_destroy", "octb200_last_error", "octb200_version", "octb200_default_params",
     "octb200_effective_fft_mode", "octb200_set_params", "octb200_set_resample_curve", "octb200_set_dispersion_curve",
     "octb200_set_window_curve", "octb200_set_postprocess_background", "octb200_get_postprocess_background",
-    "octb200_get_fpn_mean_line", "octb200_set_fpn_mean_line", "octb200_make_resample_curve",
+    "octb200_get_fpn_mean_line", "octb200_set_fpn_mean_line", "octb200_get_fpn_segment_stats", "octb200_make_resample_curve",
     "octb200_make_dispersion_curve", "octb200_make_window_curve", "octb200_make_sinusoidal_curve",
     "octb200_register_host_buffers", "octb200_unregister_host_buffers", "octb200_register_streaming_buffers",
     "octb200_unregister_streaming_buffers", "octb200_register_float_streaming_buffers",
@@ -99,6 +99,7 @@ def load() -> C.CDLL:
               "octb200_set_postprocess_background", "octb200_get_postprocess_background",
               "octb200_get_fpn_mean_line", "octb200_set_fpn_mean_line"):
         getattr(lib, n).argtypes = [P, C.c_void_p, C.c_int]
+    lib.octb200_get_fpn_segment_stats.argtypes = [P, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.octb200_make_resample_curve.argtypes = [C.c_int] + [C.c_float] * 4 + [C.c_void_p]
     lib.octb200_make_dispersion_curve.argtypes = [C.c_int] + [C.c_float] * 4 + [C.c_void_p]
     lib.octb200_make_window_curve.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]

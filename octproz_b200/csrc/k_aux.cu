@@ -227,7 +227,7 @@ cudaError_t launch_post(const PostArgs& a, int smCount, cudaStream_t st) {
 /* block = 32 bins x 9 segments.  Each thread sums its segment in line order (same order as cuda_code.cu:544-551),
  * then the 9 candidates of a bin are compared with the reference's strict '<' starting from FLT_MAX. */
 __global__ void __launch_bounds__(32 * 9) fpn_minvar_kernel(float2* __restrict__ meanLine, const float2* __restrict__ in,
-                                                             int bins, int stride, int segW) {
+                                                             int bins, int stride, int segW, float4* __restrict__ segStats) {
 	__shared__ float sVar[9][32];
 	__shared__ float2 sMean[9][32];
 	const int bx = threadIdx.x, s = threadIdx.y;
@@ -243,6 +243,8 @@ __global__ void __launch_bounds__(32 * 9) fpn_minvar_kernel(float2* __restrict__
 		}
 		mean.x = sx * factor; mean.y = sy * factor;
 		var = sxx * factor - (mean.x * mean.x + mean.y * mean.y);
+		/* diagnostics (octb200_get_fpn_segment_stats): the nine candidates of every bin, { mean, variance, mean power } */
+		if (segStats) segStats[(size_t)s * bins + bin] = make_float4(mean.x, mean.y, var, sxx * factor);
 	}
 	sVar[s][bx] = var; sMean[s][bx] = mean;
 	__syncthreads();
@@ -255,9 +257,9 @@ __global__ void __launch_bounds__(32 * 9) fpn_minvar_kernel(float2* __restrict__
 		meanLine[bin] = best;
 	}
 }
-cudaError_t launch_fpn_minvar(float2* meanLine, const float2* in, int bins, int stride, int height, cudaStream_t st) {
+cudaError_t launch_fpn_minvar(float2* meanLine, const float2* in, int bins, int stride, int height, float4* segStats, cudaStream_t st) {
 	const int segW = height / 9;   /* FIXED_PATTERN_NOISE_REMOVAL_SEGMENTS, octalgorithmparameters.h:35; integer division cuda_code.cu:531 */
-	fpn_minvar_kernel<<<(bins + 31) / 32, dim3(32, 9), 0, st>>>(meanLine, in, bins, stride, segW);
+	fpn_minvar_kernel<<<(bins + 31) / 32, dim3(32, 9), 0, st>>>(meanLine, in, bins, stride, segW, segStats);
 	return cudaGetLastError();
 }
 

@@ -65,7 +65,8 @@ cudaError_t launch_unpack12(uint16_t* out, const void* in, long long octets, int
 void launch_fill_phase(float2* ph, const float* phase, int n, cudaStream_t st);
 cudaError_t launch_pre(const PreArgs& a, int rawBytes, int sa, bool roll, int smCount, cudaStream_t st);
 cudaError_t launch_post(const PostArgs& a, int smCount, cudaStream_t st);
-cudaError_t launch_fpn_minvar(float2* meanLine, const float2* in, int bins, int stride, int height, cudaStream_t st);
+/* segStats: NULL or [9][bins] of { mean.x, mean.y, variance, mean power } -- every candidate segment of every bin */
+cudaError_t launch_fpn_minvar(float2* meanLine, const float2* in, int bins, int stride, int height, float4* segStats, cudaStream_t st);
 cudaError_t launch_sinusoidal(float* out, const float* in, const float* curve, int H, int A, long long samples,
                               int ppbgOn, const float* ppbg, float w, float o, unsigned short* conv, float convScale,
                               int smCount, cudaStream_t st);

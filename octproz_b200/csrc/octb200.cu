@@ -82,6 +82,7 @@ struct octb200_pipeline {
 	float2* dFft = nullptr;           /* S float2: SPLIT / CUFFT intermediate */
 	float2* dFpnScratch = nullptr; size_t fpnScratchElems = 0;
 	float2* dMeanLine = nullptr;
+	float4* dFpnStats = nullptr; int fpnStatsBins = 0, fpnStatsSegW = 0;    /* [9][N]: candidates of the last determination (diagnostics) */
 	float* dPpbg = nullptr;
 	float* dPhase = nullptr; float2* dPhasor = nullptr;
 	float4* dLutB = nullptr;       /* fused layout (de-interleaved by R) */
@@ -419,7 +420,8 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		if (g_cufft.ExecC2C(p->cufftPlan, p->dFft, p->dFft, kCufftInverse) != 0) return fail(p, OCTB200_ERR_CUDA, "cufftExecC2C failed");
 		p->launches++;
 		if (determine) {
-			CK(p, launch_fpn_minvar(p->dMeanLine, p->dFft, p->N, p->N, fpnHeight, p->sCompute)); p->launches++;
+			CK(p, launch_fpn_minvar(p->dMeanLine, p->dFft, p->N, p->N, fpnHeight, p->dFpnStats, p->sCompute)); p->launches++;
+			p->fpnStatsBins = p->N; p->fpnStatsSegW = fpnHeight / 9;
 			p->fpnDetermined = true; q.redetermineFixedPatternNoise = 0;
 		}
 		PostArgs po{};
@@ -435,7 +437,8 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 			FusedArgs fa = fused_args(p, st, dRaw, fpnHeight);
 			fa.cplxOut = p->dFpnScratch; fa.epi = epi_for(p, false, false);
 			CK(p, launch_fused(p->R, st.sa, st.roll, src, fa, p->smCount, p->sCompute)); p->launches++;
-			CK(p, launch_fpn_minvar(p->dMeanLine, p->dFpnScratch, p->H, p->H, fpnHeight, p->sCompute)); p->launches++;
+			CK(p, launch_fpn_minvar(p->dMeanLine, p->dFpnScratch, p->H, p->H, fpnHeight, p->dFpnStats, p->sCompute)); p->launches++;
+			p->fpnStatsBins = p->H; p->fpnStatsSegW = fpnHeight / 9;
 			p->fpnDetermined = true; q.redetermineFixedPatternNoise = 0;
 		}
 		if (src == SRC_CPLX) { PreArgs pa = pre_args(p, st, dRaw, p->lines); CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++; }
@@ -594,6 +597,7 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	}
 	RCC(dalloc(p, &p->dVolumeOwned, (size_t)(S / 2) * p->V)); p->dVolume = p->dVolumeOwned;
 	RCC(dalloc(p, &p->dMeanLine, (size_t)p->N));
+	RCC(dalloc(p, &p->dFpnStats, (size_t)9 * p->N));
 	RCC(dalloc(p, &p->dPpbg, (size_t)p->H));
 	RCC(dalloc(p, &p->dPhase, (size_t)p->N));
 	RCC(dalloc(p, &p->dPhasor, (size_t)p->N));
@@ -634,7 +638,7 @@ int octb200_destroy(octb200_pipeline* p) {
 	if (p->evComputeDone) cudaEventDestroy(p->evComputeDone);
 	if (p->evFloatCopied) cudaEventDestroy(p->evFloatCopied);
 	for (auto e : p->evConvFree) if (e) cudaEventDestroy(e);
-	dfree(p->dVolumeOwned); dfree(p->dTmp); dfree(p->dFft); dfree(p->dFpnScratch); dfree(p->dMeanLine); dfree(p->dPpbg);
+	dfree(p->dVolumeOwned); dfree(p->dTmp); dfree(p->dFft); dfree(p->dFpnScratch); dfree(p->dMeanLine); dfree(p->dFpnStats); dfree(p->dPpbg);
 	dfree(p->dPhase); dfree(p->dPhasor); dfree(p->dLutB); dfree(p->dLutB1);
 	dfree(p->dTw); dfree(p->dCtw); dfree(p->dSinCurve);
 	for (void*& c : p->dOutConv) { if (c) cudaFree(c); c = nullptr; }
@@ -694,6 +698,17 @@ int octb200_get_fpn_mean_line(octb200_pipeline* p, float* reIm, int n) {
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	CK(p, cudaStreamSynchronize(p->sCompute));
 	CK(p, cudaMemcpy(reIm, p->dMeanLine, sizeof(float2) * n, cudaMemcpyDeviceToHost));
+	return OCTB200_OK;
+}
+int octb200_get_fpn_segment_stats(octb200_pipeline* p, float* stats, int bins, int* segmentLength) {
+	if (!p || !stats || bins < 1 || bins > p->H) return fail(p, OCTB200_ERR_INVALID, "bad argument (bins must be 1 .. samplesPerLine/2)");
+	if (p->fpnStatsBins < 1) return fail(p, OCTB200_ERR_NOT_READY, "no fixed-pattern-noise determination has run on this handle yet");
+	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
+	CK(p, cudaStreamSynchronize(p->sCompute));
+	/* device layout [9][fpnStatsBins] (H bins on the own-FFT paths, N on the cuFFT path) -> caller's [9][bins] */
+	CK(p, cudaMemcpy2D(stats, (size_t)bins * sizeof(float4), p->dFpnStats, (size_t)p->fpnStatsBins * sizeof(float4), (size_t)bins * sizeof(float4), 9,
+	                   cudaMemcpyDeviceToHost));
+	if (segmentLength) *segmentLength = p->fpnStatsSegW;
 	return OCTB200_OK;
 }
 int octb200_set_fpn_mean_line(octb200_pipeline* p, const float* reIm, int n) {

@@ -244,6 +244,15 @@ class OctPipeline:
         self._ck(self._lib.octb200_get_fpn_mean_line(self._h, out.ctypes.data, n), "get_fpn_mean_line")
         return out
 
+    def fpn_segment_stats(self):
+        """the nine candidate segments of every depth bin at the last fixed-pattern-noise determination:
+        (stats [9][N/2][4] = mean.re, mean.im, fp32 variance, mean power; segment length L)"""
+        h = int(self.params.samplesPerLine) // 2
+        out = np.empty((9, h, 4), np.float32)
+        seg = C.c_int()
+        self._ck(self._lib.octb200_get_fpn_segment_stats(self._h, out.ctypes.data, h, C.byref(seg)), "get_fpn_segment_stats")
+        return out, int(seg.value)
+
     def set_fpn_mean_line(self, re_im: np.ndarray) -> None:
         a = np.ascontiguousarray(re_im, np.float32)
         self._ck(self._lib.octb200_set_fpn_mean_line(self._h, a.ctypes.data, a.shape[0]), "set_fpn_mean_line")

@@ -71,8 +71,31 @@ def main():
     out["fused_gather_max_abs_err_vs_oracle"] = e_auto
     sp.pipe.enface_gather_auto(False)
     dist.barrier()
-    # ---- timing of the two gathers (device events, max over ranks) ----
+    # ---- flow control: rank 0 runs ahead (its host enqueues 12 gathers of DIFFERENT depth frames back to back), the last rank dawdles
+    #      between its gathers; every frame every rank hands out must still be exactly the frame of that sequence number ----
     stream = torch.cuda.ExternalStream(int(sp.pipe._lib.octb200_compute_stream(sp.pipe.handle)), device=dev)
+    import time
+    frames = list(range(20, 32))
+    snaps = []
+    for f in frames:
+        ptr = sp.enface_p2p(f, 1, 0)
+
+        class _W3:  # noqa: N801
+            __cuda_array_interface__ = {"shape": (a * btot,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        with torch.cuda.stream(stream):                  # stream ordered behind the consumer kernel of this gather
+            snaps.append(torch.as_tensor(_W3(), device=dev).clone())
+        if rank == world - 1:
+            sp.sync(); time.sleep(0.02)
+    sp.sync(); torch.cuda.synchronize()
+    for f, snap in zip(frames, snaps):
+        want = orc.enface_frame(ref, n // 2, a, btot, f, 1, 0)
+        e = float(np.abs(snap.cpu().numpy() - want).max())
+        assert e < 1e-3, f"rank {rank}: frame {f} torn or stale under skew (max err {e})"
+    st = sp.pipe.enface_gather_status()
+    assert st["ack_timeouts"] == 0 and st["arrival_timeouts"] == 0, st
+    out["flow_control_frames_checked"] = len(frames)
+    dist.barrier()
+    # ---- timing of the two gathers (device events, max over ranks) ----
     loc = torch.empty(a * sp.count, dtype=torch.float32, device=dev)
     gathered = torch.empty(world * a * sp.count, dtype=torch.float32, device=dev)
     iters = 50
@@ -85,14 +108,10 @@ def main():
     for name, fn_ in (("nccl_us", t_nccl), ("p2p_us", t_p2p)):
         for _ in range(5):
             fn_()
-        if name == "p2p_us":
-            sp.pipe.enface_gather_wait()
         sp.sync(); dist.barrier(); torch.cuda.synchronize()
         sp.pipe.event_record(0)
         for _ in range(iters):
             fn_()
-        if name == "p2p_us":
-            sp.pipe.enface_gather_wait()
         sp.pipe.event_record(1)
         ms = sp.pipe.event_elapsed_ms(0, 1)
         t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
