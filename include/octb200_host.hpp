@@ -141,6 +141,29 @@ public:
 		const size_t offset = bytesOf((size_t)bscanOffset * params.samplesPerLine * params.ascansPerBscan);          /* :167 */
 		FILE* f = std::fopen(filePath.c_str(), "rb");
 		if (!f) { if (acquisitionStopped) acquisitionStopped(); return; }
+		if (buffersFromFile > 2) {
+			/* acqcuisitionSimulationLargeFile / acquisitionSimulationWithMultiFileBuffers (virtualoctsystem.cpp:107-113, 226-290): successive
+			 * buffers of the file are streamed into the two acquisition buffers in turn, rewinding after buffersFromFile buffers */
+			std::fseek(f, (long)offset, SEEK_SET);
+			int readBuffers = 0, nxt = 0;
+			acqusitionRunning.store(true);
+			buffer->currIndex.store(1);
+			if (acquisitionStarted) acquisitionStarted(this);
+			while (acqusitionRunning.load()) {
+				while (syncWithProcessing && buffer->ready(buffer->currIndex.load()) && acqusitionRunning.load()) std::this_thread::yield();
+				if (!buffer->ready(nxt)) {
+					const size_t got = std::fread(buffer->bufferArray[nxt], 1, nBytes, f); (void)got;
+					if (++readBuffers >= buffersFromFile) { std::fseek(f, (long)offset, SEEK_SET); readBuffers = 0; }
+					buffer->currIndex.store(nxt);
+					buffer->setReady(nxt, true); buffersDelivered.fetch_add(1);
+					nxt = (nxt + 1) % 2;
+				}
+				if (waitTimeUs > 0) std::this_thread::sleep_for(std::chrono::microseconds(waitTimeUs));
+			}
+			std::fclose(f);
+			if (acquisitionStopped) acquisitionStopped();
+			return;
+		}
 		auto readAt = [&](size_t off, void* dst) {
 			if (std::fseek(f, (long)off, SEEK_SET) == 0) { const size_t got = std::fread(dst, 1, nBytes, f); (void)got; }
 		};

@@ -110,6 +110,13 @@ class VirtualOCTSystem(AcquisitionSystem):
         p = self.params
         n_bytes = self._bytes(p.bscansPerBuffer * p.samplesPerLine * p.ascansPerBscan)
         offset = self._bytes(self.bscan_offset * p.samplesPerLine * p.ascansPerBscan)      # virtualoctsystem.cpp:167
+        if self.buffers_from_file > 2:
+            # acqcuisitionSimulationLargeFile / acquisitionSimulationWithMultiFileBuffers (virtualoctsystem.cpp:107-113, 226-290): successive
+            # buffers of the file are streamed into the two acquisition buffers in turn, rewinding after `buffers_from_file` buffers
+            self._stream_large_file(n_bytes, offset)
+            if self.on_acquisition_stopped:
+                self.on_acquisition_stopped()
+            return
         with open(self.file_path, "rb") as f:
             f.seek(offset)
             b0 = f.read(n_bytes)
@@ -134,6 +141,34 @@ class VirtualOCTSystem(AcquisitionSystem):
                 time.sleep(self.wait_time_us * 1e-6)
         if self.on_acquisition_stopped:
             self.on_acquisition_stopped()
+
+
+    def _stream_large_file(self, n_bytes: int, offset: int) -> None:
+        buf = self.buffer
+        with open(self.file_path, "rb") as f:
+            f.seek(offset)
+            read_buffers = 0
+            self.acqusitionRunning = True
+            buf.currIndex = 1
+            nxt = 0
+            if self.on_acquisition_started:
+                self.on_acquisition_started(self)
+            while self.acqusitionRunning:                                                    # virtualoctsystem.cpp:249-288
+                while self.sync_with_processing and buf.bufferReadyArray[buf.currIndex] and self.acqusitionRunning:
+                    time.sleep(0)
+                if not buf.bufferReadyArray[nxt]:
+                    data = f.read(n_bytes)
+                    buf.bufferArray[nxt][: len(data)] = np.frombuffer(data, np.uint8)
+                    read_buffers += 1
+                    if read_buffers >= self.buffers_from_file:                               # rewind (:268-272)
+                        f.seek(offset)
+                        read_buffers = 0
+                    buf.currIndex = nxt
+                    buf.bufferReadyArray[nxt] = True
+                    self.buffers_delivered += 1
+                    nxt = (buf.currIndex + 1) % 2
+                if self.wait_time_us > 0:
+                    time.sleep(self.wait_time_us * 1e-6)
 
 
 class Recorder:

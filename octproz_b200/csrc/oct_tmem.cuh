@@ -24,8 +24,10 @@ namespace octb200 {
 #ifndef OCT_R2_EGVAR
 #define OCT_R2_EGVAR 0
 #endif
+/* the final scale FMA of two outputs as one packed instruction (same FMA per half, bit-identical): 0.2042 -> 0.2038 ms (N = 1024),
+ * 0.5030 -> 0.4997 ms (N = 2048), profiles/r02b_variant_sweep.txt */
 #ifndef OCT_EPI_PAIR
-#define OCT_EPI_PAIR 0
+#define OCT_EPI_PAIR 1
 #endif
 /* Inter-pass twiddle layout and read width, per line-group size R (measured on one B200 box, tools/variant_sweep.sh,
  * profiles/r02a_variant_sweep.txt; every variant is bit-identical, same output hash):
@@ -36,7 +38,8 @@ namespace octb200 {
  *          still-live tuple out of the way: 66 MOV per line); 32 = two single-buffered x32 reads whose destination registers are the
  *          ones the stored values free up (MOV 74 -> 23 per line).
  *   N = 1024 (R = 1): TW4 + x32 0.2114 -> 0.2042 ms per 1024x512x256 volume (tw4 alone 0.2072, x32 alone 0.2094).
- *   N = 2048 (R = 2): x32 costs the two-warp kernel 1.5-4 % (0.504 -> 0.512-0.524 ms per 2048x1024x128 buffer); tw4 alone 0.4998. */
+ *   N = 2048 (R = 2): x32 costs the two-warp kernel 1.5-4 % (0.504 -> 0.512-0.524 ms per 2048x1024x128 buffer); tw4 alone 0.4998,
+ *                     tw4 + x16 0.4994 (profiles/r02b_variant_sweep.txt; without tw4 0.5127). */
 #ifndef OCT_R1_TW4
 #define OCT_R1_TW4 1
 #endif
@@ -47,7 +50,7 @@ namespace octb200 {
 #define OCT_R1_XCHG_X 32
 #endif
 #ifndef OCT_R2_XCHG_X
-#define OCT_R2_XCHG_X 8
+#define OCT_R2_XCHG_X 16
 #endif
 template <int R> struct XchgCfg {
 	static constexpr bool TW4 = (R == 1) ? (OCT_R1_TW4 != 0) : (OCT_R2_TW4 != 0);

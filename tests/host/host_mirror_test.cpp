@@ -85,6 +85,19 @@ int main(int argc, char** argv) {
 		for (size_t i = 0; i < fp.calls.size(); ++i) CHECK(fp.firstSample[i] == (unsigned short)(2000u & 0xFFFu));
 	}
 
+	/* buffersFromFile > 2 streams the file buffer by buffer and rewinds after buffersFromFile buffers (virtualoctsystem.cpp:226-290) */
+	{
+		VirtualOCTSystem vos(path, 12, n, a, b, 1);
+		vos.buffersFromFile = 3;
+		FakePipeline fp;
+		OctAlgorithmParameters q;
+		bool ok = false;
+		replay(vos, fp, q, 8, &ok);
+		CHECK(ok && fp.calls.size() == 8);
+		for (size_t i = 0; i < fp.calls.size(); ++i) CHECK(fp.firstSample[i] == (unsigned short)((1000u * (unsigned)(i % 3 + 1)) & 0xFFFu));
+		for (size_t i = 1; i < fp.calls.size(); ++i) CHECK(fp.calls[i] != fp.calls[i - 1]);
+	}
+
 	/* failed initialisation stops the acquisition and releases the flags (processing.cpp:151-160) */
 	{
 		VirtualOCTSystem vos(path, 12, n, a, b, 1);

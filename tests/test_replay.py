@@ -66,6 +66,23 @@ def test_replay_alternates_the_two_buffers(tmp_path, buffers_from_file):
     assert fake.init_args[0].ctypes.data in ptrs and fake.init_args[1].ctypes.data in ptrs
 
 
+def test_replay_streams_a_large_file_buffer_by_buffer(tmp_path):
+    """buffers_from_file > 2 (acqcuisitionSimulationLargeFile, virtualoctsystem.cpp:226-290): successive buffers of the file, starting
+    at bscan_offset, rewinding after buffers_from_file buffers"""
+    n, a, b = 64, 4, 2
+    vol = synth.make_volume(n, a, 6 * b, 12)
+    p = str(tmp_path / "big.raw")
+    write_raw_file(p, vol)
+    q = benchmark_params(n, a, b)
+    fake = FakePipeline()
+    proc = replay(p, q, fake, buffers=9, buffers_from_file=4, bscan_offset=b)
+    assert proc.processed_buffers == 9
+    want = [bytes(vol[b * (1 + i % 4): b * (2 + i % 4)].reshape(-1)[:4].tobytes()) for i in range(9)]
+    assert [s[1] for s in fake.seen] == want
+    ptrs = [s[0] for s in fake.seen]
+    assert len(set(ptrs)) == 2 and all(ptrs[i] != ptrs[i + 1] for i in range(8))
+
+
 def test_failed_initialisation_stops_the_acquisition(tmp_path):
     vol = synth.make_volume(64, 4, 2, 12)
     p = str(tmp_path / "v.raw"); write_raw_file(p, vol)
