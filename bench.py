@@ -42,6 +42,8 @@ WORKLOADS = {
     # name: (samplesPerLine, ascansPerBscan, bscansPerBuffer, bitDepth)
     "1024x512x256-12bit": (1024, 512, 256, 12),
     "2048x1024x128-16bit": (2048, 1024, 128, 16),
+    # the reference's DEFAULT line length (octproz/default/settings.ini:62) at the BASELINE volume shape: FUSED = the shared-memory kernel
+    "1664x512x256-12bit": (1664, 512, 256, 12),
     # BASELINE.json configs[3]: "2048-sample A-scan x 1024 x 512 16-bit, full pipeline incl. FPN + sinusoidal correction" (2 GiB raw per buffer)
     "2048x1024x512-16bit-config4": (2048, 1024, 512, 16),
 }
@@ -427,7 +429,7 @@ def secondary_resident(name, mode_name, local, steps):
         peak, _ = hbm_peak()
         out = {"workload": name, "mode": mode_name, "value": a * b / (ms * 1e3), "unit": UNIT, "ms_per_step": ms, "steps": k,
                "gpu_launches_per_step": launches / k,
-               "dominant_kernel": {"name": {"fused": "oct_fused_kernel", "split": "oct_fused_kernel<SRC_CPLX>", "cufft": "oct_pre_kernel"}[mode_name],
+               "dominant_kernel": {"name": {"fused": "oct_fused_kernel" if n in (1024, 2048) else "oct_generic_kernel", "split": "oct_fused_kernel<SRC_CPLX>", "cufft": "oct_pre_kernel"}[mode_name],
                                    "kernel_ms": kern_ms, "algorithmic_bytes_per_sample": per_sample,
                                    "frac_of_hbm_peak": a * b * n * per_sample / (kern_ms * 1e-3) / 1e9 / peak}}
         rig.close()
@@ -626,6 +628,8 @@ def main():
                 secondary.append(secondary_resident(DEFAULT_WORKLOAD, "cufft", local, args.steps))     # BASELINE configs[1]
                 secondary.append(secondary_resident(DEFAULT_WORKLOAD, "split", local, args.steps))     # BASELINE configs[2]
                 secondary.append(secondary_resident("2048x1024x512-16bit-config4", "fused", local, min(args.steps, 20)))   # BASELINE configs[3]
+                secondary.append(secondary_resident("1664x512x256-12bit", "fused", local, args.steps))      # the reference's default line length:
+                secondary.append(secondary_resident("1664x512x256-12bit", "cufft", local, args.steps))      # own shared-memory FFT vs the cuFFT chain
             ref_cuda = ref_cuda_leg(args.workload, args.steps)
 
     if dist is not None:

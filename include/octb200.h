@@ -68,10 +68,14 @@ enum { OCTB200_FLAG_SEPARATE_CONVERSION = 1 };
 
 /* which kernels run the FFT stage */
 enum {
-	OCTB200_FFT_AUTO = 0,        /* FUSED when samplesPerLine is 1024 or 2048 and the container is u16, else best available */
-	OCTB200_FFT_FUSED = 1,       /* one kernel: raw -> resample/window/phasor -> FFT -> FPN/log -> B-scan (4 B/sample) */
-	OCTB200_FFT_SPLIT = 2,       /* fused pre-FFT kernel -> float2 in HBM -> own FFT with fused epilogue (20 B/sample) */
-	OCTB200_FFT_CUFFT = 3        /* fused pre-FFT kernel -> cufftExecC2C -> fused post kernel (32 B/sample); any N */
+	OCTB200_FFT_AUTO = 0,        /* FUSED wherever one of the fused kernels takes the geometry, else CUFFT */
+	OCTB200_FFT_FUSED = 1,       /* ONE kernel: raw -> resample/window/phasor -> FFT -> FPN/log -> B-scan (container bytes in + 2 B out per
+	                                sample).  samplesPerLine 1024 / 2048 in a u16 container: the transform runs in registers (k_fused.cuh);
+	                                any other even samplesPerLine <= 8192 whose prime factors are <= 13 (e.g. the reference's default
+	                                1664 = 2^7 * 13, 512, 1536, 4096) and u8 / u32 containers: in shared memory (k_generic.cu) */
+	OCTB200_FFT_SPLIT = 2,       /* fused pre-FFT kernel -> float2 in HBM -> own FFT with fused epilogue (20 B/sample); 1024 / 2048 only */
+	OCTB200_FFT_CUFFT = 3        /* fused pre-FFT kernel -> cufftExecC2C -> fused post kernel (32 B/sample); any N: the measured library
+	                                baseline and the path for line lengths with larger prime factors */
 };
 
 /* AcquisitionParams (octproz_devkit/src/acquisitionparameter.h:31-37) + device placement */

@@ -234,17 +234,21 @@ __global__ void __launch_bounds__(32 * 9) fpn_minvar_kernel(float2* __restrict__
 	const int bin = blockIdx.x * 32 + bx;
 	float var = 0.f; float2 mean = make_float2(0.f, 0.f);
 	if (bin < bins && segW > 0) {
-		const float factor = 1.0f / (float)segW;
+		/* every operation spelled out in the form nvcc --use_fast_math gives the reference's kernel (SASS of oracle/_ref/libref_cuda.so:
+		 * FMUL dy dy -> FFMA dx dx -> FADD into sumXX; factor by MUFU.RCP; variance = FFMA(factor, sumXX, -FFMA(mx, mx, FMUL(my, my)))), so
+		 * that the compiler's choice of contractions in THIS translation unit cannot move the ill-conditioned argmin */
+		const float factor = __fdividef(1.0f, (float)segW);
 		float sx = 0.f, sy = 0.f, sxx = 0.f;
 		const float2* ptr = in + (size_t)s * segW * stride + bin;
 		for (int j = 0; j < segW; ++j) {
 			const float2 v = ptr[(size_t)j * stride];
-			sx += v.x; sy += v.y; sxx += v.x * v.x + v.y * v.y;
+			sx = __fadd_rn(sx, v.x); sy = __fadd_rn(sy, v.y);
+			sxx = __fadd_rn(sxx, __fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y)));
 		}
-		mean.x = sx * factor; mean.y = sy * factor;
-		var = sxx * factor - (mean.x * mean.x + mean.y * mean.y);
+		mean.x = __fmul_rn(sx, factor); mean.y = __fmul_rn(sy, factor);
+		var = __fmaf_rn(factor, sxx, -__fmaf_rn(mean.x, mean.x, __fmul_rn(mean.y, mean.y)));
 		/* diagnostics (octb200_get_fpn_segment_stats): the nine candidates of every bin, { mean, variance, mean power } */
-		if (segStats) segStats[(size_t)s * bins + bin] = make_float4(mean.x, mean.y, var, sxx * factor);
+		if (segStats) segStats[(size_t)s * bins + bin] = make_float4(mean.x, mean.y, var, __fmul_rn(sxx, factor));
 	}
 	sVar[s][bx] = var; sMean[s][bx] = mean;
 	__syncthreads();

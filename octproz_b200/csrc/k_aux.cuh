@@ -20,6 +20,30 @@ struct PreArgs {
 	int useBulk;            /* 1: cp.async.bulk staging (16-byte aligned geometry), 0: plain loads */
 };
 
+/* generic fused kernel (k_generic.cu): any even N <= 8192 with prime factors in {2, 3, 5, 7, 11, 13}, u8 / u16 / u32 containers; the
+ * transform runs as Stockham passes between two shared-memory line buffers */
+struct GenericArgs {
+	const void* raw;
+	float* out;              /* [lines][N/2] processed output slab (flip folded into the line address) */
+	float2* cplxOut;         /* != NULL: write the pre-FPN complex bins [lines][N/2] instead (FPN determination pass) */
+	const float4* lutB;      /* N entries, natural order: { byte offset of tap n1, w cos, w sin, t } */
+	const float2* twN;       /* exp(+2 pi i t / N), t < N */
+	const float2* meanLine;  /* N/2 */
+	const float* ppbg;       /* N/2 */
+	EpiConsts epi;
+	long long totalSamples;
+	int lines, N, A;
+	int flip;
+	unsigned bscanBase, flipEnd;
+	int shiftBits, W, HB, HA;
+	int useBulk;             /* 1: cp.async.bulk staging (16-byte aligned geometry), 0: plain loads */
+	int nPass;
+	int radix[16];
+};
+bool generic_fft_plan(int N, int* radix, int* nPass);
+bool generic_fits(int N, int rawBytes, int HB, int HA, bool roll);
+cudaError_t launch_generic(const GenericArgs& a, int rawBytes, int sa, bool roll, int smCount, cudaStream_t st);
+
 /* post kernel after cuFFT: complex [lines][N] -> float [lines][N/2] */
 struct PostArgs {
 	const float2* in;

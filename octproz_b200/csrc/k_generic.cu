@@ -1,0 +1,303 @@
+/*
+ * k_generic.cu -- the fused raw -> B-scan kernel for every line length and container the register kernel (k_fused.cuh) does not take:
+ * any even N <= 8192 whose prime factors are in {2, 3, 5, 7, 11, 13} (the reference's default acquisition geometry is N = 1664 =
+ * 2^7 * 13, octproz/default/settings.ini:62) and u8 / u16 / u32 containers.  Same stages, same per-sample arithmetic:
+ *
+ *   raw line --cp.async.bulk (TMA 1-D) + mbarrier--> shared memory                                   (one CTA works on one line at a time)
+ *     -> container -> fp32 [+ rolling-mean background removal]                                        (cuda_code.cu:109-211)
+ *     -> resampling x window x dispersion phasor from the natural-order stage LUT                     (cuda_code.cu:213-489)
+ *     -> inverse FFT: Stockham autosort passes between two shared-memory line buffers, mixed radix
+ *        (radix 4 / 2 butterflies, odd primes by the symmetric O(P^2/2) form), twiddles w_N^t from a table   (cuda_code.cu:1514-1515)
+ *     -> FPN subtract, |.|^2, log / linear scale, truncate to N/2, flip in the store address, background  (cuda_code.cu:567-807)
+ *     -> coalesced fp32 stores.  HBM traffic: the container bytes in + 2 B out per raw sample; nothing in between.
+ *
+ * The transform lives in shared memory instead of registers: ~3x the shared-memory traffic and more instructions per sample than the
+ * N = 1024 / 2048 register kernels, but one launch and 4 B/sample of HBM traffic instead of the 32 B/sample of the
+ * pre-kernel + cuFFT + post-kernel chain, which remains the path for line lengths with larger prime factors.
+ */
+#include "k_aux.cuh"
+
+namespace octb200 {
+
+template <int P> struct DftTab;
+#include "k_generic_tables.inc"
+
+template <typename RawT>
+__device__ __forceinline__ float generic_convert(RawT v, int shiftBits) {
+	if constexpr (sizeof(RawT) == 4) {
+		if (shiftBits) return (float)((double)v / 4294967296.0);   /* cuda_code.cu:144 */
+		return __uint2float_rd(v);                                  /* cuda_code.cu:124 */
+	} else {
+		return __uint2float_rd((unsigned)v >> shiftBits);           /* cuda_code.cu:118-121,138-141 */
+	}
+}
+
+/* ---- butterflies: inverse DFT of R register values, X_j = sum_k x_k exp(+2 pi i j k / R) ---- */
+template <int R>
+__device__ __forceinline__ void dft_inv(float2 (&v)[R]) {
+	if constexpr (R == 2) {
+		const float2 a = v[0], b = v[1];
+		v[0] = cadd(a, b); v[1] = csub(a, b);
+	} else if constexpr (R == 4) {
+		const float2 s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]);
+		const float2 s13 = cadd(v[1], v[3]), d13 = cmul_i(csub(v[1], v[3]));        /* +i (v1 - v3) */
+		v[0] = cadd(s02, s13); v[2] = csub(s02, s13);
+		v[1] = cadd(d02, d13); v[3] = csub(d02, d13);
+	} else {
+		/* odd prime: pair k with R - k.  a_k = x_k + x_{R-k}, b_k = x_k - x_{R-k};
+		 * X_j = x_0 + sum a_k cos(2 pi j k / R) + i sum b_k sin(2 pi j k / R), X_{R-j} the same with - i */
+		constexpr int H = (R - 1) / 2;
+		float2 a[H], b[H];
+		static_for<0, H>([&](auto kc) {
+			constexpr int k = decltype(kc)::value + 1;
+			a[k - 1] = cadd(v[k], v[R - k]);
+			b[k - 1] = csub(v[k], v[R - k]);
+		});
+		const float2 x0 = v[0];
+		float2 sum = x0;
+		static_for<0, H>([&](auto kc) { sum = cadd(sum, a[decltype(kc)::value]); });
+		v[0] = sum;
+		static_for<0, H>([&](auto jc) {
+			constexpr int j = decltype(jc)::value + 1;
+			float2 C = x0, S = make_float2(0.f, 0.f);
+			static_for<0, H>([&](auto kc) {
+				constexpr int k = decltype(kc)::value + 1;
+				constexpr float c = DftTab<R>::c[(j * k) % R], s = DftTab<R>::s[(j * k) % R];
+				C = pfma(a[k - 1], make_float2(c, c), C);
+				S = pfma(b[k - 1], make_float2(s, s), S);
+			});
+			const float2 iS = cmul_i(S);
+			v[j] = cadd(C, iS);
+			v[R - j] = csub(C, iS);
+		});
+	}
+}
+
+/* one Stockham autosort pass of radix R over a line of N complex values in shared memory (Ns = product of the earlier radices):
+ * butterfly j reads in[j + i N/R], multiplies by w_{Ns R}^{i (j mod Ns)} = twN[i (j mod Ns) N / (Ns R)], transforms, and writes
+ * out[(j - j mod Ns) R + j mod Ns + i Ns] */
+template <int R>
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out, int N, int Ns, const float2* __restrict__ twN,
+                                              int tid, int T) {
+	const int M = N / R;
+	const int tmul = N / (Ns * R);
+	for (int j = tid; j < M; j += T) {
+		float2 v[R];
+#pragma unroll
+		for (int i = 0; i < R; ++i) v[i] = in[j + i * M];
+		const int k = j % Ns;
+		if (Ns > 1) {
+			const int t = k * tmul;
+#pragma unroll
+			for (int i = 1; i < R; ++i) v[i] = cmul(v[i], __ldg(twN + i * t));
+		}
+		dft_inv<R>(v);
+		const int j0 = (j - k) * R + k;
+#pragma unroll
+		for (int i = 0; i < R; ++i) out[j0 + i * Ns] = v[i];
+	}
+}
+
+__host__ __device__ inline int generic_smem_bytes(int N, int SE, int rawBytes, bool roll) {
+	/* [buffer A: N float2][buffer B: N float2, aliased by the fp32 slot (+ rolling prefix sums)][raw slot][mbarrier] */
+	int bBytes = N * 8;
+	const int slotBytes = align_up((FSLOT_PAD + SE) * 4, 16) + (roll ? align_up((SE + 1) * 8, 16) : 0);
+	if (slotBytes > bBytes) bBytes = slotBytes;
+	return N * 8 + align_up(bBytes, 128) + align_up(SE * rawBytes, 128) + 128;
+}
+
+template <typename RawT, int SA, bool ROLL>
+__global__ void __launch_bounds__(256) oct_generic_kernel(const GenericArgs a) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	constexpr int RB = sizeof(RawT);
+	const int N = a.N, H = N / 2, SE = a.HB + N + a.HA;
+	const int tid = threadIdx.x, T = blockDim.x;
+	float2* bufA = reinterpret_cast<float2*>(smem);
+	int bBytes = N * 8;
+	{
+		const int slotBytes = align_up((FSLOT_PAD + SE) * 4, 16) + (ROLL ? align_up((SE + 1) * 8, 16) : 0);
+		if (slotBytes > bBytes) bBytes = slotBytes;
+	}
+	float2* bufB = reinterpret_cast<float2*>(smem + N * 8);
+	float* fslot = reinterpret_cast<float*>(bufB) + FSLOT_PAD;
+	unsigned long long* prefix = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bufB) + align_up((FSLOT_PAD + SE) * 4, 16));
+	RawT* rslot = reinterpret_cast<RawT*>(smem + N * 8 + align_up(bBytes, 128));
+	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + N * 8 + align_up(bBytes, 128) + align_up(SE * RB, 128));
+	const RawT* raw = reinterpret_cast<const RawT*>(a.raw);
+
+	auto issue = [&](int gline) {            /* thread 0 (bulk) or all threads (plain loads) */
+		const long long lo = (long long)gline * N - a.HB, hi = (long long)gline * N + N + a.HA;
+		const long long clo = lo < 0 ? 0 : lo, chi = hi > a.totalSamples ? a.totalSamples : hi;
+		if (a.useBulk) {
+			if (tid == 0) {
+				for (long long q = 0; q < clo - lo; ++q) rslot[q] = 0;
+				for (long long q = chi - lo; q < hi - lo; ++q) rslot[q] = 0;
+				const uint32_t bytes = (uint32_t)((chi - clo) * RB);
+				mbar_arrive_expect_tx(bar, bytes);
+				bulk_g2s(rslot + (clo - lo), raw + clo, bytes, bar);
+			}
+		} else {
+			for (long long q = lo + tid; q < hi; q += T) rslot[q - lo] = (q >= 0 && q < a.totalSamples) ? raw[q] : (RawT)0;
+		}
+	};
+
+	if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+	__syncthreads();
+	if ((int)blockIdx.x < a.lines) issue(blockIdx.x);
+
+	int it = 0;
+	for (int gline = blockIdx.x; gline < a.lines; gline += gridDim.x, ++it) {
+		if (a.useBulk) mbar_wait(bar, (uint32_t)(it & 1));
+		else __syncthreads();
+
+		/* ---- container -> fp32 (cuda_code.cu:109-147), rolling-mean background (cuda_code.cu:165-211: exact integer prefix sums) ---- */
+		if constexpr (ROLL) {
+			if (tid < 32) {
+				unsigned long long carry = 0;
+				if (tid == 0) prefix[0] = 0;
+				for (int c = 0; c < SE; c += 32) {
+					const int q = c + tid;
+					unsigned long long x = 0;
+					if (q < SE) x = (sizeof(RawT) == 4) ? (unsigned long long)rslot[q] : (unsigned long long)((unsigned)rslot[q] >> a.shiftBits);
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d); if (tid >= d) x += y; }
+					if (q < SE) prefix[q + 1] = carry + x;
+					carry += __shfl_sync(0xffffffffu, x, 31);
+				}
+			}
+		}
+		for (int q = tid; q < SE; q += T) fslot[q] = generic_convert<RawT>(rslot[q], a.shiftBits);
+		__syncthreads();
+		/* raw slot consumed: start the load of this CTA's next line */
+		if (gline + (int)gridDim.x < a.lines) issue(gline + gridDim.x);
+		if constexpr (ROLL) {
+			const int W = a.W;
+			for (int q = tid; q < SE; q += T) {
+				int lo, hi;
+				if (q < a.HB) { lo = 0; hi = a.HB - 1; }
+				else if (q >= a.HB + N) { lo = a.HB + N; hi = SE - 1; }
+				else { lo = a.HB; hi = a.HB + N - 1; }
+				const int ss = max(lo, q - W + 1), e = min(hi, q + W);
+				const unsigned long long d = prefix[e + 1] - prefix[ss];
+				float sum;
+				if (sizeof(RawT) == 4 && a.shiftBits) sum = (float)((double)d / 4294967296.0);
+				else sum = (float)d;
+				fslot[q] -= __fdividef(sum, (float)(e - ss + 1));
+			}
+			__syncthreads();
+		}
+		if constexpr (SA == SA_CUBIC) {
+			if (tid == 0) fslot[a.HB - 1] = fslot[a.HB + 1];      /* mirrored first tap of the cubic (cuda_code.cu:284) */
+			__syncthreads();
+		}
+
+		/* ---- stage A: resampling x window x phasor -> complex FFT input in buffer A ---- */
+		{
+			const float* f = fslot + a.HB;
+			const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
+			for (int m = tid; m < N; m += T) {
+				const float4 B = __ldg(a.lutB + m);
+				float2 val;
+				if constexpr (SA == SA_CUBIC) val = sample_cubic(f, B);
+				else if constexpr (SA == SA_LINEAR) val = sample_linear(f, B);
+				else if constexpr (SA == SA_NONE) val = sample_none(f, m, B);
+				else val = sample_lanczos(f, shift, B);
+				bufA[m] = val;
+			}
+		}
+		__syncthreads();
+
+		/* ---- inverse FFT: Stockham passes A -> B -> A ... ---- */
+		const float2* in = bufA; float2* out = bufB;
+		int Ns = 1;
+		for (int ps = 0; ps < a.nPass; ++ps) {
+			const int R = a.radix[ps];
+			switch (R) {
+			case 2: stockham_pass<2>(in, out, N, Ns, a.twN, tid, T); break;
+			case 3: stockham_pass<3>(in, out, N, Ns, a.twN, tid, T); break;
+			case 4: stockham_pass<4>(in, out, N, Ns, a.twN, tid, T); break;
+			case 5: stockham_pass<5>(in, out, N, Ns, a.twN, tid, T); break;
+			case 7: stockham_pass<7>(in, out, N, Ns, a.twN, tid, T); break;
+			case 11: stockham_pass<11>(in, out, N, Ns, a.twN, tid, T); break;
+			default: stockham_pass<13>(in, out, N, Ns, a.twN, tid, T); break;
+			}
+			Ns *= R;
+			__syncthreads();
+			const float2* t = in; in = out; out = const_cast<float2*>(t);
+		}
+
+		/* ---- epilogue (bins z < N/2), from `in` = the buffer the last pass wrote ---- */
+		if (a.cplxOut != nullptr) {
+			float2* o = a.cplxOut + (size_t)gline * H;
+			for (int z = tid; z < H; z += T) o[z] = in[z];
+		} else {
+			int b = gline / a.A, al = gline - b * a.A;
+			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u && (unsigned)b + a.bscanBase < a.flipEnd) al = a.A - 1 - al;
+			float* o = a.out + ((size_t)b * a.A + al) * H;
+			const EpiConsts e = a.epi;
+			for (int z = tid; z < H; z += T) {
+				float2 d = in[z];
+				if (e.fpn) d = csub(d, __ldg(a.meanLine + z));
+				const float pw = fmaf(d.x, d.x, d.y * d.y);
+				float v = e.logMode ? fmaf(oct_lg2(pw), e.scaleA, e.scaleB) : fmaf(oct_sqrt(pw), e.scaleA, e.scaleB);
+				if (e.ppbg) v = saturate01(v - fmaf(e.ppbgWeight, __ldg(a.ppbg + z), e.ppbgOffset));
+				o[z] = v;
+			}
+		}
+		__syncthreads();          /* both line buffers are free again before the next line's conversion writes into B */
+	}
+}
+
+/* radix plan: odd primes first (their odd output stride keeps the first pass's stores off the same banks), then 4s, then at most one 2 */
+bool generic_fft_plan(int N, int* radix, int* nPass) {
+	if (N < 8 || (N & 1) || N > 8192) return false;
+	int n = N, cnt = 0;
+	const int odd[] = { 13, 11, 7, 5, 3 };
+	for (int p : odd) while (n % p == 0) { if (cnt >= 16) return false; radix[cnt++] = p; n /= p; }
+	while (n % 4 == 0) { if (cnt >= 16) return false; radix[cnt++] = 4; n /= 4; }
+	if (n % 2 == 0) { if (cnt >= 16) return false; radix[cnt++] = 2; n /= 2; }
+	if (n != 1) return false;
+	*nPass = cnt;
+	return true;
+}
+
+template <typename RawT, int SA, bool ROLL>
+static cudaError_t launch_generic_t(const GenericArgs& a, int smCount, cudaStream_t st) {
+	const int SE = a.HB + a.N + a.HA;
+	const int smem = generic_smem_bytes(a.N, SE, (int)sizeof(RawT), ROLL);
+	if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+	auto k = oct_generic_kernel<RawT, SA, ROLL>;
+	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	if (e != cudaSuccess) return e;
+	const int threads = a.N >= 2048 ? 256 : 128;
+	int ctasPerSm = (227 * 1024) / (smem + 1024);
+	const int maxByThreads = 2048 / threads;
+	if (ctasPerSm > maxByThreads) ctasPerSm = maxByThreads;
+	if (ctasPerSm > 8) ctasPerSm = 8;
+	if (ctasPerSm < 1) ctasPerSm = 1;
+	int grid = smCount * ctasPerSm;
+	if (grid > a.lines) grid = a.lines;
+	if (grid < 1) grid = 1;
+	k<<<grid, threads, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+template <typename RawT>
+static cudaError_t launch_generic_raw(const GenericArgs& a, int sa, bool roll, int smCount, cudaStream_t st) {
+	if (sa == SA_CUBIC) return roll ? launch_generic_t<RawT, SA_CUBIC, true>(a, smCount, st) : launch_generic_t<RawT, SA_CUBIC, false>(a, smCount, st);
+	if (sa == SA_LINEAR) return roll ? launch_generic_t<RawT, SA_LINEAR, true>(a, smCount, st) : launch_generic_t<RawT, SA_LINEAR, false>(a, smCount, st);
+	if (sa == SA_NONE) return roll ? launch_generic_t<RawT, SA_NONE, true>(a, smCount, st) : launch_generic_t<RawT, SA_NONE, false>(a, smCount, st);
+	return roll ? launch_generic_t<RawT, SA_LANCZOS, true>(a, smCount, st) : launch_generic_t<RawT, SA_LANCZOS, false>(a, smCount, st);
+}
+
+cudaError_t launch_generic(const GenericArgs& a, int rawBytes, int sa, bool roll, int smCount, cudaStream_t st) {
+	if (rawBytes == 1) return launch_generic_raw<uint8_t>(a, sa, roll, smCount, st);
+	if (rawBytes == 2) return launch_generic_raw<uint16_t>(a, sa, roll, smCount, st);
+	return launch_generic_raw<uint32_t>(a, sa, roll, smCount, st);
+}
+
+bool generic_fits(int N, int rawBytes, int HB, int HA, bool roll) {
+	return generic_smem_bytes(N, HB + N + HA, rawBytes, roll) <= 227 * 1024;
+}
+
+}  // namespace octb200

@@ -88,6 +88,10 @@ struct octb200_pipeline {
 	float4* dLutB = nullptr;       /* fused layout (de-interleaved by R) */
 	float4* dLutB1 = nullptr;      /* natural order for the generic pre kernel */
 	float2 *dTw = nullptr, *dCtw = nullptr;
+	bool regKernel = false;           /* N in {1024, 2048} in a u16 container: the register kernels (k_fused.cuh) take the FUSED mode */
+	bool genericOk = false;           /* the shared-memory kernel (k_generic.cu) can transform this line length */
+	float2* dTwN = nullptr;           /* exp(+2 pi i t / N), t < N, for the generic kernel's passes */
+	int genRadix[16] = {}; int genPasses = 0;
 	float* dSinCurve = nullptr;
 	void* dOutConv[2] = { nullptr, nullptr };
 	int cufftPlan = -1;
@@ -291,6 +295,20 @@ PreArgs pre_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, i
 	return a;
 }
 
+GenericArgs generic_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, int lines) {
+	GenericArgs a{};
+	a.raw = dRaw; a.lutB = p->dLutB1; a.twN = p->dTwN;
+	a.meanLine = p->dMeanLine; a.ppbg = p->dPpbg;
+	a.totalSamples = p->S; a.lines = lines; a.N = p->N; a.A = p->A;
+	a.flip = p->prm.bscanFlip; a.bscanBase = p->cfg.bscanIndexBase; a.flipEnd = flip_end(p);
+	a.shiftBits = p->prm.bitshift ? 4 : 0; a.W = st.W; a.HB = st.HB; a.HA = st.HA;
+	const bool aligned = ((reinterpret_cast<uintptr_t>(dRaw) & 15) == 0) && (((size_t)p->N * p->rawBytes) % 16 == 0) && (((size_t)st.HB * p->rawBytes) % 16 == 0);
+	a.useBulk = aligned ? 1 : 0;
+	a.nPass = p->genPasses;
+	for (int i = 0; i < 16; ++i) a.radix[i] = p->genRadix[i];
+	return a;
+}
+
 /* next en-face gather of this handle: sequence number, frame window of that parity on every rank, header words */
 GatherDev next_gather(octb200_pipeline* p, unsigned frameNr, unsigned nFrames, int fn) {
 	auto& g = p->eg;
@@ -360,11 +378,15 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 	float* slab = p->dVolume + (size_t)(p->S / 2) * p->bufferNumberInVolume;
 
 	int mode = p->mode;
-	if (mode == OCTB200_FFT_FUSED) {
+	bool generic = false;              /* FUSED by the shared-memory kernel (line lengths / containers the register kernels do not take) */
+	if (mode == OCTB200_FFT_FUSED && p->regKernel) {
 		/* a huge rolling window with Lanczos halos may not fit the fused kernel's shared memory */
 		int g = 0, t = 0, sm = 0;
 		fused_launch_shape(p->R, st.sa, st.roll, SRC_RAW16, st.HB, st.HA, p->smCount, p->lines, &g, &t, &sm);
 		if (t < 32 * p->R) mode = OCTB200_FFT_SPLIT;
+	} else if (mode == OCTB200_FFT_FUSED) {
+		generic = generic_fits(p->N, p->rawBytes, st.HB, st.HA, st.roll);
+		if (!generic) mode = OCTB200_FFT_CUFFT;
 	}
 	if (mode != OCTB200_FFT_FUSED) { int rc = ensure_fft_buffer(p); if (rc) return rc; }
 
@@ -403,7 +425,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 	const int convSlot = convThisBuffer ? (int)((p->streamingBufferNumber + 1) % 2) : -1;
 	const bool convFoldable = convThisBuffer && !ppbgRecord && p->rawBytes == 2 && !(p->cfg.flags & OCTB200_FLAG_SEPARATE_CONVERSION);
 	const bool convInSinus = convFoldable && sinus;                                  /* the sinusoidal kernel writes the final slab: any FFT mode */
-	const bool convFused = convFoldable && !sinus && mode == OCTB200_FFT_FUSED;      /* the fused kernel's epilogue does */
+	const bool convFused = convFoldable && !sinus && mode == OCTB200_FFT_FUSED && !generic;      /* the register kernel's epilogue does */
 	const float convScale = (float)((1u << (p->cfg.bitDepth <= 10 ? 10 : p->cfg.bitDepth <= 12 ? 12 : 16)) - 1u);   /* cuda_code.cu:948-958 */
 
 	bool gatherDone = false;
@@ -429,6 +451,19 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		po.epi = epi_for(p, fpn, ppbgFoldMain); po.lines = p->lines; po.N = p->N; po.A = p->A;
 		po.flip = q.bscanFlip; po.bscanBase = p->cfg.bscanIndexBase; po.flipEnd = flip_end(p);
 		CK(p, launch_post(po, p->smCount, p->sCompute)); p->launches++;
+	} else if (generic) {
+		if (determine) {
+			int rc = ensure_fpn_scratch(p, (size_t)fpnHeight * p->H); if (rc) return rc;
+			GenericArgs ga = generic_args(p, st, dRaw, fpnHeight);
+			ga.cplxOut = p->dFpnScratch; ga.epi = epi_for(p, false, false);
+			CK(p, launch_generic(ga, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++;
+			CK(p, launch_fpn_minvar(p->dMeanLine, p->dFpnScratch, p->H, p->H, fpnHeight, p->dFpnStats, p->sCompute)); p->launches++;
+			p->fpnStatsBins = p->H; p->fpnStatsSegW = fpnHeight / 9;
+			p->fpnDetermined = true; q.redetermineFixedPatternNoise = 0;
+		}
+		GenericArgs ga = generic_args(p, st, dRaw, p->lines);
+		ga.out = mainOut; ga.epi = epi_for(p, fpn, ppbgFoldMain);
+		CK(p, launch_generic(ga, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++;
 	} else {
 		const int src = (mode == OCTB200_FFT_FUSED) ? rawSrc : SRC_CPLX;
 		if (determine) {
@@ -560,13 +595,16 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	}
 	p->inBytes = p->packed12 ? (size_t)S * 3 / 2 : (size_t)S * p->rawBytes;
 	const bool fftSize = (p->N == 1024 || p->N == 2048);
+	p->regKernel = fftSize && p->rawBytes == 2;
+	p->genericOk = !p->packed12 && generic_fft_plan(p->N, p->genRadix, &p->genPasses) && generic_fits(p->N, p->rawBytes, 0, 0, false);
 	int mode = cfg->fftMode;
-	if (mode == OCTB200_FFT_AUTO) mode = fftSize ? (p->rawBytes == 2 ? OCTB200_FFT_FUSED : OCTB200_FFT_SPLIT) : OCTB200_FFT_CUFFT;
-	if ((mode == OCTB200_FFT_FUSED && !(fftSize && p->rawBytes == 2)) || (mode == OCTB200_FFT_SPLIT && !fftSize) ||
+	/* FUSED = one kernel from raw samples to B-scan lines: the register kernels where they apply, else the shared-memory kernel */
+	if (mode == OCTB200_FFT_AUTO) mode = (p->regKernel || p->genericOk) ? OCTB200_FFT_FUSED : (fftSize ? OCTB200_FFT_SPLIT : OCTB200_FFT_CUFFT);
+	if ((mode == OCTB200_FFT_FUSED && !(p->regKernel || p->genericOk)) || (mode == OCTB200_FFT_SPLIT && !fftSize) ||
 	    mode < OCTB200_FFT_FUSED || mode > OCTB200_FFT_CUFFT) {
 		delete p;
-		return fail(nullptr, OCTB200_ERR_INVALID, "fftMode %d unsupported for samplesPerLine=%u bitDepth=%u (FUSED: N in {1024,2048} and 9..16 bit; SPLIT: N in {1024,2048})",
-		            cfg->fftMode, cfg->samplesPerLine, cfg->bitDepth);
+		return fail(nullptr, OCTB200_ERR_INVALID, "fftMode %d unsupported for samplesPerLine=%u bitDepth=%u (FUSED: even N <= 8192 with prime factors <= 13; "
+		            "SPLIT: N in {1024,2048}; packed 12-bit input: N in {1024,2048})", cfg->fftMode, cfg->samplesPerLine, cfg->bitDepth);
 	}
 	p->mode = mode;
 
@@ -603,6 +641,12 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	RCC(dalloc(p, &p->dPhasor, (size_t)p->N));
 	RCC(dalloc(p, &p->dLutB, (size_t)2 * p->N)); RCC(dalloc(p, &p->dLutB1, (size_t)p->N));
 	RCC(dalloc(p, &p->dTw, (size_t)1024)); RCC(dalloc(p, &p->dCtw, (size_t)1024));
+	if (p->genericOk && !p->regKernel) {
+		RCC(dalloc(p, &p->dTwN, (size_t)p->N));
+		std::vector<float2> twn((size_t)p->N);
+		for (int t = 0; t < p->N; ++t) { const double ang = 2.0 * M_PI * (double)t / (double)p->N; twn[t] = make_float2((float)std::cos(ang), (float)std::sin(ang)); }
+		CKC(cudaMemcpy(p->dTwN, twn.data(), sizeof(float2) * p->N, cudaMemcpyHostToDevice));
+	}
 	RCC(dalloc(p, &p->dSinCurve, (size_t)p->A));
 	{
 		unsigned char* c0 = nullptr; unsigned char* c1 = nullptr;
@@ -640,7 +684,7 @@ int octb200_destroy(octb200_pipeline* p) {
 	for (auto e : p->evConvFree) if (e) cudaEventDestroy(e);
 	dfree(p->dVolumeOwned); dfree(p->dTmp); dfree(p->dFft); dfree(p->dFpnScratch); dfree(p->dMeanLine); dfree(p->dFpnStats); dfree(p->dPpbg);
 	dfree(p->dPhase); dfree(p->dPhasor); dfree(p->dLutB); dfree(p->dLutB1);
-	dfree(p->dTw); dfree(p->dCtw); dfree(p->dSinCurve);
+	dfree(p->dTw); dfree(p->dCtw); dfree(p->dTwN); dfree(p->dSinCurve);
 	for (void*& c : p->dOutConv) { if (c) cudaFree(c); c = nullptr; }
 	octb200_enface_gather_close(p);
 	dfree(p->dUnpacked);
@@ -993,7 +1037,7 @@ int octb200_enface_gather_close(octb200_pipeline* p) {
 int octb200_dispersion_sweep(octb200_pipeline* p, const void* raw, const octb200_sweep_config* c, const float* coeffs, float* metricsOut, float* ascansOut) {
 	if (!p || !raw || !c || !coeffs || !metricsOut) return fail(p, OCTB200_ERR_INVALID, "null argument");
 	if (c->lines < 1 || c->trials < 1 || c->trials > 65535 || c->metric < 0 || c->metric > 3) return fail(p, OCTB200_ERR_INVALID, "bad sweep configuration");
-	if (!(p->N == 1024 || p->N == 2048) || p->rawBytes != 2)
+	if (!p->regKernel)
 		return fail(p, OCTB200_ERR_INVALID, "the dispersion sweep runs on the fused kernel: 1024 or 2048 samples per line in a 16-bit container");
 	if (c->logScale && !(c->logMax != c->logMin)) return fail(p, OCTB200_ERR_INVALID, "log scaling needs max != min");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
@@ -1103,6 +1147,10 @@ int octb200_time_kernel(octb200_pipeline* p, const void* dRaw, int iters, float*
 			PreArgs pa = pre_args(p, st, dRaw, p->lines);
 			int rc = ensure_fft_buffer(p); if (rc) return rc;
 			CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute));
+		} else if (p->mode == OCTB200_FFT_FUSED && !p->regKernel) {
+			GenericArgs ga = generic_args(p, st, dRaw, p->lines);
+			ga.out = slab; ga.epi = epi_for(p, fpn && p->fpnDetermined, false);
+			CK(p, launch_generic(ga, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute));
 		} else {
 			const int src = (p->mode == OCTB200_FFT_FUSED) ? ((p->packed12 && st.sa != SA_LANCZOS && !st.roll) ? SRC_RAW12P : SRC_RAW16) : SRC_CPLX;
 			if (p->packed12 && src != SRC_RAW12P) return fail(p, OCTB200_ERR_INVALID, "time_kernel: packed input is only timed on the direct fused path");
