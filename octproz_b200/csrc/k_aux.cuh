@@ -26,8 +26,9 @@ struct GenericArgs {
 	const void* raw;
 	float* out;              /* [lines][N/2] processed output slab (flip folded into the line address) */
 	float2* cplxOut;         /* != NULL: write the pre-FPN complex bins [lines][N/2] instead (FPN determination pass) */
-	const float4* lutB;      /* N entries, natural order: { byte offset of tap n1, w cos, w sin, t } */
-	const float2* twN;       /* exp(+2 pi i t / N), t < N */
+	const float4* lutB;      /* N entries, natural order: { byte offset of tap n1, w cos, w sin, t } (Lanczos / no resampling) */
+	const float4* lutG;      /* 4-tap interpolators: 2 N entries { byte offset of tap n1 - 1, w0, w1, w2 } { w3, w cos, w sin, - } */
+	const float2* tw;        /* per-pass twiddle tables (generic_twiddle_layout) */
 	const float2* meanLine;  /* N/2 */
 	const float* ppbg;       /* N/2 */
 	EpiConsts epi;
@@ -39,8 +40,12 @@ struct GenericArgs {
 	int useBulk;             /* 1: cp.async.bulk staging (16-byte aligned geometry), 0: plain loads */
 	int nPass;
 	int radix[16];
+	int twOff[16];
+	unsigned magic[16];      /* ceil(2^32 / Ns) of every pass: j mod Ns without a division */
 };
 bool generic_fft_plan(int N, int* radix, int* nPass);
+int generic_twiddle_layout(int N, const int* radix, int nPass, int* twOff, unsigned* magic);
+void generic_fill_twiddles(const int* radix, int nPass, const int* twOff, float2* tw);
 bool generic_fits(int N, int rawBytes, int HB, int HA, bool roll);
 cudaError_t launch_generic(const GenericArgs& a, int rawBytes, int sa, bool roll, int smCount, cudaStream_t st);
 

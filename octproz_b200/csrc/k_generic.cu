@@ -6,8 +6,9 @@
  *   raw line --cp.async.bulk (TMA 1-D) + mbarrier--> shared memory                                   (one CTA works on one line at a time)
  *     -> container -> fp32 [+ rolling-mean background removal]                                        (cuda_code.cu:109-211)
  *     -> resampling x window x dispersion phasor from the natural-order stage LUT                     (cuda_code.cu:213-489)
- *     -> inverse FFT: Stockham autosort passes between two shared-memory line buffers, mixed radix
- *        (radix 4 / 2 butterflies, odd primes by the symmetric O(P^2/2) form), twiddles w_N^t from a table   (cuda_code.cu:1514-1515)
+ *     -> inverse FFT: Stockham autosort passes between two (padded) shared-memory line buffers, mixed radix
+ *        (radix 8 / 4 / 2 butterflies, odd primes by the symmetric O(P^2/2) form), per-pass twiddle tables
+ *        laid out so that a warp reads consecutive words                                                (cuda_code.cu:1514-1515)
  *     -> FPN subtract, |.|^2, log / linear scale, truncate to N/2, flip in the store address, background  (cuda_code.cu:567-807)
  *     -> coalesced fp32 stores.  HBM traffic: the container bytes in + 2 B out per raw sample; nothing in between.
  *
@@ -43,6 +44,14 @@ __device__ __forceinline__ void dft_inv(float2 (&v)[R]) {
 		const float2 s13 = cadd(v[1], v[3]), d13 = cmul_i(csub(v[1], v[3]));        /* +i (v1 - v3) */
 		v[0] = cadd(s02, s13); v[2] = csub(s02, s13);
 		v[1] = cadd(d02, d13); v[3] = csub(d02, d13);
+	} else if constexpr (R == 8) {
+		float2 e[4] = { v[0], v[2], v[4], v[6] }, o[4] = { v[1], v[3], v[5], v[7] };
+		dft_inv<4>(e); dft_inv<4>(o);
+		const float2 t1 = mul_w32<4>(o[1]), t2 = mul_w32<8>(o[2]), t3 = mul_w32<12>(o[3]);      /* w_8^k = w_32^{4k} */
+		v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+		v[1] = cadd(e[1], t1);   v[5] = csub(e[1], t1);
+		v[2] = cadd(e[2], t2);   v[6] = csub(e[2], t2);
+		v[3] = cadd(e[3], t3);   v[7] = csub(e[3], t3);
 	} else {
 		/* odd prime: pair k with R - k.  a_k = x_k + x_{R-k}, b_k = x_k - x_{R-k};
 		 * X_j = x_0 + sum a_k cos(2 pi j k / R) + i sum b_k sin(2 pi j k / R), X_{R-j} the same with - i */
@@ -73,37 +82,42 @@ __device__ __forceinline__ void dft_inv(float2 (&v)[R]) {
 	}
 }
 
+/* line buffers are padded by one element per 32 so that the strided accesses of the first passes (stride R elements) spread over the banks */
+__host__ __device__ __forceinline__ int gpad(int i) { return i + (i >> 5); }
+__host__ __device__ inline int gpad_len(int N) { return N + (N >> 5) + 1; }
+
 /* one Stockham autosort pass of radix R over a line of N complex values in shared memory (Ns = product of the earlier radices):
- * butterfly j reads in[j + i N/R], multiplies by w_{Ns R}^{i (j mod Ns)} = twN[i (j mod Ns) N / (Ns R)], transforms, and writes
- * out[(j - j mod Ns) R + j mod Ns + i Ns] */
+ * butterfly j reads in[j + i N/R], multiplies by w_{Ns R}^{i k}, k = j mod Ns, transforms, and writes out[(j - k) R + k + i Ns].
+ * tw = this pass's table, tw[(i - 1) Ns + k] = w_{Ns R}^{i k}: the lanes of a warp (consecutive k) read consecutive words.
+ * j mod Ns by multiplication: magic = ceil(2^32 / Ns) is exact for j Ns < 2^32 / Ns, i.e. for every N <= 8192 */
 template <int R>
-__device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out, int N, int Ns, const float2* __restrict__ twN,
-                                              int tid, int T) {
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out, int N, int Ns, unsigned magic,
+                                              const float2* __restrict__ tw, int tid, int T) {
 	const int M = N / R;
-	const int tmul = N / (Ns * R);
 	for (int j = tid; j < M; j += T) {
 		float2 v[R];
 #pragma unroll
-		for (int i = 0; i < R; ++i) v[i] = in[j + i * M];
-		const int k = j % Ns;
+		for (int i = 0; i < R; ++i) v[i] = in[gpad(j + i * M)];
+		int k = 0;
 		if (Ns > 1) {
-			const int t = k * tmul;
+			k = j - (int)__umulhi((unsigned)j, magic) * Ns;
 #pragma unroll
-			for (int i = 1; i < R; ++i) v[i] = cmul(v[i], __ldg(twN + i * t));
+			for (int i = 1; i < R; ++i) v[i] = cmul(v[i], __ldg(tw + (i - 1) * Ns + k));
 		}
 		dft_inv<R>(v);
 		const int j0 = (j - k) * R + k;
 #pragma unroll
-		for (int i = 0; i < R; ++i) out[j0 + i * Ns] = v[i];
+		for (int i = 0; i < R; ++i) out[gpad(j0 + i * Ns)] = v[i];
 	}
 }
 
 __host__ __device__ inline int generic_smem_bytes(int N, int SE, int rawBytes, bool roll) {
 	/* [buffer A: N float2][buffer B: N float2, aliased by the fp32 slot (+ rolling prefix sums)][raw slot][mbarrier] */
-	int bBytes = N * 8;
+	const int aBytes = align_up(gpad_len(N) * 8, 128);
+	int bBytes = gpad_len(N) * 8;
 	const int slotBytes = align_up((FSLOT_PAD + SE) * 4, 16) + (roll ? align_up((SE + 1) * 8, 16) : 0);
 	if (slotBytes > bBytes) bBytes = slotBytes;
-	return N * 8 + align_up(bBytes, 128) + align_up(SE * rawBytes, 128) + 128;
+	return aBytes + align_up(bBytes, 128) + align_up(SE * rawBytes, 128) + 128;
 }
 
 template <typename RawT, int SA, bool ROLL>
@@ -113,16 +127,17 @@ __global__ void __launch_bounds__(256) oct_generic_kernel(const GenericArgs a) {
 	const int N = a.N, H = N / 2, SE = a.HB + N + a.HA;
 	const int tid = threadIdx.x, T = blockDim.x;
 	float2* bufA = reinterpret_cast<float2*>(smem);
-	int bBytes = N * 8;
+	const int aBytes = align_up(gpad_len(N) * 8, 128);
+	int bBytes = gpad_len(N) * 8;
 	{
 		const int slotBytes = align_up((FSLOT_PAD + SE) * 4, 16) + (ROLL ? align_up((SE + 1) * 8, 16) : 0);
 		if (slotBytes > bBytes) bBytes = slotBytes;
 	}
-	float2* bufB = reinterpret_cast<float2*>(smem + N * 8);
+	float2* bufB = reinterpret_cast<float2*>(smem + aBytes);
 	float* fslot = reinterpret_cast<float*>(bufB) + FSLOT_PAD;
 	unsigned long long* prefix = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bufB) + align_up((FSLOT_PAD + SE) * 4, 16));
-	RawT* rslot = reinterpret_cast<RawT*>(smem + N * 8 + align_up(bBytes, 128));
-	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + N * 8 + align_up(bBytes, 128) + align_up(SE * RB, 128));
+	RawT* rslot = reinterpret_cast<RawT*>(smem + aBytes + align_up(bBytes, 128));
+	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + aBytes + align_up(bBytes, 128) + align_up(SE * RB, 128));
 	const RawT* raw = reinterpret_cast<const RawT*>(a.raw);
 
 	auto issue = [&](int gline) {            /* thread 0 (bulk) or all threads (plain loads) */
@@ -196,13 +211,20 @@ __global__ void __launch_bounds__(256) oct_generic_kernel(const GenericArgs a) {
 			const float* f = fslot + a.HB;
 			const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
 			for (int m = tid; m < N; m += T) {
-				const float4 B = __ldg(a.lutB + m);
 				float2 val;
-				if constexpr (SA == SA_CUBIC) val = sample_cubic(f, B);
-				else if constexpr (SA == SA_LINEAR) val = sample_linear(f, B);
-				else if constexpr (SA == SA_NONE) val = sample_none(f, m, B);
-				else val = sample_lanczos(f, shift, B);
-				bufA[m] = val;
+				if constexpr (SA == SA_CUBIC) {
+					/* 4-tap interpolators in tap-weight form (Catmull-Rom cuda_code.cu:258-271 expanded per tap, or linear :229 as (0, 1-t, t, 0)):
+					 * the same arithmetic as the register kernels, y = sum_k w_k f[n1 - 1 + k], then y * (window * phasor) */
+					const float4 G0 = __ldg(a.lutG + 2 * m), G1 = __ldg(a.lutG + 2 * m + 1);
+					const int o = __float_as_int(G0.x);
+					const float y = fmaf(G1.x, ldf(f, o + 12), fmaf(G0.w, ldf(f, o + 8), fmaf(G0.z, ldf(f, o + 4), G0.y * ldf(f, o))));
+					val = cscale(make_float2(G1.y, G1.z), y);
+				} else {
+					const float4 B = __ldg(a.lutB + m);
+					if constexpr (SA == SA_NONE) val = sample_none(f, m, B);
+					else val = sample_lanczos(f, shift, B);
+				}
+				bufA[gpad(m)] = val;
 			}
 		}
 		__syncthreads();
@@ -212,14 +234,17 @@ __global__ void __launch_bounds__(256) oct_generic_kernel(const GenericArgs a) {
 		int Ns = 1;
 		for (int ps = 0; ps < a.nPass; ++ps) {
 			const int R = a.radix[ps];
+			const unsigned magic = a.magic[ps];
+			const float2* tw = a.tw + a.twOff[ps];
 			switch (R) {
-			case 2: stockham_pass<2>(in, out, N, Ns, a.twN, tid, T); break;
-			case 3: stockham_pass<3>(in, out, N, Ns, a.twN, tid, T); break;
-			case 4: stockham_pass<4>(in, out, N, Ns, a.twN, tid, T); break;
-			case 5: stockham_pass<5>(in, out, N, Ns, a.twN, tid, T); break;
-			case 7: stockham_pass<7>(in, out, N, Ns, a.twN, tid, T); break;
-			case 11: stockham_pass<11>(in, out, N, Ns, a.twN, tid, T); break;
-			default: stockham_pass<13>(in, out, N, Ns, a.twN, tid, T); break;
+			case 2: stockham_pass<2>(in, out, N, Ns, magic, tw, tid, T); break;
+			case 3: stockham_pass<3>(in, out, N, Ns, magic, tw, tid, T); break;
+			case 4: stockham_pass<4>(in, out, N, Ns, magic, tw, tid, T); break;
+			case 5: stockham_pass<5>(in, out, N, Ns, magic, tw, tid, T); break;
+			case 7: stockham_pass<7>(in, out, N, Ns, magic, tw, tid, T); break;
+			case 8: stockham_pass<8>(in, out, N, Ns, magic, tw, tid, T); break;
+			case 11: stockham_pass<11>(in, out, N, Ns, magic, tw, tid, T); break;
+			default: stockham_pass<13>(in, out, N, Ns, magic, tw, tid, T); break;
 			}
 			Ns *= R;
 			__syncthreads();
@@ -229,14 +254,14 @@ __global__ void __launch_bounds__(256) oct_generic_kernel(const GenericArgs a) {
 		/* ---- epilogue (bins z < N/2), from `in` = the buffer the last pass wrote ---- */
 		if (a.cplxOut != nullptr) {
 			float2* o = a.cplxOut + (size_t)gline * H;
-			for (int z = tid; z < H; z += T) o[z] = in[z];
+			for (int z = tid; z < H; z += T) o[z] = in[gpad(z)];
 		} else {
 			int b = gline / a.A, al = gline - b * a.A;
 			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u && (unsigned)b + a.bscanBase < a.flipEnd) al = a.A - 1 - al;
 			float* o = a.out + ((size_t)b * a.A + al) * H;
 			const EpiConsts e = a.epi;
 			for (int z = tid; z < H; z += T) {
-				float2 d = in[z];
+				float2 d = in[gpad(z)];
 				if (e.fpn) d = csub(d, __ldg(a.meanLine + z));
 				const float pw = fmaf(d.x, d.x, d.y * d.y);
 				float v = e.logMode ? fmaf(oct_lg2(pw), e.scaleA, e.scaleB) : fmaf(oct_sqrt(pw), e.scaleA, e.scaleB);
@@ -248,17 +273,48 @@ __global__ void __launch_bounds__(256) oct_generic_kernel(const GenericArgs a) {
 	}
 }
 
-/* radix plan: odd primes first (their odd output stride keeps the first pass's stores off the same banks), then 4s, then at most one 2 */
+/* radix plan: odd primes first, then the power of two as 8s with the remainder as 4 (2^{3q+2}), 4 * 4 (2^{3q+1}, q >= 1) or 2 */
 bool generic_fft_plan(int N, int* radix, int* nPass) {
 	if (N < 8 || (N & 1) || N > 8192) return false;
 	int n = N, cnt = 0;
 	const int odd[] = { 13, 11, 7, 5, 3 };
-	for (int p : odd) while (n % p == 0) { if (cnt >= 16) return false; radix[cnt++] = p; n /= p; }
-	while (n % 4 == 0) { if (cnt >= 16) return false; radix[cnt++] = 4; n /= 4; }
-	if (n % 2 == 0) { if (cnt >= 16) return false; radix[cnt++] = 2; n /= 2; }
+	for (int p : odd) while (n % p == 0) { if (cnt >= 12) return false; radix[cnt++] = p; n /= p; }
+	int a = 0;
+	while (n % 2 == 0) { ++a; n /= 2; }
 	if (n != 1) return false;
+	int eights = a / 3;
+	const int rem = a % 3;
+	if (rem == 1 && eights >= 1) { --eights; for (int i = 0; i < eights; ++i) radix[cnt++] = 8; radix[cnt++] = 4; radix[cnt++] = 4; }
+	else { for (int i = 0; i < eights; ++i) radix[cnt++] = 8; if (rem == 2) radix[cnt++] = 4; else if (rem == 1) radix[cnt++] = 2; }
 	*nPass = cnt;
-	return true;
+	return cnt <= 16;
+}
+
+/* per-pass twiddle tables, concatenated: pass p (radix R, Ns = product of the earlier radices) holds tw[(i - 1) Ns + k] =
+ * exp(+2 pi i * i k / (Ns R)), i = 1 .. R-1, k < Ns; the first pass (Ns = 1) has none.  Returns the total number of entries. */
+int generic_twiddle_layout(int N, const int* radix, int nPass, int* twOff, unsigned* magic) {
+	(void)N;
+	int off = 0, Ns = 1;
+	for (int p = 0; p < nPass; ++p) {
+		twOff[p] = off;
+		magic[p] = (Ns > 1) ? (unsigned)((0x100000000ull + (unsigned long long)Ns - 1ull) / (unsigned long long)Ns) : 0u;
+		if (Ns > 1) off += (radix[p] - 1) * Ns;
+		Ns *= radix[p];
+	}
+	return off > 0 ? off : 1;
+}
+void generic_fill_twiddles(const int* radix, int nPass, const int* twOff, float2* tw) {
+	int Ns = 1;
+	for (int p = 0; p < nPass; ++p) {
+		const int R = radix[p];
+		if (Ns > 1)
+			for (int i = 1; i < R; ++i)
+				for (int k = 0; k < Ns; ++k) {
+					const double ang = 2.0 * 3.14159265358979323846 * (double)i * (double)k / ((double)Ns * (double)R);
+					tw[twOff[p] + (i - 1) * Ns + k] = make_float2((float)cos(ang), (float)sin(ang));
+				}
+		Ns *= R;
+	}
 }
 
 template <typename RawT, int SA, bool ROLL>
@@ -269,11 +325,11 @@ static cudaError_t launch_generic_t(const GenericArgs& a, int smCount, cudaStrea
 	auto k = oct_generic_kernel<RawT, SA, ROLL>;
 	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess) return e;
-	const int threads = a.N >= 2048 ? 256 : 128;
+	const int threads = a.N >= 2048 ? 256 : (a.N >= 1024 ? 128 : 64);
 	int ctasPerSm = (227 * 1024) / (smem + 1024);
-	const int maxByThreads = 2048 / threads;
+	const int maxByThreads = 1536 / threads;
 	if (ctasPerSm > maxByThreads) ctasPerSm = maxByThreads;
-	if (ctasPerSm > 8) ctasPerSm = 8;
+	if (ctasPerSm > 16) ctasPerSm = 16;
 	if (ctasPerSm < 1) ctasPerSm = 1;
 	int grid = smCount * ctasPerSm;
 	if (grid > a.lines) grid = a.lines;
@@ -284,8 +340,8 @@ static cudaError_t launch_generic_t(const GenericArgs& a, int smCount, cudaStrea
 
 template <typename RawT>
 static cudaError_t launch_generic_raw(const GenericArgs& a, int sa, bool roll, int smCount, cudaStream_t st) {
-	if (sa == SA_CUBIC) return roll ? launch_generic_t<RawT, SA_CUBIC, true>(a, smCount, st) : launch_generic_t<RawT, SA_CUBIC, false>(a, smCount, st);
-	if (sa == SA_LINEAR) return roll ? launch_generic_t<RawT, SA_LINEAR, true>(a, smCount, st) : launch_generic_t<RawT, SA_LINEAR, false>(a, smCount, st);
+	/* linear = the same 4-tap kernel with weights (0, 1-t, t, 0) */
+	if (sa == SA_CUBIC || sa == SA_LINEAR) return roll ? launch_generic_t<RawT, SA_CUBIC, true>(a, smCount, st) : launch_generic_t<RawT, SA_CUBIC, false>(a, smCount, st);
 	if (sa == SA_NONE) return roll ? launch_generic_t<RawT, SA_NONE, true>(a, smCount, st) : launch_generic_t<RawT, SA_NONE, false>(a, smCount, st);
 	return roll ? launch_generic_t<RawT, SA_LANCZOS, true>(a, smCount, st) : launch_generic_t<RawT, SA_LANCZOS, false>(a, smCount, st);
 }

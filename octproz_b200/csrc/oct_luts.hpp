@@ -62,6 +62,22 @@ inline void tap_weights(int interp, float tf, float (&w)[4]) {
 	}
 }
 
+/* natural-order 4-tap table of the shared-memory kernel (k_generic.cu): two float4 per sample,
+ * { byte offset of tap n1 - 1, w0, w1, w2 } { w3, window * cos, window * sin, 0 }; f[-1] of the float slot mirrors f[1] (cuda_code.cu:284) */
+inline void build_stage_luts_taps(int N, int interp, const float* resample, const float* window, const float2* phasor, std::vector<float4>& out) {
+	StageLuts nat;
+	build_stage_luts(N, 1, resample, window, phasor, nat);
+	out.assign((size_t)2 * N, make_float4(0, 0, 0, 0));
+	for (int m = 0; m < N; ++m) {
+		const float4 B = nat.B[m];
+		int o; std::memcpy(&o, &B.x, 4);
+		float w[4];
+		tap_weights(interp, B.w, w);
+		out[2 * m] = make_float4(int_as_float(o - 4), w[0], w[1], w[2]);
+		out[2 * m + 1] = make_float4(w[3], B.y, B.z, 0.0f);
+	}
+}
+
 /* paired layout for the fused kernel (see stage_a): 2N float4s = four planes [ P | Q | W01 | W23 ] of N/2 entries.
  * taps = 0: Q = { off_a, off_b, t_a, t_b } (byte offset of tap n1 and fractional position: Lanczos, no resampling)
  * taps = 1: 4-tap interpolators, natural float slot: Q = { offX_a, offX_b, offY_a, offY_b } with offX = 4 (n1 - 1), offY = offX + 8,

@@ -90,8 +90,9 @@ struct octb200_pipeline {
 	float2 *dTw = nullptr, *dCtw = nullptr;
 	bool regKernel = false;           /* N in {1024, 2048} in a u16 container: the register kernels (k_fused.cuh) take the FUSED mode */
 	bool genericOk = false;           /* the shared-memory kernel (k_generic.cu) can transform this line length */
-	float2* dTwN = nullptr;           /* exp(+2 pi i t / N), t < N, for the generic kernel's passes */
-	int genRadix[16] = {}; int genPasses = 0;
+	float2* dTwN = nullptr;           /* per-pass twiddle tables of the generic kernel */
+	float4* dLutG = nullptr;          /* its natural-order 4-tap table (2 N entries) */
+	int genRadix[16] = {}; int genPasses = 0; int genTwOff[16] = {}; unsigned genMagic[16] = {};
 	float* dSinCurve = nullptr;
 	void* dOutConv[2] = { nullptr, nullptr };
 	int cufftPlan = -1;
@@ -238,6 +239,12 @@ int rebuild_luts(octb200_pipeline* p) {
 	build_stage_luts(N, 1, res, win, ph, l);
 	CK(p, cudaMemcpyAsync(p->dLutB1, l.B.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, p->sCompute));
 	CK(p, cudaStreamSynchronize(p->sCompute));
+	if (p->dLutG) {
+		std::vector<float4> taps;
+		build_stage_luts_taps(N, interp == OCTB200_INTERP_CUBIC ? 1 : 0, res, win, ph, taps);
+		CK(p, cudaMemcpyAsync(p->dLutG, taps.data(), sizeof(float4) * 2 * N, cudaMemcpyHostToDevice, p->sCompute));
+		CK(p, cudaStreamSynchronize(p->sCompute));
+	}
 	p->lutsDirty = false;
 	p->lutSa = st.sa; p->lutRoll = st.roll; p->lutInterp = interp; p->lutWin = q.windowing != 0; p->lutDisp = q.dispersionCompensation != 0;
 	return OCTB200_OK;
@@ -297,7 +304,7 @@ PreArgs pre_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, i
 
 GenericArgs generic_args(const octb200_pipeline* p, const Stage& st, const void* dRaw, int lines) {
 	GenericArgs a{};
-	a.raw = dRaw; a.lutB = p->dLutB1; a.twN = p->dTwN;
+	a.raw = dRaw; a.lutB = p->dLutB1; a.lutG = p->dLutG; a.tw = p->dTwN;
 	a.meanLine = p->dMeanLine; a.ppbg = p->dPpbg;
 	a.totalSamples = p->S; a.lines = lines; a.N = p->N; a.A = p->A;
 	a.flip = p->prm.bscanFlip; a.bscanBase = p->cfg.bscanIndexBase; a.flipEnd = flip_end(p);
@@ -305,7 +312,7 @@ GenericArgs generic_args(const octb200_pipeline* p, const Stage& st, const void*
 	const bool aligned = ((reinterpret_cast<uintptr_t>(dRaw) & 15) == 0) && (((size_t)p->N * p->rawBytes) % 16 == 0) && (((size_t)st.HB * p->rawBytes) % 16 == 0);
 	a.useBulk = aligned ? 1 : 0;
 	a.nPass = p->genPasses;
-	for (int i = 0; i < 16; ++i) a.radix[i] = p->genRadix[i];
+	for (int i = 0; i < 16; ++i) { a.radix[i] = p->genRadix[i]; a.twOff[i] = p->genTwOff[i]; a.magic[i] = p->genMagic[i]; }
 	return a;
 }
 
@@ -642,12 +649,13 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	RCC(dalloc(p, &p->dLutB, (size_t)2 * p->N)); RCC(dalloc(p, &p->dLutB1, (size_t)p->N));
 	RCC(dalloc(p, &p->dTw, (size_t)1024)); RCC(dalloc(p, &p->dCtw, (size_t)1024));
 	if (p->genericOk && !p->regKernel) {
-		RCC(dalloc(p, &p->dTwN, (size_t)p->N));
-		std::vector<float2> twn((size_t)p->N);
-		for (int t = 0; t < p->N; ++t) { const double ang = 2.0 * M_PI * (double)t / (double)p->N; twn[t] = make_float2((float)std::cos(ang), (float)std::sin(ang)); }
-		CKC(cudaMemcpy(p->dTwN, twn.data(), sizeof(float2) * p->N, cudaMemcpyHostToDevice));
+		const int entries = generic_twiddle_layout(p->N, p->genRadix, p->genPasses, p->genTwOff, p->genMagic);
+		RCC(dalloc(p, &p->dTwN, (size_t)entries));
+		RCC(dalloc(p, &p->dLutG, (size_t)2 * p->N));
+		std::vector<float2> twn((size_t)entries, make_float2(1.f, 0.f));
+		generic_fill_twiddles(p->genRadix, p->genPasses, p->genTwOff, twn.data());
+		CKC(cudaMemcpy(p->dTwN, twn.data(), sizeof(float2) * entries, cudaMemcpyHostToDevice));
 	}
-	RCC(dalloc(p, &p->dSinCurve, (size_t)p->A));
 	{
 		unsigned char* c0 = nullptr; unsigned char* c1 = nullptr;
 		RCC(dalloc(p, &c0, (size_t)(S / 2) * p->rawBytes)); p->dOutConv[0] = c0;
@@ -684,7 +692,7 @@ int octb200_destroy(octb200_pipeline* p) {
 	for (auto e : p->evConvFree) if (e) cudaEventDestroy(e);
 	dfree(p->dVolumeOwned); dfree(p->dTmp); dfree(p->dFft); dfree(p->dFpnScratch); dfree(p->dMeanLine); dfree(p->dFpnStats); dfree(p->dPpbg);
 	dfree(p->dPhase); dfree(p->dPhasor); dfree(p->dLutB); dfree(p->dLutB1);
-	dfree(p->dTw); dfree(p->dCtw); dfree(p->dTwN); dfree(p->dSinCurve);
+	dfree(p->dTw); dfree(p->dCtw); dfree(p->dTwN); dfree(p->dLutG); dfree(p->dSinCurve);
 	for (void*& c : p->dOutConv) { if (c) cudaFree(c); c = nullptr; }
 	octb200_enface_gather_close(p);
 	dfree(p->dUnpacked);

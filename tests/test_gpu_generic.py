@@ -33,12 +33,12 @@ def run(q, raw, mode, mean_line=None, pp_background=None):
 
 
 # 2^a * {1, 3, 5, 7, 11, 13} mixes, the smallest and the largest supported length
-LENGTHS = [8, 48, 100, 512, 640, 896, 1408, 1536, 1664, 3072, 4096, 4160, 8190, 8192]
+LENGTHS = [8, 48, 100, 512, 640, 896, 1408, 1536, 1664, 2560, 3072, 4096, 4160, 8190, 8192]
 
 
 @pytest.mark.parametrize("n", LENGTHS)
 def test_line_lengths_match_the_oracle_in_one_launch(n):
-    a, b = 12, 3
+    a, b = (12, 3) if n < 4000 else (4, 3)       # (the oracle's transform is O(N^2) for lengths that are not powers of two)
     q = benchmark_params(n, a, b, 12); q.fixedPatternNoiseRemoval = False; q.bscanFlip = True
     q.update_all_curves()
     raw = synth.make_volume(n, a, b, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
@@ -50,7 +50,8 @@ def test_line_lengths_match_the_oracle_in_one_launch(n):
     assert_parity(out, ref, q, max_frac_outside=1e-4, what=f"generic fused kernel N={n}")
     cu, _, eff_cu, _ = run(q, raw, _lib.FFT_CUFFT)
     assert eff_cu == _lib.FFT_CUFFT
-    assert_parity(out, cu, q, max_frac_outside=1e-4, what=f"generic fused kernel vs cuFFT chain N={n}")
+    # two fp32 transforms that each meet 1e-4 against the oracle may differ from one another by twice that
+    assert_parity(out, cu, q, rtol=2e-4, atol_frac=2e-4, max_frac_outside=1e-4, what=f"generic fused kernel vs cuFFT chain N={n}")
 
 
 VARIANTS = {
@@ -146,8 +147,8 @@ def test_full_size_default_geometry_properties():
     again, _, _, _ = run(q, raw, _lib.FFT_FUSED)
     assert np.array_equal(out, again), "not deterministic"
     assert np.array_equal(out[:8], out[8:16]) and np.array_equal(out[:8], out[-8:]), "periodic input must give periodic output"
-    ref, _, _ = orc.process(benchmark_params_like(q, 8), small)
-    assert_parity(out[:8], ref, q, max_frac_outside=1e-4, what="generic fused kernel, full size 1664x512x256, first tile vs oracle")
+    ref, _, _ = orc.process(benchmark_params_like(q, 1), small[:1])        # (the oracle's transform is O(N^2) for this length: one B-scan)
+    assert_parity(out[:1], ref, q, max_frac_outside=1e-4, what="generic fused kernel, full size 1664x512x256, first B-scan vs oracle")
     qf = copy.deepcopy(q); qf.bscanFlip = True
     fl, _, _, _ = run(qf, raw, _lib.FFT_FUSED)
     assert np.array_equal(fl[0::2], out[0::2, ::-1]) and np.array_equal(fl[1::2], out[1::2])

@@ -328,9 +328,13 @@ def test_host_and_device_paths_agree_and_null_reprocesses():
 
 def test_error_behaviour():
     q = benchmark_params(1024, 8, 1)
+    p = OctPipeline(fft_mode=_lib.FFT_SPLIT)
+    q8 = copy.deepcopy(q); q8.samplesPerLine = 1664
+    assert not p.initializeCuda(None, None, q8)                       # SPLIT exists for 1024 / 2048 only
+    assert "unsupported" in p._create_error
     p = OctPipeline(fft_mode=_lib.FFT_FUSED)
-    q8 = copy.deepcopy(q); q8.bitDepth = 8
-    assert not p.initializeCuda(None, None, q8)                       # FUSED needs a u16 container
+    q8 = copy.deepcopy(q); q8.samplesPerLine = 1006                   # 2 * 503: no fused kernel for this length, and no silent fallback
+    assert not p.initializeCuda(None, None, q8)
     assert "unsupported" in p._create_error
     p = OctPipeline()
     L = p._lib
