@@ -656,6 +656,7 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 		generic_fill_twiddles(p->genRadix, p->genPasses, p->genTwOff, twn.data());
 		CKC(cudaMemcpy(p->dTwN, twn.data(), sizeof(float2) * entries, cudaMemcpyHostToDevice));
 	}
+	RCC(dalloc(p, &p->dSinCurve, (size_t)p->A));
 	{
 		unsigned char* c0 = nullptr; unsigned char* c1 = nullptr;
 		RCC(dalloc(p, &c0, (size_t)(S / 2) * p->rawBytes)); p->dOutConv[0] = c0;
