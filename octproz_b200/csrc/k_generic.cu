@@ -18,6 +18,8 @@
  */
 #include "k_aux.cuh"
 
+#include <cstdlib>
+
 namespace octb200 {
 
 template <int P> struct DftTab;
@@ -88,7 +90,7 @@ __host__ __device__ inline int gpad_len(int N) { return N + (N >> 5) + 1; }
 
 /* one Stockham autosort pass of radix R over a line of N complex values in shared memory (Ns = product of the earlier radices):
  * butterfly j reads in[j + i N/R], multiplies by w_{Ns R}^{i k}, k = j mod Ns, transforms, and writes out[(j - k) R + k + i Ns].
- * tw = this pass's table, tw[(i - 1) Ns + k] = w_{Ns R}^{i k}: the lanes of a warp (consecutive k) read consecutive words.
+ * tw = this pass's table (shared memory), tw[(i - 1) Ns + k] = w_{Ns R}^{i k}: the lanes of a warp (consecutive k) read consecutive words.
  * j mod Ns by multiplication: magic = ceil(2^32 / Ns) is exact for j Ns < 2^32 / Ns, i.e. for every N <= 8192 */
 template <int R>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out, int N, int Ns, unsigned magic,
@@ -102,7 +104,7 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
 		if (Ns > 1) {
 			k = j - (int)__umulhi((unsigned)j, magic) * Ns;
 #pragma unroll
-			for (int i = 1; i < R; ++i) v[i] = cmul(v[i], __ldg(tw + (i - 1) * Ns + k));
+			for (int i = 1; i < R; ++i) v[i] = cmul(v[i], tw[(i - 1) * Ns + k]);
 		}
 		dft_inv<R>(v);
 		const int j0 = (j - k) * R + k;
@@ -111,103 +113,124 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
 	}
 }
 
-__host__ __device__ inline int generic_smem_bytes(int N, int SE, int rawBytes, bool roll) {
-	/* [buffer A: N float2][buffer B: N float2, aliased by the fp32 slot (+ rolling prefix sums)][raw slot][mbarrier] */
-	const int aBytes = align_up(gpad_len(N) * 8, 128);
+/* shared memory of one CTA: [twiddle tables][per line team: buffer A, buffer B (aliased by the fp32 slot + rolling prefix sums)]
+ * [raw region of the LB consecutive lines of a batch, with the Lanczos halos at both ends][mbarrier] */
+struct GenericSmem { int twBytes, aBytes, bBytes, teamBytes, rawOff, rawBytes, barOff, total; };
+__host__ __device__ inline GenericSmem generic_smem_layout(int N, int HB, int HA, int rawBytesPerSample, bool roll, int LB, int twEntries) {
+	GenericSmem L;
+	const int SE = HB + N + HA;
+	L.twBytes = align_up(twEntries * 8, 128);
+	L.aBytes = align_up(gpad_len(N) * 8, 128);
 	int bBytes = gpad_len(N) * 8;
 	const int slotBytes = align_up((FSLOT_PAD + SE) * 4, 16) + (roll ? align_up((SE + 1) * 8, 16) : 0);
 	if (slotBytes > bBytes) bBytes = slotBytes;
-	return aBytes + align_up(bBytes, 128) + align_up(SE * rawBytes, 128) + 128;
+	L.bBytes = align_up(bBytes, 128);
+	L.teamBytes = L.aBytes + L.bBytes;
+	L.rawOff = L.twBytes + LB * L.teamBytes;
+	L.rawBytes = align_up((LB * N + HB + HA) * rawBytesPerSample, 128);
+	L.barOff = L.rawOff + L.rawBytes;
+	L.total = L.barOff + 128;
+	return L;
 }
 
+/* blockDim = (TT, LB): LB "line teams" of TT threads; a CTA works on batches of LB consecutive lines (one bulk copy per batch), team l
+ * on line l of the batch.  The teams share the twiddle tables (shared memory, filled once per CTA), the stage LUT reads (L1) and the
+ * CTA-wide barriers between the passes. */
 template <typename RawT, int SA, bool ROLL>
-__global__ void __launch_bounds__(256) oct_generic_kernel(const GenericArgs a) {
+__global__ void __launch_bounds__(512, 2) oct_generic_kernel(const GenericArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	constexpr int RB = sizeof(RawT);
 	const int N = a.N, H = N / 2, SE = a.HB + N + a.HA;
-	const int tid = threadIdx.x, T = blockDim.x;
-	float2* bufA = reinterpret_cast<float2*>(smem);
-	const int aBytes = align_up(gpad_len(N) * 8, 128);
-	int bBytes = gpad_len(N) * 8;
-	{
-		const int slotBytes = align_up((FSLOT_PAD + SE) * 4, 16) + (ROLL ? align_up((SE + 1) * 8, 16) : 0);
-		if (slotBytes > bBytes) bBytes = slotBytes;
-	}
-	float2* bufB = reinterpret_cast<float2*>(smem + aBytes);
+	const int tid = threadIdx.x, T = blockDim.x, team = threadIdx.y, LB = blockDim.y;
+	const int ctid = team * T + tid, CT = T * LB;
+	const GenericSmem L = generic_smem_layout(N, a.HB, a.HA, RB, ROLL, LB, a.twEntries);
+	float2* stw = reinterpret_cast<float2*>(smem);
+	float2* bufA = reinterpret_cast<float2*>(smem + L.twBytes + team * L.teamBytes);
+	float2* bufB = reinterpret_cast<float2*>(smem + L.twBytes + team * L.teamBytes + L.aBytes);
 	float* fslot = reinterpret_cast<float*>(bufB) + FSLOT_PAD;
 	unsigned long long* prefix = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bufB) + align_up((FSLOT_PAD + SE) * 4, 16));
-	RawT* rslot = reinterpret_cast<RawT*>(smem + aBytes + align_up(bBytes, 128));
-	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + aBytes + align_up(bBytes, 128) + align_up(SE * RB, 128));
+	RawT* rawRegion = reinterpret_cast<RawT*>(smem + L.rawOff);
+	const RawT* rslot = rawRegion + team * N;                  /* this team's window [line start - HB, line end + HA) of the region */
+	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.barOff);
 	const RawT* raw = reinterpret_cast<const RawT*>(a.raw);
 
-	auto issue = [&](int gline) {            /* thread 0 (bulk) or all threads (plain loads) */
-		const long long lo = (long long)gline * N - a.HB, hi = (long long)gline * N + N + a.HA;
+	auto issue = [&](int g) {                /* batch of lines g .. g + LB - 1: one thread (bulk) or all threads (plain loads) */
+		const int nl = min(LB, a.lines - g);
+		const long long lo = (long long)g * N - a.HB, hi = (long long)(g + nl) * N + a.HA;
 		const long long clo = lo < 0 ? 0 : lo, chi = hi > a.totalSamples ? a.totalSamples : hi;
 		if (a.useBulk) {
-			if (tid == 0) {
-				for (long long q = 0; q < clo - lo; ++q) rslot[q] = 0;
-				for (long long q = chi - lo; q < hi - lo; ++q) rslot[q] = 0;
+			if (ctid == 0) {
+				for (long long q = 0; q < clo - lo; ++q) rawRegion[q] = 0;
+				for (long long q = chi - lo; q < hi - lo; ++q) rawRegion[q] = 0;
 				const uint32_t bytes = (uint32_t)((chi - clo) * RB);
 				mbar_arrive_expect_tx(bar, bytes);
-				bulk_g2s(rslot + (clo - lo), raw + clo, bytes, bar);
+				bulk_g2s(rawRegion + (clo - lo), raw + clo, bytes, bar);
 			}
 		} else {
-			for (long long q = lo + tid; q < hi; q += T) rslot[q - lo] = (q >= 0 && q < a.totalSamples) ? raw[q] : (RawT)0;
+			for (long long q = lo + ctid; q < hi; q += CT) rawRegion[q - lo] = (q >= 0 && q < a.totalSamples) ? raw[q] : (RawT)0;
 		}
 	};
 
-	if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+	if (ctid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+	for (int i = ctid; i < a.twEntries; i += CT) stw[i] = __ldg(a.tw + i);
 	__syncthreads();
-	if ((int)blockIdx.x < a.lines) issue(blockIdx.x);
+	const int g0 = blockIdx.x * LB, gstep = gridDim.x * LB;
+	if (g0 < a.lines) issue(g0);
 
 	int it = 0;
-	for (int gline = blockIdx.x; gline < a.lines; gline += gridDim.x, ++it) {
+	for (int g = g0; g < a.lines; g += gstep, ++it) {
+		const int gline = g + team;
+		const bool active = gline < a.lines;
 		if (a.useBulk) mbar_wait(bar, (uint32_t)(it & 1));
 		else __syncthreads();
 
 		/* ---- container -> fp32 (cuda_code.cu:109-147), rolling-mean background (cuda_code.cu:165-211: exact integer prefix sums) ---- */
-		if constexpr (ROLL) {
-			if (tid < 32) {
-				unsigned long long carry = 0;
-				if (tid == 0) prefix[0] = 0;
-				for (int c = 0; c < SE; c += 32) {
-					const int q = c + tid;
-					unsigned long long x = 0;
-					if (q < SE) x = (sizeof(RawT) == 4) ? (unsigned long long)rslot[q] : (unsigned long long)((unsigned)rslot[q] >> a.shiftBits);
+		if (active) {
+			if constexpr (ROLL) {
+				if (tid < 32) {
+					unsigned long long carry = 0;
+					if (tid == 0) prefix[0] = 0;
+					for (int c = 0; c < SE; c += 32) {
+						const int q = c + tid;
+						unsigned long long x = 0;
+						if (q < SE) x = (sizeof(RawT) == 4) ? (unsigned long long)rslot[q] : (unsigned long long)((unsigned)rslot[q] >> a.shiftBits);
 #pragma unroll
-					for (int d = 1; d < 32; d <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d); if (tid >= d) x += y; }
-					if (q < SE) prefix[q + 1] = carry + x;
-					carry += __shfl_sync(0xffffffffu, x, 31);
+						for (int d = 1; d < 32; d <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d); if (tid >= d) x += y; }
+						if (q < SE) prefix[q + 1] = carry + x;
+						carry += __shfl_sync(0xffffffffu, x, 31);
+					}
 				}
 			}
+			for (int q = tid; q < SE; q += T) fslot[q] = generic_convert<RawT>(rslot[q], a.shiftBits);
 		}
-		for (int q = tid; q < SE; q += T) fslot[q] = generic_convert<RawT>(rslot[q], a.shiftBits);
 		__syncthreads();
-		/* raw slot consumed: start the load of this CTA's next line */
-		if (gline + (int)gridDim.x < a.lines) issue(gline + gridDim.x);
+		/* raw region consumed: start the load of this CTA's next batch */
+		if (g + gstep < a.lines) issue(g + gstep);
 		if constexpr (ROLL) {
-			const int W = a.W;
-			for (int q = tid; q < SE; q += T) {
-				int lo, hi;
-				if (q < a.HB) { lo = 0; hi = a.HB - 1; }
-				else if (q >= a.HB + N) { lo = a.HB + N; hi = SE - 1; }
-				else { lo = a.HB; hi = a.HB + N - 1; }
-				const int ss = max(lo, q - W + 1), e = min(hi, q + W);
-				const unsigned long long d = prefix[e + 1] - prefix[ss];
-				float sum;
-				if (sizeof(RawT) == 4 && a.shiftBits) sum = (float)((double)d / 4294967296.0);
-				else sum = (float)d;
-				fslot[q] -= __fdividef(sum, (float)(e - ss + 1));
+			if (active) {
+				const int W = a.W;
+				for (int q = tid; q < SE; q += T) {
+					int lo, hi;
+					if (q < a.HB) { lo = 0; hi = a.HB - 1; }
+					else if (q >= a.HB + N) { lo = a.HB + N; hi = SE - 1; }
+					else { lo = a.HB; hi = a.HB + N - 1; }
+					const int ss = max(lo, q - W + 1), e = min(hi, q + W);
+					const unsigned long long d = prefix[e + 1] - prefix[ss];
+					float sum;
+					if (sizeof(RawT) == 4 && a.shiftBits) sum = (float)((double)d / 4294967296.0);
+					else sum = (float)d;
+					fslot[q] -= __fdividef(sum, (float)(e - ss + 1));
+				}
 			}
 			__syncthreads();
 		}
 		if constexpr (SA == SA_CUBIC) {
-			if (tid == 0) fslot[a.HB - 1] = fslot[a.HB + 1];      /* mirrored first tap of the cubic (cuda_code.cu:284) */
+			if (active && tid == 0) fslot[a.HB - 1] = fslot[a.HB + 1];      /* mirrored first tap of the cubic (cuda_code.cu:284) */
 			__syncthreads();
 		}
 
 		/* ---- stage A: resampling x window x phasor -> complex FFT input in buffer A ---- */
-		{
+		if (active) {
 			const float* f = fslot + a.HB;
 			const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
 			for (int m = tid; m < N; m += T) {
@@ -235,16 +258,18 @@ __global__ void __launch_bounds__(256) oct_generic_kernel(const GenericArgs a) {
 		for (int ps = 0; ps < a.nPass; ++ps) {
 			const int R = a.radix[ps];
 			const unsigned magic = a.magic[ps];
-			const float2* tw = a.tw + a.twOff[ps];
-			switch (R) {
-			case 2: stockham_pass<2>(in, out, N, Ns, magic, tw, tid, T); break;
-			case 3: stockham_pass<3>(in, out, N, Ns, magic, tw, tid, T); break;
-			case 4: stockham_pass<4>(in, out, N, Ns, magic, tw, tid, T); break;
-			case 5: stockham_pass<5>(in, out, N, Ns, magic, tw, tid, T); break;
-			case 7: stockham_pass<7>(in, out, N, Ns, magic, tw, tid, T); break;
-			case 8: stockham_pass<8>(in, out, N, Ns, magic, tw, tid, T); break;
-			case 11: stockham_pass<11>(in, out, N, Ns, magic, tw, tid, T); break;
-			default: stockham_pass<13>(in, out, N, Ns, magic, tw, tid, T); break;
+			const float2* tw = stw + a.twOff[ps];
+			if (active) {
+				switch (R) {
+				case 2: stockham_pass<2>(in, out, N, Ns, magic, tw, tid, T); break;
+				case 3: stockham_pass<3>(in, out, N, Ns, magic, tw, tid, T); break;
+				case 4: stockham_pass<4>(in, out, N, Ns, magic, tw, tid, T); break;
+				case 5: stockham_pass<5>(in, out, N, Ns, magic, tw, tid, T); break;
+				case 7: stockham_pass<7>(in, out, N, Ns, magic, tw, tid, T); break;
+				case 8: stockham_pass<8>(in, out, N, Ns, magic, tw, tid, T); break;
+				case 11: stockham_pass<11>(in, out, N, Ns, magic, tw, tid, T); break;
+				default: stockham_pass<13>(in, out, N, Ns, magic, tw, tid, T); break;
+				}
 			}
 			Ns *= R;
 			__syncthreads();
@@ -252,24 +277,26 @@ __global__ void __launch_bounds__(256) oct_generic_kernel(const GenericArgs a) {
 		}
 
 		/* ---- epilogue (bins z < N/2), from `in` = the buffer the last pass wrote ---- */
-		if (a.cplxOut != nullptr) {
-			float2* o = a.cplxOut + (size_t)gline * H;
-			for (int z = tid; z < H; z += T) o[z] = in[gpad(z)];
-		} else {
-			int b = gline / a.A, al = gline - b * a.A;
-			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u && (unsigned)b + a.bscanBase < a.flipEnd) al = a.A - 1 - al;
-			float* o = a.out + ((size_t)b * a.A + al) * H;
-			const EpiConsts e = a.epi;
-			for (int z = tid; z < H; z += T) {
-				float2 d = in[gpad(z)];
-				if (e.fpn) d = csub(d, __ldg(a.meanLine + z));
-				const float pw = fmaf(d.x, d.x, d.y * d.y);
-				float v = e.logMode ? fmaf(oct_lg2(pw), e.scaleA, e.scaleB) : fmaf(oct_sqrt(pw), e.scaleA, e.scaleB);
-				if (e.ppbg) v = saturate01(v - fmaf(e.ppbgWeight, __ldg(a.ppbg + z), e.ppbgOffset));
-				o[z] = v;
+		if (active) {
+			if (a.cplxOut != nullptr) {
+				float2* o = a.cplxOut + (size_t)gline * H;
+				for (int z = tid; z < H; z += T) o[z] = in[gpad(z)];
+			} else {
+				int b = gline / a.A, al = gline - b * a.A;
+				if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u && (unsigned)b + a.bscanBase < a.flipEnd) al = a.A - 1 - al;
+				float* o = a.out + ((size_t)b * a.A + al) * H;
+				const EpiConsts e = a.epi;
+				for (int z = tid; z < H; z += T) {
+					float2 d = in[gpad(z)];
+					if (e.fpn) d = csub(d, __ldg(a.meanLine + z));
+					const float pw = fmaf(d.x, d.x, d.y * d.y);
+					float v = e.logMode ? fmaf(oct_lg2(pw), e.scaleA, e.scaleB) : fmaf(oct_sqrt(pw), e.scaleA, e.scaleB);
+					if (e.ppbg) v = saturate01(v - fmaf(e.ppbgWeight, __ldg(a.ppbg + z), e.ppbgOffset));
+					o[z] = v;
+				}
 			}
 		}
-		__syncthreads();          /* both line buffers are free again before the next line's conversion writes into B */
+		__syncthreads();          /* both line buffers are free again before the next batch's conversion writes into B */
 	}
 }
 
@@ -317,24 +344,35 @@ void generic_fill_twiddles(const int* radix, int nPass, const int* twOff, float2
 	}
 }
 
+/* CTA shape: TT threads per line by the line length; as many line teams as fit a 512-thread CTA and ~110 KB of shared memory (two CTAs
+ * per SM), at least one.  OCTB200_GENERIC_LB overrides the team count (experiments). */
+static void generic_shape(int N, int HB, int HA, int rawBytes, bool roll, int twEntries, int* TT, int* LB, int* smemBytes) {
+	const int tt = N >= 2048 ? 256 : (N >= 1024 ? 128 : 64);
+	int lb = 512 / tt;
+	const char* env = getenv("OCTB200_GENERIC_LB");
+	if (env && atoi(env) > 0 && atoi(env) * tt <= 512) lb = atoi(env);
+	else while (lb > 1 && generic_smem_layout(N, HB, HA, rawBytes, roll, lb, twEntries).total > 112 * 1024) lb >>= 1;
+	while (lb > 1 && generic_smem_layout(N, HB, HA, rawBytes, roll, lb, twEntries).total > 227 * 1024) lb >>= 1;
+	*TT = tt; *LB = lb; *smemBytes = generic_smem_layout(N, HB, HA, rawBytes, roll, lb, twEntries).total;
+}
+
 template <typename RawT, int SA, bool ROLL>
 static cudaError_t launch_generic_t(const GenericArgs& a, int smCount, cudaStream_t st) {
-	const int SE = a.HB + a.N + a.HA;
-	const int smem = generic_smem_bytes(a.N, SE, (int)sizeof(RawT), ROLL);
+	int TT = 0, LB = 0, smem = 0;
+	generic_shape(a.N, a.HB, a.HA, (int)sizeof(RawT), ROLL, a.twEntries, &TT, &LB, &smem);
 	if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
 	auto k = oct_generic_kernel<RawT, SA, ROLL>;
 	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess) return e;
-	const int threads = a.N >= 2048 ? 256 : (a.N >= 1024 ? 128 : 64);
 	int ctasPerSm = (227 * 1024) / (smem + 1024);
-	const int maxByThreads = 1536 / threads;
+	const int maxByThreads = 2048 / (TT * LB);
 	if (ctasPerSm > maxByThreads) ctasPerSm = maxByThreads;
-	if (ctasPerSm > 16) ctasPerSm = 16;
 	if (ctasPerSm < 1) ctasPerSm = 1;
 	int grid = smCount * ctasPerSm;
-	if (grid > a.lines) grid = a.lines;
+	const int batches = (a.lines + LB - 1) / LB;
+	if (grid > batches) grid = batches;
 	if (grid < 1) grid = 1;
-	k<<<grid, threads, smem, st>>>(a);
+	k<<<grid, dim3(TT, LB), smem, st>>>(a);
 	return cudaGetLastError();
 }
 
@@ -352,8 +390,8 @@ cudaError_t launch_generic(const GenericArgs& a, int rawBytes, int sa, bool roll
 	return launch_generic_raw<uint32_t>(a, sa, roll, smCount, st);
 }
 
-bool generic_fits(int N, int rawBytes, int HB, int HA, bool roll) {
-	return generic_smem_bytes(N, HB + N + HA, rawBytes, roll) <= 227 * 1024;
+bool generic_fits(int N, int rawBytes, int HB, int HA, bool roll, int twEntries) {
+	return generic_smem_layout(N, HB, HA, rawBytes, roll, 1, twEntries).total <= 227 * 1024;
 }
 
 }  // namespace octb200

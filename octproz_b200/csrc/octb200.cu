@@ -92,7 +92,7 @@ struct octb200_pipeline {
 	bool genericOk = false;           /* the shared-memory kernel (k_generic.cu) can transform this line length */
 	float2* dTwN = nullptr;           /* per-pass twiddle tables of the generic kernel */
 	float4* dLutG = nullptr;          /* its natural-order 4-tap table (2 N entries) */
-	int genRadix[16] = {}; int genPasses = 0; int genTwOff[16] = {}; unsigned genMagic[16] = {};
+	int genRadix[16] = {}; int genPasses = 0; int genTwOff[16] = {}; unsigned genMagic[16] = {}; int genTwEntries = 1;
 	float* dSinCurve = nullptr;
 	void* dOutConv[2] = { nullptr, nullptr };
 	int cufftPlan = -1;
@@ -311,7 +311,7 @@ GenericArgs generic_args(const octb200_pipeline* p, const Stage& st, const void*
 	a.shiftBits = p->prm.bitshift ? 4 : 0; a.W = st.W; a.HB = st.HB; a.HA = st.HA;
 	const bool aligned = ((reinterpret_cast<uintptr_t>(dRaw) & 15) == 0) && (((size_t)p->N * p->rawBytes) % 16 == 0) && (((size_t)st.HB * p->rawBytes) % 16 == 0);
 	a.useBulk = aligned ? 1 : 0;
-	a.nPass = p->genPasses;
+	a.nPass = p->genPasses; a.twEntries = p->genTwEntries;
 	for (int i = 0; i < 16; ++i) { a.radix[i] = p->genRadix[i]; a.twOff[i] = p->genTwOff[i]; a.magic[i] = p->genMagic[i]; }
 	return a;
 }
@@ -392,7 +392,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		fused_launch_shape(p->R, st.sa, st.roll, SRC_RAW16, st.HB, st.HA, p->smCount, p->lines, &g, &t, &sm);
 		if (t < 32 * p->R) mode = OCTB200_FFT_SPLIT;
 	} else if (mode == OCTB200_FFT_FUSED) {
-		generic = generic_fits(p->N, p->rawBytes, st.HB, st.HA, st.roll);
+		generic = generic_fits(p->N, p->rawBytes, st.HB, st.HA, st.roll, p->genTwEntries);
 		if (!generic) mode = OCTB200_FFT_CUFFT;
 	}
 	if (mode != OCTB200_FFT_FUSED) { int rc = ensure_fft_buffer(p); if (rc) return rc; }
@@ -603,7 +603,11 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	p->inBytes = p->packed12 ? (size_t)S * 3 / 2 : (size_t)S * p->rawBytes;
 	const bool fftSize = (p->N == 1024 || p->N == 2048);
 	p->regKernel = fftSize && p->rawBytes == 2;
-	p->genericOk = !p->packed12 && generic_fft_plan(p->N, p->genRadix, &p->genPasses) && generic_fits(p->N, p->rawBytes, 0, 0, false);
+	p->genericOk = !p->packed12 && generic_fft_plan(p->N, p->genRadix, &p->genPasses);
+	if (p->genericOk) {
+		p->genTwEntries = generic_twiddle_layout(p->N, p->genRadix, p->genPasses, p->genTwOff, p->genMagic);
+		p->genericOk = generic_fits(p->N, p->rawBytes, 0, 0, false, p->genTwEntries);
+	}
 	int mode = cfg->fftMode;
 	/* FUSED = one kernel from raw samples to B-scan lines: the register kernels where they apply, else the shared-memory kernel */
 	if (mode == OCTB200_FFT_AUTO) mode = (p->regKernel || p->genericOk) ? OCTB200_FFT_FUSED : (fftSize ? OCTB200_FFT_SPLIT : OCTB200_FFT_CUFFT);
@@ -649,7 +653,7 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	RCC(dalloc(p, &p->dLutB, (size_t)2 * p->N)); RCC(dalloc(p, &p->dLutB1, (size_t)p->N));
 	RCC(dalloc(p, &p->dTw, (size_t)1024)); RCC(dalloc(p, &p->dCtw, (size_t)1024));
 	if (p->genericOk && !p->regKernel) {
-		const int entries = generic_twiddle_layout(p->N, p->genRadix, p->genPasses, p->genTwOff, p->genMagic);
+		const int entries = p->genTwEntries;
 		RCC(dalloc(p, &p->dTwN, (size_t)entries));
 		RCC(dalloc(p, &p->dLutG, (size_t)2 * p->N));
 		std::vector<float2> twn((size_t)entries, make_float2(1.f, 0.f));
