@@ -86,7 +86,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int R, int sa, bool roll,
 	off = align_up(off, 128);
 	L.offGroups = off;
 	const int SE = HB + N + HA;
-	L.slotBytes = (src_is_raw(src)) ? align_up(SE * 2, 128) : 0;
+	L.slotBytes = (src_is_raw(src)) ? align_up(src_line_bytes(src, SE), 128) : 0;
 	int work = R * XBUF_BYTES;
 	if (src_is_raw(src)) {
 		int w2 = align_up((FSLOT_PAD + SE + (R == 2 ? 4 : 0)) * 4, 16) + (roll ? align_up((SE + 1) * 4, 16) : 0);   /* R = 2: head room of the odd half */
@@ -105,12 +105,12 @@ __device__ __forceinline__ void group_sync(int barId) {
 }
 
 /* one lane: start the asynchronous load of raw line `gline` (with halos) into `slot` */
-template <int R, bool HALO, bool PACKED = false>
+template <int R, bool HALO, int SRC = SRC_RAW16>
 __device__ __forceinline__ void issue_line_load(const FusedArgs& a, int gline, unsigned char* slot, uint64_t* bar) {
 	constexpr int N = 1024 * R;
 	if constexpr (!HALO) {
 		/* no halo (every stage but Lanczos): one aligned copy of exactly the line, nothing to clip */
-		constexpr uint32_t LB = PACKED ? (uint32_t)(N * 3 / 2) : (uint32_t)(N * 2);
+		constexpr uint32_t LB = (uint32_t)src_line_bytes(SRC, N);
 		mbar_arrive_expect_tx(bar, LB);
 		bulk_g2s(slot, reinterpret_cast<const unsigned char*>(a.raw) + (size_t)gline * LB, LB, bar);
 		return;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	}
 	__syncthreads();
 	if constexpr (src_is_raw(SRC)) {
-		if (tig == 0 && g0 < a.lines) issue_line_load<R, SA == SA_LANCZOS, SRC == SRC_RAW12P>(a, g0, slot, bar);
+		if (tig == 0 && g0 < a.lines) issue_line_load<R, SA == SA_LANCZOS, SRC>(a, g0, slot, bar);
 	}
 
 #ifdef OCT_STAGGER_NS
@@ -263,6 +263,40 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 				if constexpr (SA == SA_CUBIC) {
 					/* mirrored first tap of the cubic: f[-1] = f[1] (cuda_code.cu:284) */
 					if (tig == 0) fslot[SPLIT ? SPLIT_ODD_BASE - 1 : -1] = f12(s1[0] >> 12);
+				}
+			} else if constexpr (SRC == SRC_RAW8 || SRC == SRC_RAW32) {
+				/* u8 / u32 containers (cuda_code.cu:116-125,136-146): four samples per thread and step, the same float-slot layout as u16 */
+				static_assert(SA != SA_LANCZOS && !ROLL, "u8 / u32 containers: the host takes the split chain for the halo / rolling-mean stages");
+				auto put = [&](int q, float4 c) {
+					if constexpr (SPLIT) {
+						reinterpret_cast<float2*>(fslot)[q] = make_float2(c.x, c.z);
+						reinterpret_cast<float2*>(fslot + SPLIT_ODD_BASE)[q] = make_float2(c.y, c.w);
+					} else {
+						reinterpret_cast<float4*>(fslot)[q] = c;
+					}
+				};
+				const unsigned sh = (unsigned)a.shiftBits;
+				if constexpr (SRC == SRC_RAW8) {
+					const unsigned* s1 = reinterpret_cast<const unsigned*>(slot);
+					unsigned w8[8];
+#pragma unroll
+					for (int i = 0; i < 8; ++i) w8[i] = s1[tig + 32 * R * i];
+					const unsigned msk = (0xFFu >> sh) * 0x01010101u;
+#pragma unroll
+					for (int i = 0; i < 8; ++i) {
+						const unsigned w = (w8[i] >> sh) & msk;
+						put(tig + 32 * R * i, make_float4(u8_to_float<0>(w), u8_to_float<1>(w), u8_to_float<2>(w), u8_to_float<3>(w)));
+					}
+					if constexpr (SA == SA_CUBIC) { if (tig == 0) fslot[SPLIT ? SPLIT_ODD_BASE - 1 : -1] = (float)(slot[1] >> sh); }
+				} else {
+					const uint4* s4 = reinterpret_cast<const uint4*>(slot);
+					auto c32 = [&](unsigned v) { return sh ? (float)((double)v / 4294967296.0) : __uint2float_rd(v); };      /* cuda_code.cu:124,144 */
+#pragma unroll 2
+					for (int i = 0; i < 8; ++i) {
+						const uint4 w = s4[tig + 32 * R * i];
+						put(tig + 32 * R * i, make_float4(c32(w.x), c32(w.y), c32(w.z), c32(w.w)));
+					}
+					if constexpr (SA == SA_CUBIC) { if (tig == 0) fslot[SPLIT ? SPLIT_ODD_BASE - 1 : -1] = c32(reinterpret_cast<const unsigned*>(slot)[1]); }
 				}
 			} else {
 				const uint2* s2 = reinterpret_cast<const uint2*>(slot);
@@ -332,7 +366,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			}
 			group_sync<R>(barId);
 			/* raw slot consumed: refill it with the next line of this group */
-			if (tig == 0 && glineNext < a.lines) issue_line_load<R, SA == SA_LANCZOS, SRC == SRC_RAW12P>(a, glineNext, slot, bar);
+			if (tig == 0 && glineNext < a.lines) issue_line_load<R, SA == SA_LANCZOS, SRC>(a, glineNext, slot, bar);
 			if constexpr (ROLL) {
 				const int W = a.W;
 				for (int q = tig; q < SE; q += 32 * R) {

@@ -7,12 +7,18 @@ cudaError_t launch_fused_raw12(int R, int sa, const FusedArgs& a, int smCount, c
 cudaError_t launch_fused_raw_r1_conv(int sa, bool roll, const FusedArgs& a, int smCount, cudaStream_t st);
 cudaError_t launch_fused_raw_r2_conv(int sa, bool roll, const FusedArgs& a, int smCount, cudaStream_t st);
 cudaError_t launch_fused_raw12_conv(int R, int sa, const FusedArgs& a, int smCount, cudaStream_t st);
+cudaError_t launch_fused_raw8(int R, int sa, const FusedArgs& a, int smCount, cudaStream_t st);
+cudaError_t launch_fused_raw32(int R, int sa, const FusedArgs& a, int smCount, cudaStream_t st);
 
 cudaError_t launch_fused(int R, int sa, bool roll, int src, const FusedArgs& a, int smCount, cudaStream_t st) {
 	if (src == SRC_CPLX) {
 		if (a.convOut) return cudaErrorInvalidValue;      /* the converted output is only folded into the raw-source kernels */
 		if (R == 1) return launch_fused_t<1, SA_NONE, false, SRC_CPLX>(a, smCount, st);
 		return launch_fused_t<2, SA_NONE, false, SRC_CPLX>(a, smCount, st);
+	}
+	if (src == SRC_RAW8 || src == SRC_RAW32) {
+		if (a.convOut || roll) return cudaErrorInvalidConfiguration;      /* converted output / rolling mean: u16 kernels only */
+		return src == SRC_RAW8 ? launch_fused_raw8(R, sa, a, smCount, st) : launch_fused_raw32(R, sa, a, smCount, st);
 	}
 	if (a.convOut) {
 		if (src == SRC_RAW12P) return roll ? cudaErrorInvalidConfiguration : launch_fused_raw12_conv(R, sa, a, smCount, st);

@@ -48,6 +48,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
  * __uint2float_rd(in[index]) of inputToCufftComplex (cuda_code.cu:118-121). */
 __device__ __forceinline__ float u16lo_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.0f; }
 __device__ __forceinline__ float u16hi_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f; }
+/* byte B of a word -> fp32, the same way (u8 containers) */
+template <int B> __device__ __forceinline__ float u8_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | B)) - 8388608.0f; }
 
 /* ---------------- en-face gather over peer memory, fused into the epilogue (multi-GPU shards) ----------------
  * world > 0: the lane that finalises depth bin frameNr of a line (updateDisplayedEnFaceFrame with one frame, cuda_code.cu:909)
@@ -165,7 +167,9 @@ struct FusedArgs {
 /* where a line comes from: u16 containers (the reference's raw format), float2 FFT input written by the pre-FFT kernel, or
  * 12-bit samples packed little-endian, two per three bytes (GenICam "Mono12p": an extension -- the reference only takes containers,
  * docs/docs/faq.md -- that cuts the PCIe / HBM input bytes by a quarter) */
-enum { SRC_RAW16 = 0, SRC_CPLX = 1, SRC_RAW12P = 2 };
-__host__ __device__ constexpr bool src_is_raw(int src) { return src == SRC_RAW16 || src == SRC_RAW12P; }
+enum { SRC_RAW16 = 0, SRC_CPLX = 1, SRC_RAW12P = 2, SRC_RAW8 = 3, SRC_RAW32 = 4 };      /* RAW8 / RAW32: u8 / u32 containers (cuda_code.cu:116-125) */
+__host__ __device__ constexpr bool src_is_raw(int src) { return src == SRC_RAW16 || src == SRC_RAW12P || src == SRC_RAW8 || src == SRC_RAW32; }
+/* bytes of one raw line of n samples in the TMA slot */
+__host__ __device__ constexpr int src_line_bytes(int src, int n) { return src == SRC_RAW8 ? n : (src == SRC_RAW32 ? 4 * n : (src == SRC_RAW12P ? n * 3 / 2 : 2 * n)); }
 
 }  // namespace octb200

@@ -386,11 +386,14 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 
 	int mode = p->mode;
 	bool generic = false;              /* FUSED by the shared-memory kernel (line lengths / containers the register kernels do not take) */
+	/* where the register kernel reads its lines from: u16 containers, 12-bit packed, or u8 / u32 containers */
+	int rawSrc = p->rawBytes == 1 ? SRC_RAW8 : (p->rawBytes == 4 ? SRC_RAW32 : SRC_RAW16);
 	if (mode == OCTB200_FFT_FUSED && p->regKernel) {
-		/* a huge rolling window with Lanczos halos may not fit the fused kernel's shared memory */
+		/* a huge rolling window with Lanczos halos may not fit the fused kernel's shared memory; the u8 / u32 slot conversions exist for
+		   the 4-tap and plain stages without rolling mean -- everything else takes the split chain (pre kernel + register FFT kernel) */
 		int g = 0, t = 0, sm = 0;
 		fused_launch_shape(p->R, st.sa, st.roll, SRC_RAW16, st.HB, st.HA, p->smCount, p->lines, &g, &t, &sm);
-		if (t < 32 * p->R) mode = OCTB200_FFT_SPLIT;
+		if (t < 32 * p->R || (rawSrc != SRC_RAW16 && (st.roll || st.sa == SA_LANCZOS))) mode = OCTB200_FFT_SPLIT;
 	} else if (mode == OCTB200_FFT_FUSED) {
 		generic = generic_fits(p->N, p->rawBytes, st.HB, st.HA, st.roll, p->genTwEntries);
 		if (!generic) mode = OCTB200_FFT_CUFFT;
@@ -399,7 +402,6 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 
 	/* 12-bit packed input: the fused kernel unpacks it in its slot conversion (4-tap / plain stage, no rolling mean); every other
 	   stage reads u16 containers, so the buffer is unpacked once into HBM first */
-	int rawSrc = SRC_RAW16;
 	if (p->packed12) {
 		if (mode == OCTB200_FFT_FUSED && st.sa != SA_LANCZOS && !st.roll) rawSrc = SRC_RAW12P;
 		else {
@@ -602,7 +604,7 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	}
 	p->inBytes = p->packed12 ? (size_t)S * 3 / 2 : (size_t)S * p->rawBytes;
 	const bool fftSize = (p->N == 1024 || p->N == 2048);
-	p->regKernel = fftSize && p->rawBytes == 2;
+	p->regKernel = fftSize;             /* u16 directly; u8 / u32 containers through the SRC_RAW8 / SRC_RAW32 slot conversions (4-tap and plain stages) */
 	p->genericOk = !p->packed12 && generic_fft_plan(p->N, p->genRadix, &p->genPasses);
 	if (p->genericOk) {
 		p->genTwEntries = generic_twiddle_layout(p->N, p->genRadix, p->genPasses, p->genTwOff, p->genMagic);
@@ -610,7 +612,11 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	}
 	int mode = cfg->fftMode;
 	/* FUSED = one kernel from raw samples to B-scan lines: the register kernels where they apply, else the shared-memory kernel */
-	if (mode == OCTB200_FFT_AUTO) mode = (p->regKernel || p->genericOk) ? OCTB200_FFT_FUSED : (fftSize ? OCTB200_FFT_SPLIT : OCTB200_FFT_CUFFT);
+	/* AUTO: the register kernels wherever they apply; the shared-memory kernel where it beats the cuFFT chain on a B200 (measured,
+	   profiles/r02f_generic_perf.json: line lengths that are not a power of two, and N > 2048; for short power-of-two lines the three
+	   kernel chain around cuFFT is as fast or faster); the cuFFT chain otherwise.  An explicit FUSED is honoured wherever a fused kernel exists. */
+	const bool pow2 = (p->N & (p->N - 1)) == 0;
+	if (mode == OCTB200_FFT_AUTO) mode = p->regKernel ? OCTB200_FFT_FUSED : ((p->genericOk && (!pow2 || p->N > 2048)) ? OCTB200_FFT_FUSED : OCTB200_FFT_CUFFT);
 	if ((mode == OCTB200_FFT_FUSED && !(p->regKernel || p->genericOk)) || (mode == OCTB200_FFT_SPLIT && !fftSize) ||
 	    mode < OCTB200_FFT_FUSED || mode > OCTB200_FFT_CUFFT) {
 		delete p;
@@ -1050,7 +1056,7 @@ int octb200_enface_gather_close(octb200_pipeline* p) {
 int octb200_dispersion_sweep(octb200_pipeline* p, const void* raw, const octb200_sweep_config* c, const float* coeffs, float* metricsOut, float* ascansOut) {
 	if (!p || !raw || !c || !coeffs || !metricsOut) return fail(p, OCTB200_ERR_INVALID, "null argument");
 	if (c->lines < 1 || c->trials < 1 || c->trials > 65535 || c->metric < 0 || c->metric > 3) return fail(p, OCTB200_ERR_INVALID, "bad sweep configuration");
-	if (!p->regKernel)
+	if (!p->regKernel || p->rawBytes != 2)
 		return fail(p, OCTB200_ERR_INVALID, "the dispersion sweep runs on the fused kernel: 1024 or 2048 samples per line in a 16-bit container");
 	if (c->logScale && !(c->logMax != c->logMin)) return fail(p, OCTB200_ERR_INVALID, "log scaling needs max != min");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
@@ -1165,7 +1171,10 @@ int octb200_time_kernel(octb200_pipeline* p, const void* dRaw, int iters, float*
 			ga.out = slab; ga.epi = epi_for(p, fpn && p->fpnDetermined, false);
 			CK(p, launch_generic(ga, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute));
 		} else {
-			const int src = (p->mode == OCTB200_FFT_FUSED) ? ((p->packed12 && st.sa != SA_LANCZOS && !st.roll) ? SRC_RAW12P : SRC_RAW16) : SRC_CPLX;
+			const int container = p->rawBytes == 1 ? SRC_RAW8 : (p->rawBytes == 4 ? SRC_RAW32 : SRC_RAW16);
+			if (p->mode == OCTB200_FFT_FUSED && container != SRC_RAW16 && (st.roll || st.sa == SA_LANCZOS))
+				return fail(p, OCTB200_ERR_INVALID, "time_kernel: this stage of a u8 / u32 container runs on the split chain, not on the fused kernel");
+			const int src = (p->mode == OCTB200_FFT_FUSED) ? ((p->packed12 && st.sa != SA_LANCZOS && !st.roll) ? SRC_RAW12P : container) : SRC_CPLX;
 			if (p->packed12 && src != SRC_RAW12P) return fail(p, OCTB200_ERR_INVALID, "time_kernel: packed input is only timed on the direct fused path");
 			if (src == SRC_CPLX) { int rc = ensure_fft_buffer(p); if (rc) return rc; }
 			FusedArgs fa = fused_args(p, st, dRaw, p->lines);

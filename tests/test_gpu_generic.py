@@ -43,8 +43,8 @@ def test_line_lengths_match_the_oracle_in_one_launch(n):
     q.update_all_curves()
     raw = synth.make_volume(n, a, b, 12, resample=q.resampleCurve, dispersion=q.dispersionCurve)
     ref, _, _ = orc.process(q, raw)
-    out, _, eff, launches = run(q, raw, _lib.FFT_AUTO)
-    assert eff == _lib.FFT_FUSED, "AUTO must pick the fused path for this line length"
+    out, _, eff, launches = run(q, raw, _lib.FFT_FUSED)
+    assert eff == _lib.FFT_FUSED
     # the first call also builds the phasor table (one fill_phase launch); the chain itself is one kernel
     assert launches <= 2, launches
     assert_parity(out, ref, q, max_frac_outside=1e-4, what=f"generic fused kernel N={n}")
@@ -81,20 +81,65 @@ def test_stage_variants_at_the_default_geometry(n, name):
                   atol_abs=4e-6 * float(np.abs(ml).max()) if q.fixedPatternNoiseRemoval else 0.0)
 
 
-@pytest.mark.parametrize("bits,n", [(8, 1024), (8, 1664), (32, 1024), (32, 2048), (32, 1664), (24, 512)])
-def test_u8_and_u32_containers_take_the_fused_path(bits, n):
-    """round 1 sent u8 / u32 containers through the three-kernel chain; they are one launch now, also at N = 1024 / 2048"""
+@pytest.mark.parametrize("bits,n", [(8, 1024), (8, 2048), (8, 1664), (32, 1024), (32, 2048), (32, 1664), (24, 512), (20, 1024)])
+def test_u8_and_u32_containers_take_a_fused_path(bits, n):
+    """round 1 sent u8 / u32 containers through the three-kernel chain; they are one launch now: N = 1024 / 2048 through the register
+    kernel's SRC_RAW8 / SRC_RAW32 slot conversions, other lengths through the shared-memory kernel"""
     q = benchmark_params(n, 8, 2, bits); q.fixedPatternNoiseRemoval = False; q.update_all_curves()
     raw = synth.make_volume(n, 8, 2, min(bits, 20), resample=q.resampleCurve, dispersion=q.dispersionCurve).astype(synth.container_dtype(bits))
     ref, _, _ = orc.process(q, raw)
-    out, _, eff, launches = run(q, raw, _lib.FFT_AUTO)
+    out, _, eff, launches = run(q, raw, _lib.FFT_FUSED)
     assert eff == _lib.FFT_FUSED and launches <= 2
-    assert_parity(out, ref, q, max_frac_outside=1e-4, what=f"generic bits={bits} N={n}")
-    if bits == 32:
+    assert_parity(out, ref, q, max_frac_outside=1e-4, what=f"fused, container of {bits} bits, N={n}")
+    if bits > 16:
         q.bitshift = True
         ref, _, _ = orc.process(q, raw)
-        out, _, _, _ = run(q, raw, _lib.FFT_AUTO)
-        assert_parity(out, ref, q, max_frac_outside=1e-4, what=f"generic u32 bitshift N={n}")
+        out, _, _, _ = run(q, raw, _lib.FFT_FUSED)
+        assert_parity(out, ref, q, max_frac_outside=1e-4, what=f"fused, u32 bitshift, N={n}")
+
+
+CONTAINER_VARIANTS = {
+    "linear": dict(resamplingInterpolation=0), "noresample": dict(resampling=False), "fft_only": dict(resampling=False, windowing=False, dispersionCompensation=False),
+    "flip_sinus": dict(bscanFlip=True, sinusoidalScanCorrection=True), "linscale": dict(signalLogScaling=False, signalGrayscaleMin=0.0, signalGrayscaleMax=40.0),
+    "bitshift": dict(bitshift=True), "fpn": dict(fixedPatternNoiseRemoval=True),
+    # the container kernels cover the 4-tap and plain stages; these two take the split chain (pre kernel + register FFT kernel) and must still be right
+    "lanczos": dict(resamplingInterpolation=2), "rolling16": dict(backgroundRemoval=True, rollingAverageWindowSize=16),
+}
+
+
+@pytest.mark.parametrize("name", list(CONTAINER_VARIANTS))
+@pytest.mark.parametrize("bits,n", [(8, 1024), (8, 2048), (32, 1024), (32, 2048)])
+def test_container_kernels_stage_variants(bits, n, name):
+    a, b = 20, 3
+    q = benchmark_params(n, a, b, bits); q.fixedPatternNoiseRemoval = False
+    for k, v in CONTAINER_VARIANTS[name].items():
+        setattr(q, k, v)
+    q.update_all_curves()
+    raw = synth.make_volume(n, a, b, min(bits, 20), resample=q.resampleCurve, dispersion=q.dispersionCurve).astype(synth.container_dtype(bits))
+    ref, ml, _ = orc.process(q, raw)
+    out, _, eff, launches = run(q, raw, _lib.FFT_AUTO, mean_line=ml if q.fixedPatternNoiseRemoval else None)
+    assert eff == _lib.FFT_FUSED
+    lanczos = q.resampling and q.resamplingInterpolation == 2
+    assert_parity(out, ref, q, atol_frac=2e-2 if lanczos else 1e-4, max_frac_outside=1e-4, what=f"container of {bits} bits, N={n}, {name}",
+                  atol_abs=4e-6 * float(np.abs(ml).max()) if q.fixedPatternNoiseRemoval else 0.0)
+    # bit-identical to the u16 kernel on the same values wherever those fit a u16 container
+    if bits == 8 and name not in ("lanczos", "rolling16"):
+        q16 = copy.deepcopy(q); q16.bitDepth = 16
+        out16, _, _, _ = run(q16, raw.astype(np.uint16), _lib.FFT_FUSED, mean_line=ml if q.fixedPatternNoiseRemoval else None)
+        assert np.array_equal(out, out16), "u8 container kernel differs from the u16 kernel on the same sample values"
+
+
+def test_auto_mode_policy():
+    """AUTO: register kernels for 1024 / 2048 (every container); the shared-memory kernel where it beats the cuFFT chain (not a power of
+    two, or N > 2048); the cuFFT chain for short power-of-two lines and for lengths with large prime factors"""
+    want = {(1024, 12): _lib.FFT_FUSED, (2048, 8): _lib.FFT_FUSED, (1024, 32): _lib.FFT_FUSED, (1664, 12): _lib.FFT_FUSED, (4096, 12): _lib.FFT_FUSED,
+            (1536, 8): _lib.FFT_FUSED, (512, 12): _lib.FFT_CUFFT, (256, 12): _lib.FFT_CUFFT, (1006, 12): _lib.FFT_CUFFT}
+    for (n, bits), mode in want.items():
+        q = benchmark_params(n, 4, 2, bits); q.update_all_curves()
+        p = OctPipeline(fft_mode=_lib.FFT_AUTO)
+        assert p.initializeCuda(None, None, q), getattr(p, "_create_error", "")
+        assert p.fft_mode == mode, (n, bits, p.fft_mode)
+        p.cleanupCuda()
 
 
 def test_lengths_with_large_prime_factors_keep_the_cufft_chain():
@@ -119,7 +164,7 @@ def test_matches_the_live_reference_cuda_build(shape):
     q.update_all_curves()
     raw = synth.make_volume(n, a, b, bits, resample=q.resampleCurve, dispersion=q.dispersionCurve)
     ref, ref_ml = reference_run(q, raw)
-    out, _, eff, _ = run(q, raw, _lib.FFT_AUTO, mean_line=ref_ml)
+    out, _, eff, _ = run(q, raw, _lib.FFT_FUSED, mean_line=ref_ml)
     assert eff == _lib.FFT_FUSED
     assert_parity(out, ref, q, max_frac_outside=1e-4, what=f"generic fused kernel vs live reference {shape}", atol_abs=4e-6 * float(np.abs(ref_ml).max()))
     # own determination through the generic kernel's complex-output pass
