@@ -31,12 +31,14 @@ def _ptr(x) -> int:
 
 
 def device_copy(dst, src_ptr: int, nbytes: int) -> None:
-    """copy `nbytes` from a raw device address (e.g. the frame octb200_enface_gather_wait returns) into a torch CUDA tensor"""
+    """copy `nbytes` from a raw device address (e.g. the frame octb200_enface_gather_wait returns) into a torch CUDA tensor; the raw
+    memory is wrapped through the CUDA array interface, the copy runs on torch's current stream (synchronise the pipeline first)"""
     import torch
-    rt = torch.cuda.cudart()
-    err = rt.cudaMemcpy(int(dst.data_ptr()), int(src_ptr), int(nbytes), 3)     # cudaMemcpyDeviceToDevice
-    if int(err) != 0:
-        raise _lib.Octb200Error(f"cudaMemcpy failed: {err}")
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(src_ptr), False), "version": 2}
+    src = torch.as_tensor(_Raw(), device=dst.device)
+    dst.view(torch.uint8).reshape(-1)[: int(nbytes)].copy_(src)
 
 
 class OctPipeline:
