@@ -309,6 +309,8 @@ def timed_resident(rig, steps, warmup, dist, step_fn):
     p.event_record(0)
     for i in range(steps):
         step_fn(i)
+    if rig.gather == "p2p":
+        p.enface_gather_wait()             # the compute stream waits for the consumer kernel of the LAST frame: every frame of the region was consumed inside it
     p.event_record(1)
     ms_total = p.event_elapsed_ms(0, 1)
     sync_all()
@@ -520,10 +522,10 @@ def main():
         gather_impl = "nccl" if args.enface == "nccl" else rig.connect_gather(dist, world * a * b, rank * a * b)
 
     def step_resident(i, r=rig, frame=enface, out=gathered):
+        # p2p: the process call itself gathers (peer stores from the kernel's epilogue) and enqueues the consumer kernel of this frame
+        # (wait for every rank's slab, copy the frame out, acknowledge) on the handle's display stream
         r.p.process_device(r.d_raw[i & 1])
-        if gather_impl == "p2p":
-            r.p.enface_gather_wait()       # stream-ordered: wait for every rank's slab, copy the frame out, acknowledge
-        elif gather_impl == "nccl":
+        if gather_impl == "nccl":
             r.p.changeDisplayedEnFaceFrame(100, 1, 0, frame)
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(out, frame)
@@ -555,7 +557,7 @@ def main():
                 "traffic": traffic, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
 
     # ---- end to end through octCudaPipeline(host buffer) ----
-    e2e_hook = (lambda i: p.enface_gather_wait()) if gather_impl == "p2p" else None
+    e2e_hook = None
     e2e_s, e2e_steps, e2e_launches, checksum = e2e_leg(rig, args.steps, args.warmup, dist, conv_bytes, e2e_hook)
     clocks = sampler.stop()
     e2e_mhz = world * ascans_per_step * e2e_steps / e2e_s / 1e6
@@ -580,9 +582,7 @@ def main():
 
         def step_strong(i):
             rs.p.process_device(rs.d_raw[i & 1])
-            if g2 == "p2p":
-                rs.p.enface_gather_wait()
-            else:
+            if g2 != "p2p":
                 rs.p.changeDisplayedEnFaceFrame(100, 1, 0, en_s)
                 with torch.cuda.stream(torch.cuda.ExternalStream(int(rs.p._lib.octb200_compute_stream(rs.p.handle)), device=torch.device("cuda", local))):
                     dist.all_gather_into_tensor(ga_s, en_s)
@@ -647,7 +647,7 @@ def main():
             "volumes_per_s": value * 1e6 / ascans_per_step, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours", "config": config, "mode": args.mode,
-            "gather": None if world == 1 else {"impl": gather_impl, "every_step": "peer-memory stores from the fused kernel's epilogue + consume (wait, copy out, acknowledge)"
+            "gather": None if world == 1 else {"impl": gather_impl, "every_step": "peer-memory stores from the fused kernel's epilogue + consumer kernel (wait for all slabs, copy out, acknowledge) on the display stream"
                                                if gather_impl == "p2p" else "extraction kernel + ncclAllGather", "check": gcheck},
             "e2e": {"value": e2e_mhz, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": conv_bytes,
                     "ms_per_step": e2e_s * 1e3 / e2e_steps, "steps": e2e_steps, "timer": "host wall clock between device synchronisations, max over ranks",

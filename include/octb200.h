@@ -64,7 +64,11 @@ enum { OCTB200_PACK_CONTAINER = 0, OCTB200_PACK_12P = 1 };
 /* octb200_config.flags.  SEPARATE_CONVERSION: run floatToOutput (cuda_code.cu:943-967) as its own pass over the finished slab, as
    the reference does (cuda_code.cu:1366), instead of writing the converted u16 line from the fused kernel's epilogue (the default
    when the slab is final after that kernel; results are bit-identical, the flag exists for A/B measurement) */
-enum { OCTB200_FLAG_SEPARATE_CONVERSION = 1 };
+enum { OCTB200_FLAG_SEPARATE_CONVERSION = 1,
+       /* NO_DEPENDENT_LAUNCH: back-to-back buffers are normally launched with programmatic stream serialization (the next buffer's
+          kernel prologue -- tensor-memory allocation, table fill, first line load -- overlaps the previous kernel's tail; results are
+          identical).  The flag launches every kernel plainly (A/B measurement) */
+       OCTB200_FLAG_NO_DEPENDENT_LAUNCH = 2 };
 
 /* which kernels run the FFT stage */
 enum {
@@ -229,19 +233,21 @@ OCTB200_API int octb200_float_to_output(octb200_pipeline* p, uint32_t bufferNrIn
      connect : handles = world * 64 bytes, rank-major; opens every peer window
      gather  : enqueue extraction + peer stores + flag publication on the compute stream, then the consumer side for the same
                sequence number: wait for ALL ranks' slabs, copy the assembled frame into this rank's private display frame and
-               acknowledge to every producer.  Frame buffers in the windows are double-buffered by sequence number; a producer only
-               overwrites a buffer after every rank has acknowledged the frame it held (flow control in the kernels' prologue), so a
-               rank that runs ahead can never tear a frame a slower rank is still reading.  COLLECTIVE: every rank must issue the
-               same sequence of gathers; a rank that stops gathering stalls its peers two gathers later -- for at most 10 s per
-               launch: every device-side wait has a time-out that is counted (status) instead of hanging
+               acknowledge to every producer -- on the handle's own display stream, so the compute stream goes straight on to the
+               next buffer.  The windows hold three frame buffers used round-robin by sequence number; a producer only overwrites a
+               buffer after every rank has acknowledged the frame it held (flow control in the kernels' prologue), so a rank that
+               runs ahead can never tear a frame a slower rank is still reading.  COLLECTIVE: every rank must issue the same
+               sequence of gathers; a rank that stops gathering stalls its peers three gathers later -- for at most 10 s per launch:
+               every device-side wait has a time-out that is counted (status) instead of hanging
      auto    : from now on EVERY octb200_process_* call also gathers frame (frameNr, frames, function) of the buffer it produced.
                When one depth frame is displayed and the slab is final after the fused kernel (single-slab volume, no sinusoidal
                correction, no background recording) the extraction and the peer stores happen inside that kernel's epilogue, spread
                over the whole kernel (a line group stores the values of up to 8 neighbouring lines with one coalesced store per
                rank; no end-of-kernel push, no grid-wide barrier) -- compute and collective in one launch; otherwise the stand-alone
                gather kernel is appended to the chain
-     wait    : *dFrame = device pointer of this rank's display frame [globalLines] floats, reference order disp[(E-1)-i]; valid
-               (stream ordered on the compute stream) until the next gather.  The consumer kernel was already enqueued by gather
+     wait    : *dFrame = device pointer of this rank's display frame [globalLines] floats, reference order disp[(E-1)-i]; the
+               compute stream is made to wait for the consumer kernel of the latest gather, so work enqueued on it after this call
+               sees that frame; it stays valid until the consumer kernel of the next gather runs
      status  : sequence number of the latest gather and the number of time-outs so far (0 / 0 in a healthy run); synchronises
      close   : release (collective in spirit: call after a barrier, peers must have stopped gathering) */
 #define OCTB200_IPC_HANDLE_BYTES 64

@@ -36,6 +36,7 @@ FFT_AUTO, FFT_FUSED, FFT_SPLIT, FFT_CUFFT = 0, 1, 2, 3
 INTERP_LINEAR, INTERP_CUBIC, INTERP_LANCZOS = 0, 1, 2
 PACK_CONTAINER, PACK_12P = 0, 1
 FLAG_SEPARATE_CONVERSION = 1
+FLAG_NO_DEPENDENT_LAUNCH = 2
 
 
 class Config(C.Structure):

@@ -424,11 +424,11 @@ cudaError_t launch_enface_frame(float* disp, const float* vol, unsigned W, unsig
  * awaited first, the last CTA to finish publishes `seq` in each rank's arrived[] word for this rank (release, system scope). */
 
 __global__ void __launch_bounds__(256) enface_gather_kernel(const EnfaceGatherArgs a) {
-	if (a.world > 1 && a.seq >= 3u) {
+	if (a.world > 0 && a.seq > (unsigned)OCT_GATHER_FRAMES) {
 		if (threadIdx.x == 0) {
 			const unsigned* acks = a.flags[a.rank] + OCT_GATHER_ACK;
 			bool ok = true;
-			for (int c = 0; c < a.world; ++c) ok = gather_spin_ge(acks + c, a.seq - 2u) && ok;
+			for (int c = 0; c < a.world; ++c) ok = gather_spin_ge(acks + c, a.seq - (unsigned)OCT_GATHER_FRAMES) && ok;
 			if (!ok) atomicAdd(a.status, 1u);
 		}
 		__syncthreads();

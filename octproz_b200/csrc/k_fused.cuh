@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(smem + L.offW);
 	if (warp == 0) tmem_alloc(tmemBaseSlot, TmemMap<R>::ALLOC);
 	/* multi-GPU en-face gather: every consumer has released the frame buffer this launch overwrites (flow control, oct_device.cuh) */
-	if (a.eg.world > 1 && threadIdx.x == blockDim.x - 1) gather_wait_acks(a.eg);
+	if (a.eg.world > 0 && threadIdx.x == blockDim.x - 1) gather_wait_acks(a.eg);
 	tmem_fence_before_sync();
 	__syncthreads();
 	tmem_fence_after_sync();
@@ -214,6 +214,10 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	if constexpr (src_is_raw(SRC)) {
 		if (tig == 0 && g0 < a.lines) issue_line_load<R, SA == SA_LANCZOS, SRC>(a, g0, slot, bar);
 	}
+	/* back-to-back buffers: everything above only read tables and the raw input; the previous kernel's output slab, converted lines and
+	 * gather frames are written below.  (No-ops in a plain launch.) */
+	grid_launch_dependents();
+	grid_dependency_wait();
 
 #ifdef OCT_STAGGER_NS
 	/* de-phase the line groups of a CTA so that shared-memory-heavy (stage A) and FMA-heavy (FFT) phases of different

@@ -25,6 +25,16 @@ cudaError_t launch_fused_t(const FusedArgs& a, int smCount, cudaStream_t st) {
 	const int maxGrid = (a.lines + groups - 1) / groups;
 	if (grid > maxGrid) grid = maxGrid;
 	if (grid < 1) grid = 1;
+	if (a.pdl) {
+		/* programmatic dependent launch: this grid's prologue may overlap the tail of the previous main launch (oct_device.cuh) */
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(grid, a.trials > 1 ? a.trials : 1); cfg.blockDim = dim3(groups * R * 32); cfg.dynamicSmemBytes = (size_t)L.total; cfg.stream = st;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = at; cfg.numAttrs = 1;
+		return cudaLaunchKernelEx(&cfg, k, a);
+	}
 	k<<<dim3(grid, a.trials > 1 ? a.trials : 1), groups * R * 32, L.total, st>>>(a);
 	return cudaGetLastError();
 }

@@ -43,6 +43,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+/* ---------------- programmatic dependent launch (back-to-back buffers on one stream) ----------------
+ * launch_dependents: the next kernel in the stream (launched with the programmatic-serialization attribute) may become resident as soon as
+ * SMs free up, i.e. its prologue (tensor-memory allocation, table fill, first line load) overlaps this kernel's tail; it calls
+ * grid_dependency_wait before it touches anything the previous kernel writes.  Both are no-ops in a plain launch. */
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 /* ---------------- exact u16 -> fp32 without the conversion pipe ----------------
  * 0x4B000000 | v is the float 2^23 + v; subtracting 2^23 is exact for v < 2^23.  Same value as
  * __uint2float_rd(in[index]) of inputToCufftComplex (cuda_code.cu:118-121). */
@@ -59,15 +66,18 @@ template <int B> __device__ __forceinline__ float u8_to_float(uint32_t w) { retu
  * stores are spread over the whole kernel, there is no end-of-kernel push and no grid barrier: a CTA that has finished its lines
  * fences once at system scope and bumps a counter; the last one publishes `seq` in every rank's "arrived" word for this rank.
  *
- * Window of a rank (octb200.cu EnfaceGather): [64 words arrived[producer]] [64 words ack[consumer]] ... [frame 0] [frame 1].
- * Frames are double-buffered by sequence parity.  Flow control: before a producer stores frame `seq` into a peer's window that
- * peer must have consumed frame seq - 2 (same parity): the consumer's enface_consume_kernel (k_aux.cu) waits for all arrived[]
- * words, copies the frame into its private display buffer and THEN writes ack[consumer] = seq into every producer's window; a
- * producer checks its own (local) ack words in the kernel prologue.  Every spin has a time-out (status word), never a hang.
+ * Window of a rank (octb200.cu EnfaceGather): [64 words arrived[producer]] [64 words ack[consumer]] ... [frame 0] [frame 1] [frame 2].
+ * Frames are used round-robin by sequence number (seq % 3).  Flow control: before a producer stores frame `seq` into a peer's window
+ * that peer must have consumed frame seq - 3 (the previous user of the buffer): the consumer's enface_consume_kernel (k_aux.cu, on
+ * the handle's display stream) waits for all arrived[] words, copies the frame into its private display buffer and THEN writes
+ * ack[consumer] = seq into every producer's window; a producer checks its own (local) ack words in the kernel prologue.  Three
+ * buffers give the consumers a full step of slack: the consume kernel of step s runs beside the compute kernel of step s + 1.
+ * Every spin has a time-out (status word), never a hang.
  * See k_aux.cu enface_gather_kernel for the stand-alone form used for multi-frame averages / MIP and when later passes
  * (sinusoidal correction, background recording) still change the slab. */
 constexpr int OCT_MAX_PEERS = 16;
 constexpr int OCT_GATHER_ARRIVED = 0, OCT_GATHER_ACK = 64, OCT_GATHER_HEADER_BYTES = 1024;
+constexpr int OCT_GATHER_FRAMES = 3;       /* frame buffers per window, used round-robin by sequence number */
 constexpr unsigned long long OCT_GATHER_TIMEOUT_NS = 10ull * 1000ull * 1000ull * 1000ull;
 struct GatherDev {
 	float* frames[OCT_MAX_PEERS];      /* frame window (parity of seq) of every rank */
@@ -99,10 +109,10 @@ __device__ __forceinline__ bool gather_spin_ge(const unsigned* word, unsigned wa
 }
 /* producer prologue (one thread per CTA): every consumer has released the frame buffer this launch is about to overwrite */
 __device__ __forceinline__ void gather_wait_acks(const GatherDev& g) {
-	if (g.world < 2 || g.seq < 3u) return;
+	if (g.world < 1 || g.seq <= (unsigned)OCT_GATHER_FRAMES) return;       /* (also with one rank: its own consumer runs on another stream) */
 	const unsigned* acks = g.flags[g.rank] + OCT_GATHER_ACK;
 	bool ok = true;
-	for (int c = 0; c < g.world; ++c) ok = gather_spin_ge(acks + c, g.seq - 2u) && ok;
+	for (int c = 0; c < g.world; ++c) ok = gather_spin_ge(acks + c, g.seq - (unsigned)OCT_GATHER_FRAMES) && ok;
 	if (!ok) atomicAdd(g.status, 1u);
 }
 /* after a block of `cnt` consecutive lines starting at `firstLine`: lanes 0 .. cnt-1 hold their en-face values */
@@ -150,6 +160,7 @@ struct FusedArgs {
 	int W;
 	int HB, HA;
 	GatherDev eg;            /* eg.world == 0: no en-face gather in this launch */
+	int pdl;                 /* launched with programmatic stream serialization behind another main launch of the same handle */
 	int lineBlock;           /* a line group works through blocks of this many consecutive lines (1, 2, 4, 8; 0 = 1); see GatherDev */
 	unsigned flipEnd;        /* B-scans with (index + bscanBase) >= flipEnd are never flipped: with an odd number of B-scans the reference's
 	                            cuda_bscanFlip leaves the last one alone (cuda_code.cu:794-805 runs over samplesPerBuffer/4 elements) */

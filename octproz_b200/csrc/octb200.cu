@@ -109,6 +109,8 @@ struct octb200_pipeline {
 	void *hostFloat[2] = { nullptr, nullptr }; size_t hostFloatBytes = 0; bool hostFloatRegistered = false; bool hostFloatMine[2] = { false, false };
 	octb200_host_callback cbStreaming = nullptr, cbFloat = nullptr, cbBackground = nullptr;
 	unsigned long long launches = 0;
+	unsigned long long pdlStamp = ~0ull;  /* value of `launches` right after the last main launch of the register kernel: the next main launch
+	                                         may overlap its tail (programmatic dependent launch) only if nothing else was launched since */
 
 	/* dispersion sweep scratch (grown on demand) */
 	unsigned char* dSweepRaw = nullptr; size_t sweepRawBytes = 0;
@@ -128,6 +130,8 @@ struct octb200_pipeline {
 		bool connected = false;
 		unsigned* counter = nullptr;       /* [0] producer kernels, [1] consume kernel, [2..3] status (time-outs: acks, arrivals) */
 		float* display = nullptr;          /* private copy of the last consumed frame */
+		cudaStream_t sConsume = nullptr;   /* the display stream: consumer kernels run beside the next buffer's compute kernel */
+		cudaEvent_t evGathered = nullptr, evConsumed = nullptr;
 		bool autoOn = false;               /* every process call also gathers the en-face frame */
 		unsigned autoFrame = 0, autoFrames = 1; int autoFn = 0;
 	} eg;
@@ -322,7 +326,7 @@ GatherDev next_gather(octb200_pipeline* p, unsigned frameNr, unsigned nFrames, i
 	GatherDev d{};
 	g.seq++;
 	for (int r = 0; r < g.world; ++r) {
-		d.frames[r] = reinterpret_cast<float*>(g.peerBase[r] + OCT_GATHER_HEADER_BYTES + (size_t)(g.seq & 1u) * g.frameStride);
+		d.frames[r] = reinterpret_cast<float*>(g.peerBase[r] + OCT_GATHER_HEADER_BYTES + (size_t)(g.seq % (unsigned)OCT_GATHER_FRAMES) * g.frameStride);
 		d.flags[r] = reinterpret_cast<unsigned*>(g.peerBase[r]);
 	}
 	d.counter = g.counter; d.status = g.counter + 2; d.Eglobal = g.Eglobal; d.offset = g.offset; d.seq = g.seq;
@@ -340,19 +344,27 @@ cudaError_t launch_gather_standalone(octb200_pipeline* p, const GatherDev& d) {
 	return launch_enface_gather(a, p->sCompute);
 }
 /* consumer side of the latest gather (once per sequence number): wait for every rank's slab, copy the frame into the private display
-   frame, acknowledge to every producer.  Enqueued right behind every gather: a rank consumes each frame it takes part in, so the
-   producers' flow-control wait (two gathers later) is normally satisfied long before they look. */
+   frame, acknowledge to every producer.  Enqueued behind every gather ON THE DISPLAY STREAM: a rank consumes each frame it takes part
+   in, beside its next compute kernel, so the producers' flow-control wait (three gathers later) is normally satisfied long before they look. */
 cudaError_t consume_gather(octb200_pipeline* p) {
 	auto& g = p->eg;
 	if (g.consumedSeq == g.seq) return cudaSuccess;
 	EnfaceConsumeArgs a{};
 	for (int r = 0; r < g.world; ++r) a.peerHeaders[r] = reinterpret_cast<unsigned*>(g.peerBase[r]);
 	a.window = reinterpret_cast<const unsigned*>(g.window);
-	a.frame = reinterpret_cast<const float*>(g.window + OCT_GATHER_HEADER_BYTES + (size_t)(g.seq & 1u) * g.frameStride);
+	a.frame = reinterpret_cast<const float*>(g.window + OCT_GATHER_HEADER_BYTES + (size_t)(g.seq % (unsigned)OCT_GATHER_FRAMES) * g.frameStride);
 	a.display = g.display; a.counter = g.counter + 1; a.status = g.counter + 2;
 	a.Eglobal = g.Eglobal; a.seq = g.seq; a.world = g.world; a.rank = g.rank;
-	cudaError_t e = launch_enface_consume(a, p->smCount, p->sCompute);
-	if (e == cudaSuccess) { g.consumedSeq = g.seq; p->launches++; }
+	/* on the display stream, behind the producing kernel of this sequence number: the compute stream goes straight on to the next buffer */
+	cudaError_t e = cudaEventRecord(g.evGathered, p->sCompute);
+	if (e == cudaSuccess) e = cudaStreamWaitEvent(g.sConsume, g.evGathered, 0);
+	if (e == cudaSuccess) e = launch_enface_consume(a, p->smCount, g.sConsume);
+	if (e == cudaSuccess) e = cudaEventRecord(g.evConsumed, g.sConsume);
+	if (e == cudaSuccess) {
+		g.consumedSeq = g.seq;
+		if (p->pdlStamp == p->launches) p->pdlStamp++;      /* (not on the compute stream: it does not come between two main launches) */
+		p->launches++;
+	}
 	return e;
 }
 
@@ -499,7 +511,11 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 			fa.convOut = static_cast<unsigned short*>(p->dOutConv[convSlot]);
 			fa.convScale = convScale;
 		}
+		/* back-to-back buffers: when the previous launch of this handle was this same main kernel (nothing in between that writes a table
+		   the prologue reads), let this grid's prologue overlap its tail */
+		fa.pdl = (src != SRC_CPLX && !determine && p->pdlStamp == p->launches && !(p->cfg.flags & OCTB200_FLAG_NO_DEPENDENT_LAUNCH)) ? 1 : 0;
 		CK(p, launch_fused(p->R, st.sa, st.roll, src, fa, p->smCount, p->sCompute)); p->launches++;
+		p->pdlStamp = p->launches;
 	}
 
 	if (sinus) {
@@ -918,6 +934,7 @@ int octb200_sync(octb200_pipeline* p) {
 	CK(p, cudaStreamSynchronize(p->sH2D));
 	CK(p, cudaStreamSynchronize(p->sCompute));
 	CK(p, cudaStreamSynchronize(p->sD2H));
+	if (p->eg.sConsume) CK(p, cudaStreamSynchronize(p->eg.sConsume));
 	return OCTB200_OK;
 }
 uint32_t octb200_current_buffer_nr(const octb200_pipeline* p) { return p ? p->bufferNumberInVolume : 0; }
@@ -980,7 +997,10 @@ int octb200_enface_gather_init(octb200_pipeline* p, int rank, int world, uint32_
 	auto& g = p->eg;
 	g.world = world; g.rank = rank; g.Eglobal = globalLines; g.offset = lineOffset; g.seq = 0; g.consumedSeq = 0;
 	g.frameStride = ((size_t)globalLines * sizeof(float) + 255) / 256 * 256;
-	{ int rc = dalloc(p, &g.window, OCT_GATHER_HEADER_BYTES + 2 * g.frameStride); if (rc) return rc; }
+	{ int rc = dalloc(p, &g.window, OCT_GATHER_HEADER_BYTES + OCT_GATHER_FRAMES * g.frameStride); if (rc) return rc; }
+	CK(p, cudaStreamCreateWithFlags(&g.sConsume, cudaStreamNonBlocking));
+	CK(p, cudaEventCreateWithFlags(&g.evGathered, cudaEventDisableTiming));
+	CK(p, cudaEventCreateWithFlags(&g.evConsumed, cudaEventDisableTiming));
 	{ int rc = dalloc(p, &g.counter, 4); if (rc) return rc; }
 	{ int rc = dalloc(p, &g.display, (size_t)globalLines + 4); if (rc) return rc; }
 	cudaIpcMemHandle_t h;
@@ -1023,6 +1043,7 @@ int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame) {
 	if (!p || !p->eg.connected || p->eg.seq == 0) return fail(p, OCTB200_ERR_NOT_READY, "no en-face gather issued");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	CK(p, consume_gather(p));          /* already enqueued behind the gather itself; a no-op then */
+	CK(p, cudaStreamWaitEvent(p->sCompute, p->eg.evConsumed, 0));      /* what the caller enqueues on the compute stream next sees the frame */
 	if (dFrame) *dFrame = p->eg.display;
 	return OCTB200_OK;
 }
@@ -1031,6 +1052,7 @@ int octb200_enface_gather_status(octb200_pipeline* p, uint32_t* sequence, uint32
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	unsigned st[2] = { 0, 0 };
 	CK(p, cudaStreamSynchronize(p->sCompute));
+	if (p->eg.sConsume) CK(p, cudaStreamSynchronize(p->eg.sConsume));
 	CK(p, cudaMemcpy(st, p->eg.counter + 2, sizeof(st), cudaMemcpyDeviceToHost));
 	if (sequence) *sequence = p->eg.seq;
 	if (ackTimeouts) *ackTimeouts = st[0];
@@ -1043,6 +1065,9 @@ int octb200_enface_gather_close(octb200_pipeline* p) {
 	if (!g.window && !g.counter) return OCTB200_OK;
 	cudaSetDevice(p->device);
 	if (p->sCompute) cudaStreamSynchronize(p->sCompute);
+	if (g.sConsume) { cudaStreamSynchronize(g.sConsume); cudaStreamDestroy(g.sConsume); g.sConsume = nullptr; }
+	if (g.evGathered) { cudaEventDestroy(g.evGathered); g.evGathered = nullptr; }
+	if (g.evConsumed) { cudaEventDestroy(g.evConsumed); g.evConsumed = nullptr; }
 	for (int r = 0; r < OCT_MAX_PEERS; ++r) {
 		if (g.opened[r] && g.peerBase[r]) cudaIpcCloseMemHandle(g.peerBase[r]);
 		g.opened[r] = false; g.peerBase[r] = nullptr;
@@ -1179,6 +1204,7 @@ int octb200_time_kernel(octb200_pipeline* p, const void* dRaw, int iters, float*
 			if (src == SRC_CPLX) { int rc = ensure_fft_buffer(p); if (rc) return rc; }
 			FusedArgs fa = fused_args(p, st, dRaw, p->lines);
 			fa.out = slab; fa.epi = epi_for(p, fpn && p->fpnDetermined, false);
+			fa.pdl = (i > 0 && src != SRC_CPLX && !(p->cfg.flags & OCTB200_FLAG_NO_DEPENDENT_LAUNCH)) ? 1 : 0;
 			CK(p, launch_fused(p->R, st.sa, st.roll, src, fa, p->smCount, p->sCompute));
 		}
 		p->launches++;

@@ -19,7 +19,7 @@ a, b, bits = (512, 256, 12) if n == 1024 else (1024, 128, 16)
 q = benchmark_params(n, a, b, bits); q.update_all_curves()
 small = synth.make_volume(n, a, 4, bits, resample=q.resampleCurve, dispersion=q.dispersionCurve)
 raw = np.ascontiguousarray(np.tile(small, (b // 4, 1, 1)))
-p = OctPipeline(fft_mode=_lib.FFT_FUSED)
+p = OctPipeline(fft_mode=_lib.FFT_FUSED, flags=int(os.environ.get("OCTB200_FLAGS", "0")))      # 2 = no programmatic dependent launch
 assert p.initializeCuda(None, None, q), getattr(p, "_create_error", "")
 p.octCudaPipeline(raw); p.sync()
 for _ in range(5):
