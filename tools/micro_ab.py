@@ -22,6 +22,9 @@ raw = np.ascontiguousarray(np.tile(small, (b // 4, 1, 1)))
 p = OctPipeline(fft_mode=_lib.FFT_FUSED, flags=int(os.environ.get("OCTB200_FLAGS", "0")))      # 2 = no programmatic dependent launch
 assert p.initializeCuda(None, None, q), getattr(p, "_create_error", "")
 p.octCudaPipeline(raw); p.sync()
+if os.environ.get("OCTB200_AUTOGATHER"):          # single-rank en-face gather fused into the kernel + its consumer kernel, every buffer
+    p.enface_gather_connect(p.enface_gather_init(0, 1, a * b, 0))
+    p.enface_gather_auto(True, 100, 1, 0)
 for _ in range(5):
     p.octCudaPipeline(None)
 p.sync()
