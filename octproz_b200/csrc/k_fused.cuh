@@ -227,7 +227,6 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	/* en-face gather fused into the epilogue: k2 index of the displayed depth bin (bin = lane + 32 k2), -1 = off */
 	const int egK2 = (a.eg.world > 0) ? (int)(a.eg.frameNr >> 5) : -1;
 	int it = 0, jb = 0;                /* jb: position inside the current block */
-	float egKeep = 0.f;                /* lane j: en-face value of line j of the current block */
 	for (int gline = g0; gline < a.lines; ++it) {
 		const int glineNext = gline + ((jb + 1 == LB) ? blockStep : 1);
 		float2 v[32];
@@ -435,27 +434,34 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 			if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u && (unsigned)b + a.bscanBase < a.flipEnd) al = a.A - 1 - al;
 			float* o = a.out + (size_t)blockIdx.y * a.trialOutStride + ((size_t)b * a.A + al) * H;
 #if OCT_TMEM_LUT
-			float egVal = 0.f;
 			ConvOut co;
 			co.line = CONV ? a.convOut + ((size_t)b * a.A + al) * H : nullptr;
 			co.scale = a.convScale;
-			if (R == 1 || p == 0) epilogue_tmem<R, 0, CONV>(lane, v, a.epi, tq, o, co, egK2, egVal); else epilogue_tmem<R, 16, CONV>(lane, v, a.epi, tq, o, co, egK2, egVal);
-			if (egK2 >= 0 && (R == 1 || p == (egK2 >> 4))) {
-				/* the value sits in lane frameNr % 32; lane jb keeps it until the block is complete, then lanes 0 .. jb store the block's
-				 * neighbouring values into every rank's frame (flip is an A-scan permutation inside a B-scan: a flipped line is stored alone) */
-				const float val = __shfl_sync(0xffffffffu, egVal, (int)(a.eg.frameNr & 31u));
-				if (a.flip) gather_store_block(a.eg, (unsigned)(b * a.A + al), 1, lane, val);
-				else {
-					if (lane == jb) egKeep = val;
-					if (jb + 1 == LB || glineNext >= a.lines) gather_store_block(a.eg, (unsigned)(gline - jb), jb + 1, lane, egKeep);
-				}
-			}
+			if (R == 1 || p == 0) epilogue_tmem<R, 0, CONV>(lane, v, a.epi, tq, o, co); else epilogue_tmem<R, 16, CONV>(lane, v, a.epi, tq, o, co);
 #else
 			static_assert(!CONV, "the converted output is written by the tensor-memory epilogue only (OCT_TMEM_LUT = 1)");
 			if (R == 1 || p == 0) epilogue_scaled<0>(lane, v, a.epi, sMean, sPpbg, o); else epilogue_scaled<16>(lane, v, a.epi, sMean, sPpbg, o);
 #endif
 		}
 		group_sync<R>(barId);              /* tile / slot reads finished before the next line's conversion overwrites them */
+#if OCT_TMEM_LUT
+		/* ---- en-face gather: once a block of LB consecutive lines is complete, lanes 0 .. cnt-1 of the group's first warp read the
+		 * displayed depth bin of "their" line back (the stores above are ordered before the barrier; the lines are still in L2) and
+		 * store it into every rank's frame -- neighbouring lines are neighbouring frame elements, so the peer stores coalesce.  The
+		 * epilogue itself carries no per-output cost for the gather. ---- */
+		if (egK2 >= 0 && a.cplxOut == nullptr && (R == 1 || p == 0) && (jb + 1 == LB || glineNext >= a.lines)) {
+			if (lane <= jb) {
+				const int l = gline - jb + lane;
+				int b = l / a.A, al = l - b * a.A;
+				if (a.flip && (((unsigned)b + a.bscanBase) & 1u) == 0u && (unsigned)b + a.bscanBase < a.flipEnd) al = a.A - 1 - al;
+				const size_t row = (size_t)b * a.A + al;
+				const float val = __ldcg(a.out + row * H + a.eg.frameNr);
+				const unsigned idx = (a.eg.Eglobal - 1u) - (a.eg.offset + (unsigned)row);      /* the reference writes the frame reversed (cuda_code.cu:909) */
+#pragma unroll 1
+				for (int r = 0; r < a.eg.world; ++r) a.eg.frames[r][idx] = val;
+			}
+		}
+#endif
 		gline = glineNext;
 		jb = (jb + 1 == LB) ? 0 : jb + 1;
 	}

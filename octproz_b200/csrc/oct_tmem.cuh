@@ -449,40 +449,12 @@ __device__ __forceinline__ void epilogue_tmem_sel(int lane, const float2 (&v)[32
 	default: epilogue_tmem_t<R, K2LO, true, true, true, CONV, EG>(lane, v, e, tq, outLine, co, egK2, egVal); break;
 	}
 }
-/* the ONE output per line the en-face gather needs (depth bin lane + 32 egK2 of the lane that owns it), recomputed from the register
- * that holds the bin with exactly the operations of epilogue_tmem_t (bit-identical to the stored value): a 16-way switch over the
- * compile-time register index costs ~10 instructions per line where the "keep the value while storing" variant of the epilogue cost
- * a compare + select per output (32 per line) */
-template <int R, int K2LO>
-__device__ __forceinline__ float epilogue_single(const float2 (&v)[32], const EpiConsts& e, uint32_t tq, int egK2) {
-	using M = TmemMap<R>;
-	const int i = egK2 - K2LO;                            /* 0 .. 15 */
-	float2 d = make_float2(0.f, 0.f);
-	switch (i) {
-#define OCT_EG_CASE(I) case I: d = v[bitrev5(K2LO + I)]; break;
-	OCT_EG_CASE(0) OCT_EG_CASE(1) OCT_EG_CASE(2) OCT_EG_CASE(3) OCT_EG_CASE(4) OCT_EG_CASE(5) OCT_EG_CASE(6) OCT_EG_CASE(7)
-	OCT_EG_CASE(8) OCT_EG_CASE(9) OCT_EG_CASE(10) OCT_EG_CASE(11) OCT_EG_CASE(12) OCT_EG_CASE(13) OCT_EG_CASE(14) OCT_EG_CASE(15)
-#undef OCT_EG_CASE
-	default: break;
-	}
-	if (e.fpn) {
-		float m[2];
-		tmem_ld2(tq + M::MEAN + 2 * i, m);
-		d = csub(d, make_float2(m[0], m[1]));
-	}
-	const float pw = fmaf(d.x, d.x, d.y * d.y);
-	float o = e.logMode ? fmaf(oct_lg2(pw), e.scaleA, e.scaleB) : fmaf(oct_sqrt(pw), e.scaleA, e.scaleB);
-	if (e.ppbg) {
-		float g[2];
-		tmem_ld2(tq + M::PPBG + (i & ~1), g);
-		o = saturate01(o - fmaf(e.ppbgWeight, (i & 1) ? g[1] : g[0], e.ppbgOffset));
-	}
-	return o;
-}
+/* (EG: the variant that keeps the displayed en-face bin in a register while storing is no longer used by the fused kernel -- the gather
+ * reads the finished values back, one block of lines at a time, k_fused.cuh -- so the epilogue has no per-output cost for it) */
 template <int R, int K2LO, bool CONV>
-__device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co, int egK2, float& egVal) {
-	epilogue_tmem_sel<R, K2LO, CONV, false>(lane, v, e, tq, outLine, co, egK2, egVal);
-	if (egK2 >= K2LO && egK2 < K2LO + 16) egVal = epilogue_single<R, K2LO>(v, e, tq, egK2);
+__device__ __forceinline__ void epilogue_tmem(int lane, const float2 (&v)[32], const EpiConsts& e, uint32_t tq, float* outLine, const ConvOut& co) {
+	float unused = 0.f;
+	epilogue_tmem_sel<R, K2LO, CONV, false>(lane, v, e, tq, outLine, co, -1, unused);
 }
 
 }  // namespace octb200
