@@ -244,9 +244,7 @@ OCTB200_API int octb200_float_to_output(octb200_pipeline* p, uint32_t bufferNrIn
                correction, no background recording) the extraction and the peer stores happen inside that kernel's epilogue, spread
                over the whole kernel (a line group stores the values of up to 8 neighbouring lines with one coalesced store per
                rank; no end-of-kernel push, no grid-wide barrier) -- compute and collective in one launch; otherwise the stand-alone
-               gather kernel is appended to the chain.  The consumer side of a fused gather rides in the prologue of the NEXT buffer's
-               kernel (all CTAs wait for the slabs, copy their share of the frame out, the last one acknowledges), or is enqueued by
-               `wait`, whichever comes first
+               gather kernel is appended to the chain
      wait    : *dFrame = device pointer of this rank's display frame [globalLines] floats, reference order disp[(E-1)-i]; the
                compute stream is made to wait for the consumer kernel of the latest gather, so work enqueued on it after this call
                sees that frame; it stays valid until the consumer kernel of the next gather runs

@@ -218,7 +218,6 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	 * gather frames are written below.  (No-ops in a plain launch.) */
 	grid_launch_dependents();
 	grid_dependency_wait();
-	if (a.eg.world > 0 && a.eg.consumeSeq != 0u) gather_consume_in_kernel(a.eg);      /* the previous buffer's en-face frame: wait, copy out, acknowledge */
 
 #ifdef OCT_STAGGER_NS
 	/* de-phase the line groups of a CTA so that shared-memory-heavy (stage A) and FMA-heavy (FFT) phases of different

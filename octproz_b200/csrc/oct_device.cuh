@@ -88,12 +88,6 @@ struct GatherDev {
 	unsigned frameNr, nFrames;
 	int fn;
 	int world, rank;
-	/* consumer side of the PREVIOUS gather folded into this launch's prologue (consumeSeq != 0): all CTAs wait for every rank's slab of
-	 * that frame, copy their share of it into the private display frame, the last one acknowledges -- no kernel of its own between two
-	 * buffers, and the work is spread evenly over the persistent CTAs */
-	unsigned consumeSeq;
-	const float* consumeFrame;         /* frame buffer of consumeSeq in THIS rank's window */
-	float* display;
 };
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 /* after ONE __threadfence_system(): a relaxed system-scope store per flag word (fence + relaxed store = release; a st.release per
@@ -120,30 +114,6 @@ __device__ __forceinline__ void gather_wait_acks(const GatherDev& g) {
 	bool ok = true;
 	for (int c = 0; c < g.world; ++c) ok = gather_spin_ge(acks + c, g.seq - (unsigned)OCT_GATHER_FRAMES) && ok;
 	if (!ok) atomicAdd(g.status, 1u);
-}
-/* consumer side in the prologue of the next compute kernel (all threads of every CTA; counter word [1] of the handle) */
-__device__ __forceinline__ void gather_consume_in_kernel(const GatherDev& g) {
-	if ((int)threadIdx.x < g.world) {
-		if (!gather_spin_ge(g.flags[g.rank] + OCT_GATHER_ARRIVED + threadIdx.x, g.consumeSeq) && blockIdx.x == 0) atomicAdd(g.status + 1, 1u);
-	}
-	__syncthreads();
-	const unsigned quads = g.Eglobal >> 2;
-	const unsigned per = (quads + gridDim.x - 1) / gridDim.x;
-	const unsigned q0 = blockIdx.x * per, q1 = (q0 + per < quads) ? q0 + per : quads;
-	for (unsigned q = q0 + threadIdx.x; q < q1; q += blockDim.x)
-		reinterpret_cast<float4*>(g.display)[q] = __ldcg(reinterpret_cast<const float4*>(g.consumeFrame) + q);
-	if (blockIdx.x == 0) for (unsigned i = (quads << 2) + threadIdx.x; i < g.Eglobal; i += blockDim.x) g.display[i] = __ldcg(g.consumeFrame + i);
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		const unsigned done = atomicAdd(g.counter + 1, 1u);
-		if (done == gridDim.x - 1u) {
-			g.counter[1] = 0;
-			__threadfence_system();
-#pragma unroll 1
-			for (int r = 0; r < g.world; ++r) st_relaxed_sys_u32(g.flags[r] + OCT_GATHER_ACK + g.rank, g.consumeSeq);
-		}
-	}
 }
 /* after a block of `cnt` consecutive lines starting at `firstLine`: lanes 0 .. cnt-1 hold their en-face values */
 __device__ __forceinline__ void gather_store_block(const GatherDev& g, unsigned firstLine, int cnt, int lane, float val) {

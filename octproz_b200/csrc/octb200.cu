@@ -449,7 +449,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 	const bool convFused = convFoldable && !sinus && mode == OCTB200_FFT_FUSED && !generic;      /* the register kernel's epilogue does */
 	const float convScale = (float)((1u << (p->cfg.bitDepth <= 10 ? 10 : p->cfg.bitDepth <= 12 ? 12 : 16)) - 1u);   /* cuda_code.cu:948-958 */
 
-	bool gatherDone = false, gatherFused = false;
+	bool gatherDone = false;
 	if (mode == OCTB200_FFT_CUFFT) {
 		PreArgs pa = pre_args(p, st, dRaw, p->lines);
 		CK(p, launch_pre(pa, p->rawBytes, st.sa, st.roll, p->smCount, p->sCompute)); p->launches++;
@@ -502,18 +502,9 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		fa.out = mainOut; fa.epi = epi_for(p, fpn, ppbgFoldMain);
 		/* automatic en-face gather: fused into this kernel's epilogue when the slab is final after it */
 		if (p->eg.autoOn && p->eg.connected && !sinus && !ppbgRecord && p->V == 1 && p->eg.autoFrames <= 1) {
-			/* the consumer side of the PREVIOUS frame rides in this launch's prologue (oct_device.cuh gather_consume_in_kernel) */
-			const unsigned prevSeq = p->eg.seq;
-			const bool consumePrev = prevSeq != 0 && p->eg.consumedSeq != prevSeq;
 			fa.eg = next_gather(p, p->eg.autoFrame, p->eg.autoFrames, p->eg.autoFn);
-			if (consumePrev) {
-				fa.eg.consumeSeq = prevSeq;
-				fa.eg.consumeFrame = reinterpret_cast<const float*>(p->eg.window + OCT_GATHER_HEADER_BYTES + (size_t)(prevSeq % (unsigned)OCT_GATHER_FRAMES) * p->eg.frameStride);
-				fa.eg.display = p->eg.display;
-				p->eg.consumedSeq = prevSeq;
-			}
 			fa.lineBlock = gather_line_block(p, st, src, p->lines);
-			gatherDone = true; gatherFused = true;
+			gatherDone = true;
 		}
 		if (convFused) {
 			if (p->convPending[convSlot]) { CK(p, cudaStreamWaitEvent(p->sCompute, p->evConvFree[convSlot], 0)); p->convPending[convSlot] = false; }
@@ -548,9 +539,7 @@ int run_chain(octb200_pipeline* p, const void* dRaw) {
 		const GatherDev d = next_gather(p, p->eg.autoFrame, p->eg.autoFrames, p->eg.autoFn);
 		CK(p, launch_gather_standalone(p, d)); p->launches++;
 	}
-	/* consumer side: a fused gather is consumed in the prologue of the next buffer's kernel (or by octb200_enface_gather_wait, whichever
-	   comes first); a stand-alone gather kernel is followed by its consumer kernel on the display stream right away */
-	if (p->eg.autoOn && p->eg.connected && !gatherFused) CK(p, consume_gather(p));
+	if (p->eg.autoOn && p->eg.connected) CK(p, consume_gather(p));
 
 	/* ---- streaming to the host (cuda_code.cu:1357-1386,1595-1604) ---- */
 	const bool wantFloat = q.streamFloatToHost && p->hostFloat[0] && p->hostFloat[1];
