@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(fused_max_threads(R, SA), 1) oct_fused_kernel(
 	uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(smem + L.offW);
 	if (warp == 0) tmem_alloc(tmemBaseSlot, TmemMap<R>::ALLOC);
 	/* multi-GPU en-face gather: every consumer has released the frame buffer this launch overwrites (flow control, oct_device.cuh) */
-	if (a.eg.world > 0 && threadIdx.x == blockDim.x - 1) gather_wait_acks(a.eg);
+	if (a.eg.world > 0 && warp == (int)(blockDim.x >> 5) - 1) gather_wait_acks(a.eg, lane);
 	tmem_fence_before_sync();
 	__syncthreads();
 	tmem_fence_after_sync();

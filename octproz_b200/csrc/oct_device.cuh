@@ -107,13 +107,14 @@ __device__ __forceinline__ bool gather_spin_ge(const unsigned* word, unsigned wa
 	}
 	return true;
 }
-/* producer prologue (one thread per CTA): every consumer has released the frame buffer this launch is about to overwrite */
-__device__ __forceinline__ void gather_wait_acks(const GatherDev& g) {
+/* producer prologue (the lanes of ONE warp per CTA, lane c looks at consumer c: one load latency for all ranks): every consumer has
+ * released the frame buffer this launch is about to overwrite */
+__device__ __forceinline__ void gather_wait_acks(const GatherDev& g, int lane) {
 	if (g.world < 1 || g.seq <= (unsigned)OCT_GATHER_FRAMES) return;       /* (also with one rank: its own consumer runs on another stream) */
-	const unsigned* acks = g.flags[g.rank] + OCT_GATHER_ACK;
-	bool ok = true;
-	for (int c = 0; c < g.world; ++c) ok = gather_spin_ge(acks + c, g.seq - (unsigned)OCT_GATHER_FRAMES) && ok;
-	if (!ok) atomicAdd(g.status, 1u);
+	if (lane < g.world) {
+		const unsigned* acks = g.flags[g.rank] + OCT_GATHER_ACK;
+		if (!gather_spin_ge(acks + lane, g.seq - (unsigned)OCT_GATHER_FRAMES)) atomicAdd(g.status, 1u);
+	}
 }
 /* after a block of `cnt` consecutive lines starting at `firstLine`: lanes 0 .. cnt-1 hold their en-face values */
 __device__ __forceinline__ void gather_store_block(const GatherDev& g, unsigned firstLine, int cnt, int lane, float val) {
