@@ -131,7 +131,8 @@ struct octb200_pipeline {
 		unsigned* counter = nullptr;       /* [0] producer kernels, [1] consume kernel, [2..3] status (time-outs: acks, arrivals) */
 		float* display = nullptr;          /* private copy of the last consumed frame */
 		cudaStream_t sConsume = nullptr;   /* the display stream: consumer kernels run beside the next buffer's compute kernel */
-		cudaEvent_t evGathered = nullptr, evConsumed = nullptr;
+		cudaEvent_t evGathered = nullptr;
+		cudaEvent_t evConsumed[OCT_GATHER_FRAMES] = {};   /* consumer kernel of sequence number s done: evConsumed[s % 3] */
 		bool autoOn = false;               /* every process call also gathers the en-face frame */
 		unsigned autoFrame = 0, autoFrames = 1; int autoFn = 0;
 	} eg;
@@ -325,6 +326,11 @@ GatherDev next_gather(octb200_pipeline* p, unsigned frameNr, unsigned nFrames, i
 	auto& g = p->eg;
 	GatherDev d{};
 	g.seq++;
+	/* flow control, host side: the kernel that produces frame `seq` spins in its prologue until every rank has acknowledged frame seq - 3.
+	   A spinning grid holds every SM, so THIS rank's consumer kernel of seq - 3 must have run before that grid is launched -- the compute
+	   stream waits for it (normally long done: it runs beside the kernel of seq - 2 on the high-priority display stream).  Every rank does
+	   the same, so every acknowledgement a prologue waits for comes from a consumer kernel that is guaranteed to get its SMs. */
+	if (g.seq > (unsigned)OCT_GATHER_FRAMES && g.evConsumed[g.seq % OCT_GATHER_FRAMES]) cudaStreamWaitEvent(p->sCompute, g.evConsumed[g.seq % OCT_GATHER_FRAMES], 0);
 	for (int r = 0; r < g.world; ++r) {
 		d.frames[r] = reinterpret_cast<float*>(g.peerBase[r] + OCT_GATHER_HEADER_BYTES + (size_t)(g.seq % (unsigned)OCT_GATHER_FRAMES) * g.frameStride);
 		d.flags[r] = reinterpret_cast<unsigned*>(g.peerBase[r]);
@@ -359,7 +365,7 @@ cudaError_t consume_gather(octb200_pipeline* p) {
 	cudaError_t e = cudaEventRecord(g.evGathered, p->sCompute);
 	if (e == cudaSuccess) e = cudaStreamWaitEvent(g.sConsume, g.evGathered, 0);
 	if (e == cudaSuccess) e = launch_enface_consume(a, p->smCount, g.sConsume);
-	if (e == cudaSuccess) e = cudaEventRecord(g.evConsumed, g.sConsume);
+	if (e == cudaSuccess) e = cudaEventRecord(g.evConsumed[g.seq % OCT_GATHER_FRAMES], g.sConsume);
 	if (e == cudaSuccess) {
 		g.consumedSeq = g.seq;
 		if (p->pdlStamp == p->launches) p->pdlStamp++;      /* (not on the compute stream: it does not come between two main launches) */
@@ -998,9 +1004,15 @@ int octb200_enface_gather_init(octb200_pipeline* p, int rank, int world, uint32_
 	g.world = world; g.rank = rank; g.Eglobal = globalLines; g.offset = lineOffset; g.seq = 0; g.consumedSeq = 0;
 	g.frameStride = ((size_t)globalLines * sizeof(float) + 255) / 256 * 256;
 	{ int rc = dalloc(p, &g.window, OCT_GATHER_HEADER_BYTES + OCT_GATHER_FRAMES * g.frameStride); if (rc) return rc; }
-	CK(p, cudaStreamCreateWithFlags(&g.sConsume, cudaStreamNonBlocking));
+	{
+		/* highest priority: when the SMs of a finishing compute kernel free up, the pending consumer kernel gets them before the CTAs of the
+		   next compute kernel (which programmatic dependent launch has already queued) */
+		int lo = 0, hi = 0;
+		CK(p, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CK(p, cudaStreamCreateWithPriority(&g.sConsume, cudaStreamNonBlocking, hi));
+	}
 	CK(p, cudaEventCreateWithFlags(&g.evGathered, cudaEventDisableTiming));
-	CK(p, cudaEventCreateWithFlags(&g.evConsumed, cudaEventDisableTiming));
+	for (auto& e : g.evConsumed) CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	{ int rc = dalloc(p, &g.counter, 4); if (rc) return rc; }
 	{ int rc = dalloc(p, &g.display, (size_t)globalLines + 4); if (rc) return rc; }
 	cudaIpcMemHandle_t h;
@@ -1043,7 +1055,7 @@ int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame) {
 	if (!p || !p->eg.connected || p->eg.seq == 0) return fail(p, OCTB200_ERR_NOT_READY, "no en-face gather issued");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	CK(p, consume_gather(p));          /* already enqueued behind the gather itself; a no-op then */
-	CK(p, cudaStreamWaitEvent(p->sCompute, p->eg.evConsumed, 0));      /* what the caller enqueues on the compute stream next sees the frame */
+	CK(p, cudaStreamWaitEvent(p->sCompute, p->eg.evConsumed[p->eg.seq % OCT_GATHER_FRAMES], 0));      /* what the caller enqueues on the compute stream next sees the frame */
 	if (dFrame) *dFrame = p->eg.display;
 	return OCTB200_OK;
 }
@@ -1067,7 +1079,7 @@ int octb200_enface_gather_close(octb200_pipeline* p) {
 	if (p->sCompute) cudaStreamSynchronize(p->sCompute);
 	if (g.sConsume) { cudaStreamSynchronize(g.sConsume); cudaStreamDestroy(g.sConsume); g.sConsume = nullptr; }
 	if (g.evGathered) { cudaEventDestroy(g.evGathered); g.evGathered = nullptr; }
-	if (g.evConsumed) { cudaEventDestroy(g.evConsumed); g.evConsumed = nullptr; }
+	for (auto& e : g.evConsumed) if (e) { cudaEventDestroy(e); e = nullptr; }
 	for (int r = 0; r < OCT_MAX_PEERS; ++r) {
 		if (g.opened[r] && g.peerBase[r]) cudaIpcCloseMemHandle(g.peerBase[r]);
 		g.opened[r] = false; g.peerBase[r] = nullptr;

@@ -95,6 +95,28 @@ def main():
     assert st["ack_timeouts"] == 0 and st["arrival_timeouts"] == 0, st
     out["flow_control_frames_checked"] = len(frames)
     dist.barrier()
+    # ---- back-to-back SHORT buffers with the gather fused into every kernel (the strong-scaling regime: a few lines per SM and buffer):
+    #      the producers' flow control must never wait for a consumer kernel that cannot get an SM (status counters stay 0, no stall) ----
+    sp.pipe.enface_gather_auto(True, 17, 1, 0)
+    d_local = torch.from_numpy(np.ascontiguousarray(sp.local_slice(raw)).view(np.int16)).to(dev)
+    sp.pipe.process_device(d_local); sp.sync(); dist.barrier()
+    t0 = time.perf_counter()
+    raw_call, h, ptr_local = sp.pipe._lib.octb200_process_device, sp.pipe.handle, int(d_local.data_ptr())
+    for _ in range(2000):               # the bare C call: the host stays far ahead of the GPU, the compute stream is saturated
+        assert raw_call(h, ptr_local) == 0
+    ptr = sp.pipe.enface_gather_wait(); sp.sync()
+    dt = time.perf_counter() - t0
+    st = sp.pipe.enface_gather_status()
+    assert st["ack_timeouts"] == 0 and st["arrival_timeouts"] == 0, f"rank {rank}: {st}"
+    assert dt < 5.0, f"rank {rank}: 2000 short buffers took {dt:.1f} s"
+
+    class _W4:  # noqa: N801
+        __cuda_array_interface__ = {"shape": (a * btot,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    got = torch.as_tensor(_W4(), device=dev).clone().cpu().numpy()
+    assert float(np.abs(got - orc.enface_frame(ref, n // 2, a, btot, 17, 1, 0)).max()) < 1e-3
+    out["short_buffers_us_per_step"] = dt / 2000 * 1e6
+    sp.pipe.enface_gather_auto(False)
+    dist.barrier()
     # ---- timing of the two gathers (device events, max over ranks) ----
     loc = torch.empty(a * sp.count, dtype=torch.float32, device=dev)
     gathered = torch.empty(world * a * sp.count, dtype=torch.float32, device=dev)
