@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(256) oct_pre_kernel(const PreArgs a) {
 		const float* f = fslot + a.HB;
 		const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
 		float2* o = a.out + (size_t)gline * N;
+		/* four table reads in flight per lane: the loop was bound by the latency of one L1/L2 read per sample (ncu: long_scoreboard 5.9
+		 * warps per issue cycle, profiles/r02m_fused_ncu_summary.md) */
+#pragma unroll 4
 		for (int m = lane; m < N; m += 32) {
 			const float4 B = __ldg(a.lutB + m);
 			float2 val;

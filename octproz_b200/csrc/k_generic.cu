@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(512, 2) oct_generic_kernel(const GenericArgs a
 		if (active) {
 			const float* f = fslot + a.HB;
 			const int shift = (SA == SA_LANCZOS && gline == 0) ? 8 : 0;
+#pragma unroll 2
 			for (int m = tid; m < N; m += T) {
 				float2 val;
 				if constexpr (SA == SA_CUBIC) {
@@ -347,8 +348,10 @@ void generic_fill_twiddles(const int* radix, int nPass, const int* twOff, float2
 /* CTA shape: TT threads per line by the line length; as many line teams as fit a 512-thread CTA and ~110 KB of shared memory (two CTAs
  * per SM), at least one.  OCTB200_GENERIC_LB overrides the team count (experiments). */
 static void generic_shape(int N, int HB, int HA, int rawBytes, bool roll, int twEntries, int* TT, int* LB, int* smemBytes) {
-	const int tt = N >= 2048 ? 256 : (N >= 1024 ? 128 : 64);
-	int lb = 512 / tt;
+	int tt = N >= 2048 ? 256 : (N >= 1024 ? 128 : 64);
+	const char* envT = getenv("OCTB200_GENERIC_TT");       /* experiments */
+	if (envT && (atoi(envT) == 64 || atoi(envT) == 128 || atoi(envT) == 256 || atoi(envT) == 512)) tt = atoi(envT);
+	int lb = 1;        /* one line per CTA: more teams per CTA bought nothing on a B200 (profiles/r02f_generic_lb_sweep.txt) */
 	const char* env = getenv("OCTB200_GENERIC_LB");
 	if (env && atoi(env) > 0 && atoi(env) * tt <= 512) lb = atoi(env);
 	else while (lb > 1 && generic_smem_layout(N, HB, HA, rawBytes, roll, lb, twEntries).total > 112 * 1024) lb >>= 1;
