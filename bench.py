@@ -310,7 +310,7 @@ def timed_resident(rig, steps, warmup, dist, step_fn):
     for i in range(steps):
         step_fn(i)
     if rig.gather == "p2p":
-        p.enface_gather_wait()             # the compute stream waits for the consumer kernel of the LAST frame: every frame of the region was consumed inside it
+        p.enface_gather_wait()             # (every frame of the region was consumed inside it: the consumer kernels run in stream order)
     p.event_record(1)
     ms_total = p.event_elapsed_ms(0, 1)
     sync_all()
@@ -523,7 +523,7 @@ def main():
 
     def step_resident(i, r=rig, frame=enface, out=gathered):
         # p2p: the process call itself gathers (peer stores from the kernel's epilogue) and enqueues the consumer kernel of this frame
-        # (wait for every rank's slab, copy the frame out, acknowledge) on the handle's display stream
+        # (wait for every rank's slab, copy the frame out, acknowledge) behind it
         r.p.process_device(r.d_raw[i & 1])
         if gather_impl == "nccl":
             r.p.changeDisplayedEnFaceFrame(100, 1, 0, frame)
@@ -652,7 +652,7 @@ def main():
             "volumes_per_s": value * 1e6 / ascans_per_step, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours", "config": config, "mode": args.mode,
-            "gather": None if world == 1 else {"impl": gather_impl, "every_step": "peer-memory stores from the fused kernel's epilogue + consumer kernel (wait for all slabs, copy out, acknowledge) on the display stream"
+            "gather": None if world == 1 else {"impl": gather_impl, "every_step": "peer-memory stores from the fused kernel's epilogue + consumer kernel (wait for all slabs, copy out, acknowledge) in stream order"
                                                if gather_impl == "p2p" else "extraction kernel + ncclAllGather", "check": gcheck},
             "e2e": {"value": e2e_mhz, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": conv_bytes,
                     "ms_per_step": e2e_s * 1e3 / e2e_steps, "steps": e2e_steps, "timer": "host wall clock between device synchronisations, max over ranks",

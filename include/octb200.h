@@ -233,8 +233,8 @@ OCTB200_API int octb200_float_to_output(octb200_pipeline* p, uint32_t bufferNrIn
      connect : handles = world * 64 bytes, rank-major; opens every peer window
      gather  : enqueue extraction + peer stores + flag publication on the compute stream, then the consumer side for the same
                sequence number: wait for ALL ranks' slabs, copy the assembled frame into this rank's private display frame and
-               acknowledge to every producer -- on the handle's own display stream, so the compute stream goes straight on to the
-               next buffer.  The windows hold three frame buffers used round-robin by sequence number; a producer only overwrites a
+               acknowledge to every producer -- in stream order, as the programmatic dependent of the producing kernel (its launch
+               latency hides behind that kernel's tail).  The windows hold three frame buffers used round-robin by sequence number; a producer only overwrites a
                buffer after every rank has acknowledged the frame it held (flow control in the kernels' prologue), so a rank that
                runs ahead can never tear a frame a slower rank is still reading.  COLLECTIVE: every rank must issue the same
                sequence of gathers; a rank that stops gathering stalls its peers three gathers later -- for at most 10 s per launch:
@@ -245,9 +245,8 @@ OCTB200_API int octb200_float_to_output(octb200_pipeline* p, uint32_t bufferNrIn
                over the whole kernel (a line group stores the values of up to 8 neighbouring lines with one coalesced store per
                rank; no end-of-kernel push, no grid-wide barrier) -- compute and collective in one launch; otherwise the stand-alone
                gather kernel is appended to the chain
-     wait    : *dFrame = device pointer of this rank's display frame [globalLines] floats, reference order disp[(E-1)-i]; the
-               compute stream is made to wait for the consumer kernel of the latest gather, so work enqueued on it after this call
-               sees that frame; it stays valid until the consumer kernel of the next gather runs
+     wait    : *dFrame = device pointer of this rank's display frame [globalLines] floats, reference order disp[(E-1)-i]; valid
+               (stream ordered on the compute stream) until the next gather.  The consumer kernel was already enqueued by gather
      status  : sequence number of the latest gather and the number of time-outs so far (0 / 0 in a healthy run); synchronises
      close   : release (collective in spirit: call after a barrier, peers must have stopped gathering) */
 #define OCTB200_IPC_HANDLE_BYTES 64

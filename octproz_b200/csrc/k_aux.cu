@@ -473,6 +473,10 @@ __global__ void __launch_bounds__(256) enface_gather_kernel(const EnfaceGatherAr
  * check that acknowledgement before they overwrite this frame buffer two gathers later (flow control: a rank that runs ahead can
  * never tear a frame a slower rank is still reading). */
 __global__ void __launch_bounds__(256) enface_consume_kernel(const EnfaceConsumeArgs a) {
+	/* in stream order behind the kernel that produced this rank's slab, launched as its programmatic dependent: the launch latency hides
+	 * behind that kernel's tail, and the next compute kernel (this kernel's dependent) may run its prologue meanwhile */
+	grid_launch_dependents();
+	grid_dependency_wait();
 	if ((int)threadIdx.x < a.world) {
 		if (!gather_spin_ge(a.window + OCT_GATHER_ARRIVED + threadIdx.x, a.seq) && blockIdx.x == 0) atomicAdd(a.status + 1, 1u);
 	}
@@ -498,10 +502,19 @@ cudaError_t launch_enface_gather(const EnfaceGatherArgs& a, cudaStream_t st) {
 	enface_gather_kernel<<<(a.E + 255) / 256, 256, 0, st>>>(a);
 	return cudaGetLastError();
 }
-cudaError_t launch_enface_consume(const EnfaceConsumeArgs& a, int smCount, cudaStream_t st) {
+cudaError_t launch_enface_consume(const EnfaceConsumeArgs& a, int smCount, bool dependent, cudaStream_t st) {
 	int blocks = (int)((a.Eglobal / 4 + 255) / 256);
 	if (blocks > smCount) blocks = smCount;
 	if (blocks < 1) blocks = 1;
+	if (dependent) {
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = at; cfg.numAttrs = 1;
+		return cudaLaunchKernelEx(&cfg, enface_consume_kernel, a);
+	}
 	enface_consume_kernel<<<blocks, 256, 0, st>>>(a);
 	return cudaGetLastError();
 }

@@ -88,7 +88,7 @@ struct EnfaceConsumeArgs {
 	int world, rank;
 };
 cudaError_t launch_enface_gather(const EnfaceGatherArgs& a, cudaStream_t st);
-cudaError_t launch_enface_consume(const EnfaceConsumeArgs& a, int smCount, cudaStream_t st);
+cudaError_t launch_enface_consume(const EnfaceConsumeArgs& a, int smCount, bool dependent, cudaStream_t st);
 
 cudaError_t launch_sweep_metric(float* metrics, const float* data, int trials, int lines, int H, int metric, float thr, int ignore, cudaStream_t st);
 cudaError_t launch_unpack12(uint16_t* out, const void* in, long long octets, int smCount, cudaStream_t st);

@@ -68,10 +68,10 @@ template <int B> __device__ __forceinline__ float u8_to_float(uint32_t w) { retu
  *
  * Window of a rank (octb200.cu EnfaceGather): [64 words arrived[producer]] [64 words ack[consumer]] ... [frame 0] [frame 1] [frame 2].
  * Frames are used round-robin by sequence number (seq % 3).  Flow control: before a producer stores frame `seq` into a peer's window
- * that peer must have consumed frame seq - 3 (the previous user of the buffer): the consumer's enface_consume_kernel (k_aux.cu, on
- * the handle's display stream) waits for all arrived[] words, copies the frame into its private display buffer and THEN writes
- * ack[consumer] = seq into every producer's window; a producer checks its own (local) ack words in the kernel prologue.  Three
- * buffers give the consumers a full step of slack: the consume kernel of step s runs beside the compute kernel of step s + 1.
+ * that peer must have consumed frame seq - 3 (the previous user of the buffer): the consumer's enface_consume_kernel (k_aux.cu, in
+ * stream order behind its own rank's producing kernel) waits for all arrived[] words, copies the frame into its private display
+ * buffer and THEN writes ack[consumer] = seq into every producer's window; a producer checks its own (local) ack words in the kernel
+ * prologue.  Three buffers give a slow rank two steps of slack before it holds the others up.
  * Every spin has a time-out (status word), never a hang.
  * See k_aux.cu enface_gather_kernel for the stand-alone form used for multi-frame averages / MIP and when later passes
  * (sinusoidal correction, background recording) still change the slab. */

@@ -130,9 +130,6 @@ struct octb200_pipeline {
 		bool connected = false;
 		unsigned* counter = nullptr;       /* [0] producer kernels, [1] consume kernel, [2..3] status (time-outs: acks, arrivals) */
 		float* display = nullptr;          /* private copy of the last consumed frame */
-		cudaStream_t sConsume = nullptr;   /* the display stream: consumer kernels run beside the next buffer's compute kernel */
-		cudaEvent_t evGathered = nullptr;
-		cudaEvent_t evConsumed[OCT_GATHER_FRAMES] = {};   /* consumer kernel of sequence number s done: evConsumed[s % 3] */
 		bool autoOn = false;               /* every process call also gathers the en-face frame */
 		unsigned autoFrame = 0, autoFrames = 1; int autoFn = 0;
 	} eg;
@@ -326,16 +323,6 @@ GatherDev next_gather(octb200_pipeline* p, unsigned frameNr, unsigned nFrames, i
 	auto& g = p->eg;
 	GatherDev d{};
 	g.seq++;
-	/* flow control, host side: the kernel that produces frame `seq` spins in its prologue until every rank has acknowledged frame seq - 3.
-	   A spinning grid holds every SM, so THIS rank's consumer kernel of seq - 3 must have run before that grid is launched -- the compute
-	   stream waits for it (normally long done: it runs beside the kernel of seq - 2 on the high-priority display stream).  Every rank does
-	   the same, so every acknowledgement a prologue waits for comes from a consumer kernel that is guaranteed to get its SMs. */
-	if (g.seq > (unsigned)OCT_GATHER_FRAMES && g.evConsumed[g.seq % OCT_GATHER_FRAMES]) {
-		/* only when that consumer kernel has NOT finished yet (a saturated compute stream can starve it): a stream operation between two
-		   compute kernels costs the programmatic overlap of their tail and prologue, and in the steady state the event is long complete */
-		cudaEvent_t ev = g.evConsumed[g.seq % OCT_GATHER_FRAMES];
-		if (cudaEventQuery(ev) != cudaSuccess) { cudaGetLastError(); cudaStreamWaitEvent(p->sCompute, ev, 0); }
-	}
 	for (int r = 0; r < g.world; ++r) {
 		d.frames[r] = reinterpret_cast<float*>(g.peerBase[r] + OCT_GATHER_HEADER_BYTES + (size_t)(g.seq % (unsigned)OCT_GATHER_FRAMES) * g.frameStride);
 		d.flags[r] = reinterpret_cast<unsigned*>(g.peerBase[r]);
@@ -355,8 +342,8 @@ cudaError_t launch_gather_standalone(octb200_pipeline* p, const GatherDev& d) {
 	return launch_enface_gather(a, p->sCompute);
 }
 /* consumer side of the latest gather (once per sequence number): wait for every rank's slab, copy the frame into the private display
-   frame, acknowledge to every producer.  Enqueued behind every gather ON THE DISPLAY STREAM: a rank consumes each frame it takes part
-   in, beside its next compute kernel, so the producers' flow-control wait (three gathers later) is normally satisfied long before they look. */
+   frame, acknowledge to every producer.  Enqueued behind every gather: a rank consumes each frame it takes part in, so the producers'
+   flow-control wait (three gathers later) is satisfied long before they look. */
 cudaError_t consume_gather(octb200_pipeline* p) {
 	auto& g = p->eg;
 	if (g.consumedSeq == g.seq) return cudaSuccess;
@@ -366,15 +353,18 @@ cudaError_t consume_gather(octb200_pipeline* p) {
 	a.frame = reinterpret_cast<const float*>(g.window + OCT_GATHER_HEADER_BYTES + (size_t)(g.seq % (unsigned)OCT_GATHER_FRAMES) * g.frameStride);
 	a.display = g.display; a.counter = g.counter + 1; a.status = g.counter + 2;
 	a.Eglobal = g.Eglobal; a.seq = g.seq; a.world = g.world; a.rank = g.rank;
-	/* on the display stream, behind the producing kernel of this sequence number: the compute stream goes straight on to the next buffer */
-	cudaError_t e = cudaEventRecord(g.evGathered, p->sCompute);
-	if (e == cudaSuccess) e = cudaStreamWaitEvent(g.sConsume, g.evGathered, 0);
-	if (e == cudaSuccess) e = launch_enface_consume(a, p->smCount, g.sConsume);
-	if (e == cudaSuccess) e = cudaEventRecord(g.evConsumed[g.seq % OCT_GATHER_FRAMES], g.sConsume);
+	/* in stream order, as the programmatic dependent of the kernel that produced this rank's slab.  (A consumer kernel on a stream of its
+	   own was measured and dropped: a saturated compute stream starves it -- every SM goes to the next, already queued compute grid --
+	   and a compute grid that spins in its prologue for acknowledgements then holds every SM the consumer needs: 10 s time-outs per
+	   buffer at 8 GPUs, profiles/r02l_bench_n8.json.  In order it can never be starved, and the acknowledgement of frame s is on its
+	   way before the kernel of s + 1 starts, three buffers ahead of need.) */
+	const bool dependent = (p->pdlStamp == p->launches) && !(p->cfg.flags & OCTB200_FLAG_NO_DEPENDENT_LAUNCH);
+	cudaError_t e = launch_enface_consume(a, p->smCount, dependent, p->sCompute);
 	if (e == cudaSuccess) {
 		g.consumedSeq = g.seq;
-		if (p->pdlStamp == p->launches) p->pdlStamp++;      /* (not on the compute stream: it does not come between two main launches) */
+		const bool chain = p->pdlStamp == p->launches;
 		p->launches++;
+		if (chain) p->pdlStamp = p->launches;      /* the next main launch may be this kernel's programmatic dependent in turn */
 	}
 	return e;
 }
@@ -945,7 +935,6 @@ int octb200_sync(octb200_pipeline* p) {
 	CK(p, cudaStreamSynchronize(p->sH2D));
 	CK(p, cudaStreamSynchronize(p->sCompute));
 	CK(p, cudaStreamSynchronize(p->sD2H));
-	if (p->eg.sConsume) CK(p, cudaStreamSynchronize(p->eg.sConsume));
 	return OCTB200_OK;
 }
 uint32_t octb200_current_buffer_nr(const octb200_pipeline* p) { return p ? p->bufferNumberInVolume : 0; }
@@ -1009,19 +998,6 @@ int octb200_enface_gather_init(octb200_pipeline* p, int rank, int world, uint32_
 	g.world = world; g.rank = rank; g.Eglobal = globalLines; g.offset = lineOffset; g.seq = 0; g.consumedSeq = 0;
 	g.frameStride = ((size_t)globalLines * sizeof(float) + 255) / 256 * 256;
 	{ int rc = dalloc(p, &g.window, OCT_GATHER_HEADER_BYTES + OCT_GATHER_FRAMES * g.frameStride); if (rc) return rc; }
-	{
-		/* default priority: measured at two GPUs, a high-priority display stream takes SMs from the starting compute kernel at every
-		   boundary (weak-scaling step 0.2129 -> 0.2218 ms together with an unconditional stream wait); starvation of the consumer by a
-		   saturated compute stream is handled by the host-side guard in next_gather instead */
-		int lo = 0, hi = 0;
-		CK(p, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-		const char* env = getenv("OCTB200_DISPLAY_PRIORITY");      /* experiments: "high" */
-		CK(p, cudaStreamCreateWithPriority(&g.sConsume, cudaStreamNonBlocking, (env && env[0] == 'h') ? hi : 0));
-	}
-	CK(p, cudaEventCreateWithFlags(&g.evGathered, cudaEventDisableTiming));
-	for (auto& e : g.evConsumed) CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-	{ int rc = dalloc(p, &g.counter, 4); if (rc) return rc; }
-	{ int rc = dalloc(p, &g.display, (size_t)globalLines + 4); if (rc) return rc; }
 	cudaIpcMemHandle_t h;
 	CK(p, cudaIpcGetMemHandle(&h, g.window));
 	static_assert(sizeof(h) == OCTB200_IPC_HANDLE_BYTES, "ipc handle size");
@@ -1062,7 +1038,6 @@ int octb200_enface_gather_wait(octb200_pipeline* p, float** dFrame) {
 	if (!p || !p->eg.connected || p->eg.seq == 0) return fail(p, OCTB200_ERR_NOT_READY, "no en-face gather issued");
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	CK(p, consume_gather(p));          /* already enqueued behind the gather itself; a no-op then */
-	CK(p, cudaStreamWaitEvent(p->sCompute, p->eg.evConsumed[p->eg.seq % OCT_GATHER_FRAMES], 0));      /* what the caller enqueues on the compute stream next sees the frame */
 	if (dFrame) *dFrame = p->eg.display;
 	return OCTB200_OK;
 }
@@ -1071,7 +1046,6 @@ int octb200_enface_gather_status(octb200_pipeline* p, uint32_t* sequence, uint32
 	if (use_device(p)) return fail(p, OCTB200_ERR_CUDA, "cudaSetDevice failed");
 	unsigned st[2] = { 0, 0 };
 	CK(p, cudaStreamSynchronize(p->sCompute));
-	if (p->eg.sConsume) CK(p, cudaStreamSynchronize(p->eg.sConsume));
 	CK(p, cudaMemcpy(st, p->eg.counter + 2, sizeof(st), cudaMemcpyDeviceToHost));
 	if (sequence) *sequence = p->eg.seq;
 	if (ackTimeouts) *ackTimeouts = st[0];
@@ -1084,9 +1058,6 @@ int octb200_enface_gather_close(octb200_pipeline* p) {
 	if (!g.window && !g.counter) return OCTB200_OK;
 	cudaSetDevice(p->device);
 	if (p->sCompute) cudaStreamSynchronize(p->sCompute);
-	if (g.sConsume) { cudaStreamSynchronize(g.sConsume); cudaStreamDestroy(g.sConsume); g.sConsume = nullptr; }
-	if (g.evGathered) { cudaEventDestroy(g.evGathered); g.evGathered = nullptr; }
-	for (auto& e : g.evConsumed) if (e) { cudaEventDestroy(e); e = nullptr; }
 	for (int r = 0; r < OCT_MAX_PEERS; ++r) {
 		if (g.opened[r] && g.peerBase[r]) cudaIpcCloseMemHandle(g.peerBase[r]);
 		g.opened[r] = false; g.peerBase[r] = nullptr;
