@@ -6,13 +6,16 @@ speaks (octproz_plugins/octproz-socket-stream-extension, docs/docs/plugin-socket
   * text protocol on the same socket (src/broadcaster.cpp:262-291): `ping` -> `pong\\n`, `enable_command_only_mode` /
     `disable_command_only_mode` move a connection between the data list and the command list, anything else is handed to the
     host as a remote command (`remote_start`, `set_disp_coeff:...`, ...);
-  * transports: TCP/IP and IPC (QLocalServer = a Unix domain socket on Linux).  The WebSocket mode of the reference needs a
-    WebSocket stack and is not provided here.
+  * transports: TCP/IP, IPC (QLocalServer = a Unix domain socket on Linux) and WebSocket (QWebSocketServer in the reference,
+    broadcaster.cpp:74-76,104-110,192-247: every buffer is ONE binary message, header included; commands and replies are text
+    messages) -- a minimal RFC 6455 server side here (handshake, unfragmented frames, ping / close), enough for browser clients.
 Pure host code (stdlib sockets); the payload is the converted output the pipeline streams to the host
 (octb200_register_streaming_buffers + callback, the reference's Gpu2HostNotifier path).
 """
 from __future__ import annotations
 
+import base64
+import hashlib
 import math
 import os
 import selectors
@@ -25,7 +28,79 @@ START_IDENTIFIER = 299792458                      # broadcaster.cpp:39
 HEADER_FORMAT = ">IIHHB"                          # QDataStream BigEndian: quint32 quint32 quint16 quint16 quint8 (broadcaster.cpp:295-301)
 HEADER_SIZE = struct.calcsize(HEADER_FORMAT)      # 13
 
-MODE_IPC, MODE_TCPIP = "ipc", "tcpip"             # CommunicationMode (socketstreamextensionparameters.h:10-14)
+MODE_IPC, MODE_TCPIP, MODE_WEBSOCKET = "ipc", "tcpip", "websocket"    # CommunicationMode (socketstreamextensionparameters.h:10-14)
+WS_GUID = "258EAFA5-E914-47DA-95CA-C5AB0DC85B11"  # RFC 6455 section 1.3
+WS_TEXT, WS_BINARY, WS_CLOSE, WS_PING, WS_PONG = 0x1, 0x2, 0x8, 0x9, 0xA
+
+
+def _recv_exact(sock: socket.socket, n: int) -> bytes:
+    chunks, got = [], 0
+    while got < n:
+        b = sock.recv(min(1 << 20, n - got))
+        if not b:
+            raise ConnectionError("socket closed")
+        chunks.append(b); got += len(b)
+    return b"".join(chunks)
+
+
+def ws_accept_key(key: str) -> str:
+    return base64.b64encode(hashlib.sha1((key + WS_GUID).encode()).digest()).decode()
+
+
+def ws_frame(opcode: int, payload: bytes, mask: bytes | None = None) -> bytes:
+    """one unfragmented frame; servers send unmasked, clients masked (RFC 6455 section 5.2)"""
+    n = len(payload)
+    head = bytes([0x80 | opcode])
+    mbit = 0x80 if mask else 0
+    if n < 126:
+        head += bytes([mbit | n])
+    elif n < (1 << 16):
+        head += bytes([mbit | 126]) + struct.pack(">H", n)
+    else:
+        head += bytes([mbit | 127]) + struct.pack(">Q", n)
+    if mask:
+        payload = bytes(b ^ mask[i & 3] for i, b in enumerate(payload)) if n < 4096 else _ws_mask_fast(payload, mask)
+        return head + mask + payload
+    return head + payload
+
+
+def _ws_mask_fast(payload: bytes, mask: bytes) -> bytes:
+    import numpy as np
+    a = np.frombuffer(payload, np.uint8)
+    m = np.frombuffer((mask * ((len(payload) + 3) // 4))[: len(payload)], np.uint8)
+    return (a ^ m).tobytes()
+
+
+def ws_read_frame(sock: socket.socket):
+    """(opcode, payload) of the next frame, unmasked if it was masked"""
+    b0, b1 = _recv_exact(sock, 2)
+    n = b1 & 0x7F
+    if n == 126:
+        n = struct.unpack(">H", _recv_exact(sock, 2))[0]
+    elif n == 127:
+        n = struct.unpack(">Q", _recv_exact(sock, 8))[0]
+    mask = _recv_exact(sock, 4) if (b1 & 0x80) else None
+    payload = _recv_exact(sock, n) if n else b""
+    if mask:
+        payload = bytes(b ^ mask[i & 3] for i, b in enumerate(payload)) if n < 4096 else _ws_mask_fast(payload, mask)
+    return b0 & 0x0F, payload
+
+
+def ws_client_connect(host: str, port: int, timeout: float = 5.0) -> socket.socket:
+    """client side of the opening handshake (tests, headless consumers)"""
+    c = socket.create_connection((host, port), timeout=timeout)
+    key = base64.b64encode(os.urandom(16)).decode()
+    c.sendall((f"GET / HTTP/1.1\r\nHost: {host}:{port}\r\nUpgrade: websocket\r\nConnection: Upgrade\r\n"
+               f"Sec-WebSocket-Key: {key}\r\nSec-WebSocket-Version: 13\r\n\r\n").encode())
+    resp = b""
+    while b"\r\n\r\n" not in resp:
+        b = c.recv(4096)
+        if not b:
+            raise ConnectionError("handshake failed")
+        resp += b
+    if b" 101 " not in resp.split(b"\r\n", 1)[0] or ws_accept_key(key).encode() not in resp:
+        raise ConnectionError("bad handshake response")
+    return c
 
 
 def pack_header(buffer_size_in_bytes: int, frame_width: int, frame_height: int, bit_depth: int) -> bytes:
@@ -67,6 +142,7 @@ class Broadcaster:
         self.dataConnections: list[socket.socket] = []
         self.commandConnections: list[socket.socket] = []
         self._unix_path = None
+        self._ws = set()              # connections that completed the WebSocket opening handshake
 
     def setParams(self, params: SocketStreamExtensionParameters) -> None:
         self.params = params
@@ -86,8 +162,12 @@ class Broadcaster:
             srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
             srv.bind(path)
             self._unix_path = path
+        elif p.mode == MODE_WEBSOCKET:
+            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)                       # QHostAddress::Any (broadcaster.cpp:106)
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind(("0.0.0.0", int(p.port)))
         else:
-            raise ValueError("unknown communication mode (WebSocket mode is not provided)")
+            raise ValueError("unknown communication mode")
         srv.listen(16)
         srv.setblocking(False)
         self._srv = srv
@@ -136,6 +216,9 @@ class Broadcaster:
                     except OSError:
                         continue
                     conn.setblocking(True)
+                    if self.params.mode == MODE_WEBSOCKET and not self._ws_handshake(conn):
+                        conn.close()
+                        continue
                     with self._lock:
                         self.dataConnections.append(conn)           # new clients receive data until they opt out (:186)
                     self._sel.register(conn, selectors.EVENT_READ, "client")
@@ -143,16 +226,60 @@ class Broadcaster:
                         self.on_info("Client connected!")
                 else:
                     conn = key.fileobj
-                    try:
-                        data = conn.recv(65536)
-                    except OSError:
-                        data = b""
-                    if not data:
-                        self._drop(conn)
-                        continue
+                    if conn in self._ws:
+                        try:
+                            op, data = ws_read_frame(conn)
+                        except (OSError, ConnectionError, struct.error):
+                            op, data = WS_CLOSE, b""
+                        if op == WS_PING:
+                            self._send(conn, data, WS_PONG)
+                            continue
+                        if op == WS_CLOSE:
+                            self._drop(conn)
+                            continue
+                        if op not in (WS_TEXT, WS_BINARY):
+                            continue
+                    else:
+                        try:
+                            data = conn.recv(65536)
+                        except OSError:
+                            data = b""
+                        if not data:
+                            self._drop(conn)
+                            continue
                     self.processIncomingMessage(data.decode("utf-8", "replace").strip(), conn)
 
+    def _ws_handshake(self, conn) -> bool:
+        """server side of the opening handshake (RFC 6455 section 4.2)"""
+        try:
+            conn.settimeout(2.0)
+            req = b""
+            while b"\r\n\r\n" not in req and len(req) < 16384:
+                b = conn.recv(4096)
+                if not b:
+                    return False
+                req += b
+            key = None
+            for line in req.split(b"\r\n"):
+                if line.lower().startswith(b"sec-websocket-key:"):
+                    key = line.split(b":", 1)[1].strip().decode()
+            if key is None:
+                conn.sendall(b"HTTP/1.1 400 Bad Request\r\n\r\n")
+                return False
+            conn.sendall(("HTTP/1.1 101 Switching Protocols\r\nUpgrade: websocket\r\nConnection: Upgrade\r\n"
+                          f"Sec-WebSocket-Accept: {ws_accept_key(key)}\r\n\r\n").encode())
+            conn.settimeout(None)
+            self._ws.add(conn)
+            return True
+        except OSError:
+            return False
+
+    def _send(self, conn, data: bytes, ws_opcode: int = WS_TEXT) -> None:
+        """a reply on the connection's own framing: raw bytes, or one WebSocket message"""
+        conn.sendall(ws_frame(ws_opcode, data) if conn in self._ws else data)
+
     def _drop(self, conn) -> None:
+        self._ws.discard(conn)
         try:
             self._sel.unregister(conn)
         except (KeyError, ValueError):
@@ -170,21 +297,21 @@ class Broadcaster:
     def processIncomingMessage(self, dataString: str, device) -> None:
         """broadcaster.cpp:262-291"""
         if dataString == "ping":
-            device.sendall(b"pong\n")
+            self._send(device, b"pong\n")
         elif dataString == "enable_command_only_mode":
             with self._lock:
                 moved = device in self.dataConnections
                 if moved:
                     self.dataConnections.remove(device); self.commandConnections.append(device)
             if moved:
-                device.sendall(b"Command mode enabled.\n")
+                self._send(device, b"Command mode enabled.\n")
         elif dataString == "disable_command_only_mode":
             with self._lock:
                 moved = device in self.commandConnections
                 if moved:
                     self.commandConnections.remove(device); self.dataConnections.append(device)
             if moved:
-                device.sendall(b"Command mode disabled.\n")
+                self._send(device, b"Command mode disabled.\n")
         elif self.on_remote_command:
             self.on_remote_command(dataString)
 
@@ -197,7 +324,11 @@ class Broadcaster:
         sent = 0
         for c in targets:
             try:
-                c.sendall(head); c.sendall(payload); sent += 1
+                if c in self._ws:
+                    c.sendall(ws_frame(WS_BINARY, head + bytes(payload)))     # one binary message per buffer (broadcaster.cpp:321-325)
+                else:
+                    c.sendall(head); c.sendall(payload)
+                sent += 1
             except OSError:
                 self._drop(c)
         return sent

@@ -72,3 +72,19 @@ def test_header_is_plain_c99_and_links(tmp_path):
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "abi ok" in out.stdout
     assert f"sizeof_config {C.sizeof(_lib.Config)} sizeof_params {C.sizeof(_lib.Params)}" in out.stdout
+
+
+def test_adapter_gl_interop_branch_compiles():
+    """the adapter's CUDA-GL interop branch (cuda_registerGlBuffer*, PBO mapping in octCudaPipeline, the volume view
+    through octb200_volume_u8 + cudaMemcpy3DAsync, cuda_code.cu:1310-1355,1607-1695) is compiled by oracle/Makefile against the toolkit's
+    cuda_gl_interop.h and the <GL/gl.h> stand-in (there is no libGL in the image: compile-only); the object must define the three
+    registration entry points with the GL branch's code behind them"""
+    import subprocess
+    obj = os.path.join(ROOT, "oracle", "_ref", "adapter_gl.o")
+    if not os.path.exists(obj):
+        pytest.skip("oracle/_ref/adapter_gl.o is built where /root/reference exists")
+    syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True, check=True).stdout
+    for name in ("cuda_registerGlBufferBscan", "cuda_registerGlBufferEnFaceView", "cuda_registerGlBufferVolumeView", "octCudaPipeline"):
+        assert f" T {name}" in syms, name
+    for need in ("cudaGraphicsGLRegisterBuffer", "cudaGraphicsGLRegisterImage", "cudaGraphicsSubResourceGetMappedArray", "cudaMemcpy3DAsync", "octb200_volume_u8"):
+        assert f" U {need}" in syms, need

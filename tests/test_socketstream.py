@@ -77,3 +77,36 @@ def test_broadcast_and_text_protocol(mode, tmp_path):
     finally:
         b.stopBroadcasting()
     assert not b.isBroadcasting and b.address is None
+
+
+def test_websocket_mode_binary_messages_and_text_protocol():
+    """CommunicationMode::WebSocket (broadcaster.cpp:74-76,192-247,321-325): one binary message per processed buffer (13-byte header
+    included), commands and replies as text messages, over an RFC 6455 connection"""
+    from octproz_b200.socketstream import (MODE_WEBSOCKET, WS_BINARY, WS_CLOSE, WS_PING, WS_PONG, WS_TEXT, unpack_header, ws_accept_key,
+                                           ws_client_connect, ws_frame, ws_read_frame, HEADER_SIZE)
+    assert ws_accept_key("dGhlIHNhbXBsZSBub25jZQ==") == "s3pPLMBiTxaQ9kYGzzhZRbK+xOo="      # the known answer of RFC 6455 section 1.3
+    cmds = []
+    b = Broadcaster(SocketStreamExtensionParameters(mode=MODE_WEBSOCKET, port=0), on_remote_command=cmds.append)
+    b.startBroadcasting()
+    try:
+        port = b.address[1]
+        data, cmd = ws_client_connect("127.0.0.1", port), ws_client_connect("127.0.0.1", port)
+        assert _wait(lambda: len(b.dataConnections) == 2)
+        mask = b"\x11\x22\x33\x44"
+        cmd.sendall(ws_frame(WS_TEXT, b"ping", mask)); assert ws_read_frame(cmd) == (WS_TEXT, b"pong\n")
+        cmd.sendall(ws_frame(WS_PING, b"abc", mask)); assert ws_read_frame(cmd) == (WS_PONG, b"abc")
+        cmd.sendall(ws_frame(WS_TEXT, b"enable_command_only_mode", mask)); assert ws_read_frame(cmd) == (WS_TEXT, b"Command mode enabled.\n")
+        assert _wait(lambda: len(b.dataConnections) == 1 and len(b.commandConnections) == 1)
+        cmd.sendall(ws_frame(WS_TEXT, b"remote_start", mask))
+        assert _wait(lambda: cmds == ["remote_start"])
+        # a buffer larger than 64 KiB: 64-bit payload length
+        frames = (np.arange(2 * 128 * 256, dtype=np.uint32) * 7 % 4096).astype(np.uint16).reshape(2, 128, 256)
+        assert SocketStreamExtension(b).processedDataReceived(frames, 12, 256, 128, 2) == 1
+        op, msg = ws_read_frame(data)
+        assert op == WS_BINARY and unpack_header(msg) == {"size": frames.nbytes, "width": 256, "height": 128, "bitDepth": 12}
+        assert msg[HEADER_SIZE:] == frames.tobytes()
+        data.sendall(ws_frame(WS_CLOSE, b"", mask))
+        assert _wait(lambda: len(b.dataConnections) == 0)
+        cmd.close()
+    finally:
+        b.stopBroadcasting()
