@@ -998,6 +998,8 @@ int octb200_enface_gather_init(octb200_pipeline* p, int rank, int world, uint32_
 	g.world = world; g.rank = rank; g.Eglobal = globalLines; g.offset = lineOffset; g.seq = 0; g.consumedSeq = 0;
 	g.frameStride = ((size_t)globalLines * sizeof(float) + 255) / 256 * 256;
 	{ int rc = dalloc(p, &g.window, OCT_GATHER_HEADER_BYTES + OCT_GATHER_FRAMES * g.frameStride); if (rc) return rc; }
+	{ int rc = dalloc(p, &g.counter, 4); if (rc) return rc; }
+	{ int rc = dalloc(p, &g.display, (size_t)globalLines + 4); if (rc) return rc; }
 	cudaIpcMemHandle_t h;
 	CK(p, cudaIpcGetMemHandle(&h, g.window));
 	static_assert(sizeof(h) == OCTB200_IPC_HANDLE_BYTES, "ipc handle size");
