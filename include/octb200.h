@@ -146,6 +146,16 @@ OCTB200_API const char* octb200_last_error(const octb200_pipeline* p);   /* p ma
 OCTB200_API int octb200_version(void);
 OCTB200_API void octb200_default_params(octb200_params* out);           /* octalgorithmparameters.cpp:36-112 defaults */
 OCTB200_API int octb200_effective_fft_mode(const octb200_pipeline* p);
+/* which kernels OCTB200_FFT_AUTO runs the FFT stage of a geometry on -- host logic only, needs no GPU.  Returns one of OCTB200_PATH_*
+   (negative: invalid geometry); for the shared-memory kernel `radices[0 .. *nPasses)` receives the plan of its Stockham passes
+   (product = samplesPerLine; radices 13, 11, 7, 5, 3 first, then 8s, then 4 / 4·4 / 2).  radices (16 ints) and nPasses may be NULL.
+   The reference plans cuFFT for any length (cuda_code.cu:1140); its default geometry is 1664 samples per line. */
+enum { OCTB200_PATH_REGISTER_KERNEL = 1,                 /* 1024 / 2048: fused, transform in registers (u8 / u16 / u32 containers) */
+       OCTB200_PATH_SHARED_MEMORY_KERNEL = 2,            /* fused, mixed-radix transform in shared memory */
+       OCTB200_PATH_CUFFT_CHAIN = 3,                     /* pre kernel + cuFFT + post kernel: prime factors > 13 or > 8192 samples */
+       OCTB200_PATH_CUFFT_CHAIN_SHARED_AVAILABLE = 4 };  /* short power-of-two lines: AUTO takes the cuFFT chain (as fast or faster on a
+                                                            B200), an explicit OCTB200_FFT_FUSED gets the shared-memory kernel */
+OCTB200_API int octb200_query_fft_path(uint32_t samplesPerLine, uint32_t bitDepth, int32_t* radices, int32_t* nPasses);
 
 /* ---------- parameters and curves ---------- */
 /* replaces the unsynchronised reads of the OctAlgorithmParameters singleton inside octCudaPipeline */

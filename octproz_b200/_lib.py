@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("OCTB200_LIB", os.path.join(_HERE, "liboctb200.so"))  
 # every symbol include/octb200.h declares (tests check the list against the header)
 SYMBOLS = [
     "octb200_create", "octb200_destroy", "octb200_last_error", "octb200_version", "octb200_default_params",
-    "octb200_effective_fft_mode", "octb200_set_params", "octb200_set_resample_curve", "octb200_set_dispersion_curve",
+    "octb200_effective_fft_mode", "octb200_query_fft_path", "octb200_set_params", "octb200_set_resample_curve", "octb200_set_dispersion_curve",
     "octb200_set_window_curve", "octb200_set_postprocess_background", "octb200_get_postprocess_background",
     "octb200_get_fpn_mean_line", "octb200_set_fpn_mean_line", "octb200_get_fpn_segment_stats", "octb200_make_resample_curve",
     "octb200_make_dispersion_curve", "octb200_make_window_curve", "octb200_make_sinusoidal_curve",
@@ -37,6 +37,7 @@ INTERP_LINEAR, INTERP_CUBIC, INTERP_LANCZOS = 0, 1, 2
 PACK_CONTAINER, PACK_12P = 0, 1
 FLAG_SEPARATE_CONVERSION = 1
 FLAG_NO_DEPENDENT_LAUNCH = 2
+PATH_REGISTER_KERNEL, PATH_SHARED_MEMORY_KERNEL, PATH_CUFFT_CHAIN, PATH_CUFFT_CHAIN_SHARED_AVAILABLE = 1, 2, 3, 4
 
 
 class Config(C.Structure):
@@ -95,6 +96,7 @@ def load() -> C.CDLL:
     lib.octb200_last_error.argtypes = [P]; lib.octb200_last_error.restype = C.c_char_p
     lib.octb200_default_params.argtypes = [C.POINTER(Params)]; lib.octb200_default_params.restype = None
     lib.octb200_effective_fft_mode.argtypes = [P]
+    lib.octb200_query_fft_path.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.octb200_set_params.argtypes = [P, C.POINTER(Params)]
     for n in ("octb200_set_resample_curve", "octb200_set_dispersion_curve", "octb200_set_window_curve",
               "octb200_set_postprocess_background", "octb200_get_postprocess_background",

@@ -595,6 +595,24 @@ void octb200_default_params(octb200_params* o) {
 const char* octb200_last_error(const octb200_pipeline* p) { return p ? p->err.c_str() : g_createError.c_str(); }
 int octb200_effective_fft_mode(const octb200_pipeline* p) { return p ? p->mode : OCTB200_ERR_INVALID; }
 
+int octb200_query_fft_path(uint32_t samplesPerLine, uint32_t bitDepth, int32_t* radices, int32_t* nPasses) {
+	if (samplesPerLine < 8 || (samplesPerLine & 1) || bitDepth < 1 || bitDepth > 32) return OCTB200_ERR_INVALID;
+	const int N = (int)samplesPerLine;
+	const int rawBytes = bitDepth <= 8 ? 1 : (bitDepth <= 16 ? 2 : 4);
+	if (nPasses) *nPasses = 0;
+	if (N == 1024 || N == 2048) return OCTB200_PATH_REGISTER_KERNEL;
+	int radix[16] = {}, passes = 0, twOff[16]; unsigned magic[16];
+	bool generic = generic_fft_plan(N, radix, &passes);
+	if (generic) generic = generic_fits(N, rawBytes, 0, 0, false, generic_twiddle_layout(N, radix, passes, twOff, magic));
+	if (generic) {
+		if (nPasses) *nPasses = passes;
+		if (radices) for (int i = 0; i < passes; ++i) radices[i] = radix[i];
+		const bool pow2 = (N & (N - 1)) == 0;
+		return (!pow2 || N > 2048) ? OCTB200_PATH_SHARED_MEMORY_KERNEL : OCTB200_PATH_CUFFT_CHAIN_SHARED_AVAILABLE;
+	}
+	return OCTB200_PATH_CUFFT_CHAIN;
+}
+
 int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	if (!cfg || !out) return fail(nullptr, OCTB200_ERR_INVALID, "null argument");
 	*out = nullptr;

@@ -88,3 +88,39 @@ def test_adapter_gl_interop_branch_compiles():
         assert f" T {name}" in syms, name
     for need in ("cudaGraphicsGLRegisterBuffer", "cudaGraphicsGLRegisterImage", "cudaGraphicsSubResourceGetMappedArray", "cudaMemcpy3DAsync", "octb200_volume_u8"):
         assert f" U {need}" in syms, need
+
+
+def test_fft_path_query_and_plans_without_a_gpu():
+    """host logic of the kernel selection (include/octb200.h octb200_query_fft_path): the Stockham plan of the shared-memory kernel
+    multiplies out to the line length with radices from {2, 3, 4, 5, 7, 8, 11, 13}, odd primes first; AUTO's policy per geometry"""
+    lib = _lib.load()
+    def q(n, bits=12):
+        rad = (C.c_int32 * 16)(); cnt = C.c_int32()
+        rc = lib.octb200_query_fft_path(n, bits, rad, C.byref(cnt))
+        return rc, list(rad[: cnt.value])
+    assert q(1024)[0] == _lib.PATH_REGISTER_KERNEL and q(2048, 8)[0] == _lib.PATH_REGISTER_KERNEL and q(1024, 32)[0] == _lib.PATH_REGISTER_KERNEL
+    assert q(1664) == (_lib.PATH_SHARED_MEMORY_KERNEL, [13, 8, 4, 4])          # the reference's default line length: 13 * 128
+    assert q(4096) == (_lib.PATH_SHARED_MEMORY_KERNEL, [8, 8, 8, 8])
+    assert q(8192) == (_lib.PATH_SHARED_MEMORY_KERNEL, [8, 8, 8, 4, 4])
+    assert q(1536) == (_lib.PATH_SHARED_MEMORY_KERNEL, [3, 8, 8, 8])
+    assert q(8190)[1] == [13, 7, 5, 3, 3, 2]
+    assert q(512) == (_lib.PATH_CUFFT_CHAIN_SHARED_AVAILABLE, [8, 8, 8]) and q(16) == (_lib.PATH_CUFFT_CHAIN_SHARED_AVAILABLE, [4, 4])
+    assert q(1006)[0] == _lib.PATH_CUFFT_CHAIN and q(34)[0] == _lib.PATH_CUFFT_CHAIN and q(8232)[0] == _lib.PATH_CUFFT_CHAIN and q(16384)[0] == _lib.PATH_CUFFT_CHAIN
+    assert q(1001)[0] == _lib.ERR_INVALID and q(4)[0] == _lib.ERR_INVALID and q(1024, 40)[0] == _lib.ERR_INVALID
+    for n in range(8, 8193, 2):
+        rc, rad = q(n)
+        if rc in (_lib.PATH_SHARED_MEMORY_KERNEL, _lib.PATH_CUFFT_CHAIN_SHARED_AVAILABLE):
+            prod = 1
+            for r in rad:
+                assert r in (2, 3, 4, 5, 7, 8, 11, 13)
+                prod *= r
+            assert prod == n and len(rad) <= 16, (n, rad)
+            odd = [r for r in rad if r % 2]
+            assert rad[: len(odd)] == odd == sorted(odd, reverse=True), (n, rad)      # odd primes first, descending
+            assert sum(1 for r in rad if r == 2) <= 1
+        elif rc == _lib.PATH_CUFFT_CHAIN:
+            m = n
+            for pr in (2, 3, 5, 7, 11, 13):
+                while m % pr == 0:
+                    m //= pr
+            assert m != 1, n                 # only lengths with a prime factor above 13 are left to cuFFT below 8192
