@@ -44,9 +44,7 @@ struct GenericArgs {
 	unsigned magic[16];      /* ceil(2^32 / Ns) of every pass: j mod Ns without a division */
 	int twEntries;           /* total entries of the twiddle tables (copied into shared memory once per CTA) */
 };
-bool generic_fft_plan(int N, int* radix, int* nPass);
-int generic_twiddle_layout(int N, const int* radix, int nPass, int* twOff, unsigned* magic);
-void generic_fill_twiddles(const int* radix, int nPass, const int* twOff, float2* tw);
+/* plan / twiddle builders: generic_fft.cuh (inline, shared with the CPU emulator) */
 bool generic_fits(int N, int rawBytes, int HB, int HA, bool roll, int twEntries);
 cudaError_t launch_generic(const GenericArgs& a, int rawBytes, int sa, bool roll, int smCount, cudaStream_t st);
 

@@ -9,6 +9,7 @@
  */
 #include "../../include/octb200.h"
 #include "k_aux.cuh"
+#include "generic_fft.cuh"
 #include "oct_curves.hpp"
 #include "oct_luts.hpp"
 

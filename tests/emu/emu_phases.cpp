@@ -116,3 +116,42 @@ extern "C" int emu_fused_line(int N, int sa, int interp, const float* fslot /* h
 	}
 	return 0;
 }
+
+/* ---- the shared-memory kernel's transform (generic_fft.cuh): plan, per-pass twiddle tables, padded line buffers and the Stockham
+ * passes exactly as oct_generic_kernel runs them, with T "threads" executed one after the other (a pass reads one buffer and writes the
+ * other, so the order of the threads inside a pass does not matter -- as on the GPU between two barriers) ---- */
+#include "generic_fft.cuh"
+
+extern "C" int emu_generic_ifft(int N, int T, const float* in, float* out /* N complex, natural order */, int* radixOut, int* nPassOut) {
+	int radix[16] = {}, nPass = 0, twOff[16]; unsigned magic[16];
+	if (!generic_fft_plan(N, radix, &nPass)) return -1;
+	const int entries = generic_twiddle_layout(N, radix, nPass, twOff, magic);
+	std::vector<float2> tw((size_t)entries, make_float2(1.f, 0.f));
+	generic_fill_twiddles(radix, nPass, twOff, tw.data());
+	std::vector<float2> A((size_t)gpad_len(N)), B((size_t)gpad_len(N));
+	for (int m = 0; m < N; ++m) A[gpad(m)] = make_float2(in[2 * m], in[2 * m + 1]);
+	const float2* src = A.data(); float2* dst = B.data();
+	int Ns = 1;
+	for (int ps = 0; ps < nPass; ++ps) {
+		const int R = radix[ps];
+		for (int tid = 0; tid < T; ++tid) {
+			switch (R) {
+			case 2: stockham_pass<2>(src, dst, N, Ns, magic[ps], tw.data() + twOff[ps], tid, T); break;
+			case 3: stockham_pass<3>(src, dst, N, Ns, magic[ps], tw.data() + twOff[ps], tid, T); break;
+			case 4: stockham_pass<4>(src, dst, N, Ns, magic[ps], tw.data() + twOff[ps], tid, T); break;
+			case 5: stockham_pass<5>(src, dst, N, Ns, magic[ps], tw.data() + twOff[ps], tid, T); break;
+			case 7: stockham_pass<7>(src, dst, N, Ns, magic[ps], tw.data() + twOff[ps], tid, T); break;
+			case 8: stockham_pass<8>(src, dst, N, Ns, magic[ps], tw.data() + twOff[ps], tid, T); break;
+			case 11: stockham_pass<11>(src, dst, N, Ns, magic[ps], tw.data() + twOff[ps], tid, T); break;
+			case 13: stockham_pass<13>(src, dst, N, Ns, magic[ps], tw.data() + twOff[ps], tid, T); break;
+			default: return -2;
+			}
+		}
+		Ns *= R;
+		const float2* t = src; src = dst; dst = const_cast<float2*>(t);
+	}
+	for (int z = 0; z < N; ++z) { out[2 * z] = src[gpad(z)].x; out[2 * z + 1] = src[gpad(z)].y; }
+	if (radixOut) for (int i = 0; i < nPass; ++i) radixOut[i] = radix[i];
+	if (nPassOut) *nPassOut = nPass;
+	return 0;
+}

@@ -65,3 +65,25 @@ def test_fused_line_matches_oracle(emu, n, case):
                             None, None, 0.0, 0.0, out.ctypes.data, None)
     assert rc == 0
     assert_parity(out.reshape(1, 1, -1), ref, q, what=f"emulated fused line N={n} {case}")
+
+
+@pytest.mark.parametrize("n", [8, 16, 48, 100, 130, 512, 640, 896, 1024, 1408, 1536, 1664, 2560, 3072, 4096, 4160, 5632, 8190, 8192])
+def test_generic_mixed_radix_transform(emu, n):
+    """the shared-memory kernel's inverse transform (octproz_b200/csrc/generic_fft.cuh: Stockham autosort passes over padded line
+    buffers, radices 13 / 11 / 7 / 5 / 3 / 8 / 4 / 2, per-pass twiddle tables, j mod Ns by multiply-high) executed on the CPU with the
+    kernel's own thread counts against numpy, for every radix and the lengths the GPU tests use"""
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    ref = np.fft.ifft(x.astype(np.complex128)) * n
+    for threads in {64 if n < 1024 else (128 if n < 2048 else 256), 32}:
+        o = np.zeros(n, np.complex64)
+        rad = (C.c_int * 16)(); cnt = C.c_int()
+        rc = emu.emu_generic_ifft(n, threads, x.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), rad, C.byref(cnt))
+        assert rc == 0
+        assert int(np.prod(list(rad[: cnt.value]))) == n
+        assert np.abs(o - ref).max() < 2e-6 * np.abs(ref).max(), (n, threads, list(rad[: cnt.value]))
+
+
+def test_generic_transform_refuses_large_prime_factors(emu):
+    o = np.zeros(34, np.complex64)
+    assert emu.emu_generic_ifft(34, 32, o.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), None, None) == -1      # 2 * 17
