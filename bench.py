@@ -480,6 +480,11 @@ def main():
         return reference_arm(args, q, config)
 
     # ------------------------------------------------------------------ our arm (B200)
+    # stdout carries exactly ONE line, the JSON: libraries that print there (NCCL's version banner at the first communicator) are
+    # sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from octproz_b200 import _lib
     if not torch.cuda.is_available():
@@ -669,7 +674,8 @@ def main():
         line["ref_cuda"] = ref_cuda
     if secondary is not None:
         line["secondary"] = secondary
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     return 0
 
 
