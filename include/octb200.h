@@ -142,7 +142,7 @@ typedef void (*octb200_host_callback)(void* hostBuffer);
 OCTB200_API int octb200_create(const octb200_config* cfg, octb200_pipeline** out);
 /* replaces cleanupCuda / releaseBuffers / destroyStreamsAndEvents (kernels.h:65-67, cuda_code.cu:1164-1212) */
 OCTB200_API int octb200_destroy(octb200_pipeline* p);
-OCTB200_API const char* octb200_last_error(const octb200_pipeline* p);   /* p may be NULL: error of the last failed create */
+OCTB200_API const char* octb200_last_error(const octb200_pipeline* p);   /* p may be NULL: error of the calling thread's last failed create */
 OCTB200_API int octb200_version(void);
 OCTB200_API void octb200_default_params(octb200_params* out);           /* octalgorithmparameters.cpp:36-112 defaults */
 OCTB200_API int octb200_effective_fft_mode(const octb200_pipeline* p);

@@ -59,9 +59,10 @@ __device__ __forceinline__ float u16hi_to_float(uint32_t w) { return __uint_as_f
 template <int B> __device__ __forceinline__ float u8_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | B)) - 8388608.0f; }
 
 /* ---------------- en-face gather over peer memory, fused into the epilogue (multi-GPU shards) ----------------
- * world > 0: the lane that finalises depth bin frameNr of a line (updateDisplayedEnFaceFrame with one frame, cuda_code.cu:909)
- * keeps that output value in a register; a line group works through blocks of `lineBlock` CONSECUTIVE lines, so after a block its
- * warp holds lineBlock neighbouring en-face values and stores them -- one coalesced 4*lineBlock-byte store per rank -- straight into
+ * world > 0: a line group works through blocks of `lineBlock` CONSECUTIVE lines; after a block, lanes 0 .. lineBlock-1 of its first
+ * warp read depth bin frameNr of "their" line (updateDisplayedEnFaceFrame with one frame, cuda_code.cu:909) back from L2 -- the
+ * epilogue's stores are ordered before the group's end-of-line barrier -- and store the lineBlock neighbouring en-face values, one
+ * coalesced 4*lineBlock-byte store per rank, straight into
  * the frame window of EVERY rank (peer-mapped pointers: P2P stores over NVLink / NVSwitch; the own rank is a plain store).  The
  * stores are spread over the whole kernel, there is no end-of-kernel push and no grid barrier: a CTA that has finished its lines
  * fences once at system scope and bumps a counter; the last one publishes `seq` in every rank's "arrived" word for this rank.
@@ -80,7 +81,7 @@ constexpr int OCT_GATHER_ARRIVED = 0, OCT_GATHER_ACK = 64, OCT_GATHER_HEADER_BYT
 constexpr int OCT_GATHER_FRAMES = 3;       /* frame buffers per window, used round-robin by sequence number */
 constexpr unsigned long long OCT_GATHER_TIMEOUT_NS = 10ull * 1000ull * 1000ull * 1000ull;
 struct GatherDev {
-	float* frames[OCT_MAX_PEERS];      /* frame window (parity of seq) of every rank */
+	float* frames[OCT_MAX_PEERS];      /* frame buffer seq % OCT_GATHER_FRAMES in the window of every rank */
 	unsigned* flags[OCT_MAX_PEERS];    /* header of every rank's window: arrived[] at word 0, ack[] at word 64 */
 	unsigned* counter;                 /* local CTA completion counter (zero between launches) */
 	unsigned* status;                  /* local: [0] = time-outs waiting for acknowledgements, [1] = time-outs waiting for arrivals */
@@ -110,7 +111,7 @@ __device__ __forceinline__ bool gather_spin_ge(const unsigned* word, unsigned wa
 /* producer prologue (the lanes of ONE warp per CTA, lane c looks at consumer c: one load latency for all ranks): every consumer has
  * released the frame buffer this launch is about to overwrite */
 __device__ __forceinline__ void gather_wait_acks(const GatherDev& g, int lane) {
-	if (g.world < 1 || g.seq <= (unsigned)OCT_GATHER_FRAMES) return;       /* (also with one rank: its own consumer runs on another stream) */
+	if (g.world < 1 || g.seq <= (unsigned)OCT_GATHER_FRAMES) return;       /* (the first three gathers find their buffers unused) */
 	if (lane < g.world) {
 		const unsigned* acks = g.flags[g.rank] + OCT_GATHER_ACK;
 		if (!gather_spin_ge(acks + lane, g.seq - (unsigned)OCT_GATHER_FRAMES)) atomicAdd(g.status, 1u);

@@ -27,7 +27,7 @@ using namespace octb200;
 
 namespace {
 
-std::string g_createError;
+thread_local std::string g_createError;   /* octb200_last_error(NULL): the failure of THIS thread's last octb200_create */
 
 /* ---- lazily bound cuFFT (only OCTB200_FFT_CUFFT touches it; the measured library baseline) ---- */
 struct CufftApi {
@@ -120,7 +120,7 @@ struct octb200_pipeline {
 	float* dSweepPhase = nullptr; float2* dSweepPhasor = nullptr; size_t sweepPhaseElems = 0;
 	float* dSweepMetric = nullptr; size_t sweepMetricElems = 0;
 
-	/* en-face gather over peer memory (multi-GPU shards): local window = [1 KiB header: arrived[], ack[]][frame 0][frame 1] (oct_device.cuh) */
+	/* en-face gather over peer memory (multi-GPU shards): local window = [1 KiB header: arrived[], ack[]][frame 0][frame 1][frame 2] (oct_device.cuh) */
 	struct EnfaceGather {
 		int world = 0, rank = 0;
 		unsigned Eglobal = 0, offset = 0, seq = 0, consumedSeq = 0;
@@ -319,7 +319,7 @@ GenericArgs generic_args(const octb200_pipeline* p, const Stage& st, const void*
 	return a;
 }
 
-/* next en-face gather of this handle: sequence number, frame window of that parity on every rank, header words */
+/* next en-face gather of this handle: sequence number, frame buffer seq % 3 in every rank's window, header words */
 GatherDev next_gather(octb200_pipeline* p, unsigned frameNr, unsigned nFrames, int fn) {
 	auto& g = p->eg;
 	GatherDev d{};
@@ -357,7 +357,7 @@ cudaError_t consume_gather(octb200_pipeline* p) {
 	/* in stream order, as the programmatic dependent of the kernel that produced this rank's slab.  (A consumer kernel on a stream of its
 	   own was measured and dropped: a saturated compute stream starves it -- every SM goes to the next, already queued compute grid --
 	   and a compute grid that spins in its prologue for acknowledgements then holds every SM the consumer needs: 10 s time-outs per
-	   buffer at 8 GPUs, profiles/r02l_bench_n8.json.  In order it can never be starved, and the acknowledgement of frame s is on its
+	   buffer at 8 GPUs, profiles/r02l_bench_n8_display_stream_stall.json.  In order it can never be starved, and the acknowledgement of frame s is on its
 	   way before the kernel of s + 1 starts, three buffers ahead of need.) */
 	const bool dependent = (p->pdlStamp == p->launches) && !(p->cfg.flags & OCTB200_FLAG_NO_DEPENDENT_LAUNCH);
 	cudaError_t e = launch_enface_consume(a, p->smCount, dependent, p->sCompute);
@@ -649,7 +649,7 @@ int octb200_create(const octb200_config* cfg, octb200_pipeline** out) {
 	int mode = cfg->fftMode;
 	/* FUSED = one kernel from raw samples to B-scan lines: the register kernels where they apply, else the shared-memory kernel */
 	/* AUTO: the register kernels wherever they apply; the shared-memory kernel where it beats the cuFFT chain on a B200 (measured,
-	   profiles/r02f_generic_perf.json: line lengths that are not a power of two, and N > 2048; for short power-of-two lines the three
+	   profiles/r02g_generic_and_container_perf.json: line lengths that are not a power of two, and N > 2048; for short power-of-two lines the three
 	   kernel chain around cuFFT is as fast or faster); the cuFFT chain otherwise.  An explicit FUSED is honoured wherever a fused kernel exists. */
 	const bool pow2 = (p->N & (p->N - 1)) == 0;
 	if (mode == OCTB200_FFT_AUTO) mode = p->regKernel ? OCTB200_FFT_FUSED : ((p->genericOk && (!pow2 || p->N > 2048)) ? OCTB200_FFT_FUSED : OCTB200_FFT_CUFFT);
