@@ -279,6 +279,27 @@ class Rig:
             p.enface_gather_auto(True, frame, 1, 0)
         return self.gather
 
+    def gather_health(self, dist):
+        """after a few warm-up steps: the device-side time-out counters of the peer gather, worst rank (0 / 0 in a healthy run).  If any
+        rank timed out, every rank drops to the NCCL gather together -- a stalled protocol costs 10 s per wait and would turn the timed
+        region into a measurement of the time-out -- and the JSON line says so."""
+        if self.gather != "p2p":
+            return None
+        torch = self.torch
+        try:
+            st = self.p.enface_gather_status()
+            worst = torch.tensor([float(st["ack_timeouts"]), float(st["arrival_timeouts"])], device="cuda")
+        except Exception as e:  # noqa: BLE001
+            print(f"rank {self.rank}: enface_gather_status failed ({e})", file=sys.stderr, flush=True)
+            worst = torch.zeros(2, device="cuda")
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        health = {"ack_timeouts_worst_rank": int(worst[0].item()), "arrival_timeouts_worst_rank": int(worst[1].item())}
+        if health["ack_timeouts_worst_rank"] or health["arrival_timeouts_worst_rank"]:
+            self.p.enface_gather_auto(False)
+            self.gather = "nccl"
+            health["fallback"] = "peer gather timed out during warm-up: NCCL all-gather used for the timed region"
+        return health
+
     def close(self, dist=None):
         if dist is not None:
             self.p.sync(); self.torch.cuda.synchronize(); dist.barrier()       # peers have stopped writing into this rank's window
@@ -530,7 +551,7 @@ def main():
         # p2p: the process call itself gathers (peer stores from the kernel's epilogue) and enqueues the consumer kernel of this frame
         # (wait for every rank's slab, copy the frame out, acknowledge) behind it
         r.p.process_device(r.d_raw[i & 1])
-        if gather_impl == "nccl":
+        if r.gather == "nccl":
             r.p.changeDisplayedEnFaceFrame(100, 1, 0, frame)
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(out, frame)
@@ -538,6 +559,15 @@ def main():
     # warm-up (includes LUT build, FPN determination, cuFFT plan if any)
     p.process_device(rig.d_raw[0]); p.sync(); fpn_share(rig)
 
+    ghealth = None
+    if dist is not None:
+        if args.enface == "nccl":
+            rig.gather = "nccl"
+        for i in range(4):
+            step_resident(i)
+        rig.p.sync(); torch.cuda.synchronize()
+        ghealth = rig.gather_health(dist)
+        gather_impl = rig.gather
     sampler = ClockSampler(local); sampler.start()     # samples run until the end of the end-to-end region
     ms_step, launches = timed_resident(rig, args.steps, args.warmup, dist, step_resident)
     value = world * ascans_per_step / (ms_step * 1e3)   # MHz
@@ -592,18 +622,25 @@ def main():
             # parameter marshalling of OctPipeline.process_device alone would be as long
             if strong_call(strong_h, strong_ptr[i & 1]) != 0:
                 raise RuntimeError("octb200_process_device failed")
-            if g2 != "p2p":
+            if rs.gather != "p2p":
                 rs.p.changeDisplayedEnFaceFrame(100, 1, 0, en_s)
                 with torch.cuda.stream(torch.cuda.ExternalStream(int(rs.p._lib.octb200_compute_stream(rs.p.handle)), device=torch.device("cuda", local))):
                     dist.all_gather_into_tensor(ga_s, en_s)
         rs.p.process_device(rs.d_raw[0]); rs.p.sync(); fpn_share(rs)
+        if g2 != "p2p":
+            rs.gather = "nccl"
+        for i in range(4):
+            step_strong(i)
+        rs.p.sync(); torch.cuda.synchronize()
+        health_s = rs.gather_health(dist)
+        g2 = rs.gather
         k_strong = max(args.steps, 50)
         ms_s, l_s = timed_resident(rs, k_strong, args.warmup, dist, step_strong)
         sc = gather_check(rs, dist, a * bs) if g2 == "p2p" else None
         kern_s = rs.p.time_kernel(rs.d_raw[1], 50)
         strong = {"scaling": "strong", "value": ascans_per_step / (ms_s * 1e3), "unit": UNIT, "volumes_per_s": 1e3 / ms_s, "ms_per_volume": ms_s,
                   "steps": k_strong, "bscans_per_rank": bs, "gpu_launches_per_step": l_s / k_strong, "fused_kernel_alone_ms": kern_s,
-                  "tail_us_per_step": (ms_s - kern_s) * 1e3, "gather": g2, "gather_check": sc,
+                  "tail_us_per_step": (ms_s - kern_s) * 1e3, "gather": g2, "gather_check": sc, "gather_health": health_s,
                   "note": "each step = the whole 1024x512x256 volume; per-rank inputs (32 MiB at N = 8) alternate between two buffers and stay L2-resident "
                           "at N >= 4 -- the kernel is not HBM-bound, so this does not flatter it"}
         rs.close(dist)
@@ -658,7 +695,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours", "config": config, "mode": args.mode,
             "gather": None if world == 1 else {"impl": gather_impl, "every_step": "peer-memory stores from the fused kernel's epilogue + consumer kernel (wait for all slabs, copy out, acknowledge) in stream order"
-                                               if gather_impl == "p2p" else "extraction kernel + ncclAllGather", "check": gcheck},
+                                               if gather_impl == "p2p" else "extraction kernel + ncclAllGather", "check": gcheck, "health": ghealth},
             "e2e": {"value": e2e_mhz, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": conv_bytes,
                     "ms_per_step": e2e_s * 1e3 / e2e_steps, "steps": e2e_steps, "timer": "host wall clock between device synchronisations, max over ranks",
                     "checksum": checksum, "gpu_launches_per_step": e2e_launches,
