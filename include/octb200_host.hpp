@@ -12,7 +12,8 @@
  *   OctPipeline                              the kernels.h entry points (kernels.h:63-84) as methods over an octb200 handle
  *   Processing                               octproz/src/processing.cpp:124-229 (block the buffers, initializeCuda, poll the double
  *                                            buffer, octCudaPipeline, release the buffer, per-second statistics :194-207)
- *   Recorder                                 octproz/src/recorder.cpp:99-152 (N buffers into one headerless file)
+ *   Recorder / RecordingParams               octproz/src/recorder.cpp, octalgorithmparameters.h:84-98 (N buffers into one headerless file; session
+ *                                            file naming, start with the first buffer of a volume, abort, meta file = settings INI copy)
  *   DispersionEstimationEngine               octproz-dispersion-estimator-extension/src/dispersionestimationengine.cpp:21-158 (the
  *                                            search; every sweep is one octb200_dispersion_sweep call instead of n CPU passes)
  *
@@ -32,6 +33,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -422,20 +424,57 @@ private:
 	OctAlgorithmParameters* octParams_;
 };
 
-/* Recorder::slot_record (octproz/src/recorder.cpp:99-152): append `buffersToRecord` buffers (raw or processed, whatever the caller
- * connects) to ONE headerless little-endian file, then stop -- the format the Virtual OCT System replays (docs/docs/faq.md:5). */
+/* OctAlgorithmParameters::RecordingParams (octproz/src/octalgorithmparameters.h:84-98) without the GUI-only screenshot switch */
+struct RecordingParams {
+	std::string timestamp, fileName, savePath;
+	size_t bufferSizeInBytes = 0;
+	unsigned int buffersToRecord = 0;
+	bool startWithFirstBuffer = false, recordRaw = false, recordProcessed = false, saveMetaData = false, saveAs32bitFloat = false, stopAfterRecord = false;
+
+	/* <savePath>/<timestamp>[_<fileName>]: shared by every file of one recording session (recorder.cpp:77-82, octprozapp.cpp:296) */
+	std::string sessionPrefix() const { return savePath + "/" + timestamp + (fileName.empty() ? std::string() : "_" + fileName); }
+	/* what Processing::slot_enableRecording hands to the processed-data recorder (processing.cpp:243-249) */
+	RecordingParams forProcessedData(const AcquisitionParams& a) const {
+		RecordingParams r = *this;
+		r.bufferSizeInBytes = saveAs32bitFloat ? (size_t)(a.samplesPerLine / 2) * a.ascansPerBscan * a.bscansPerBuffer * sizeof(float) : bufferSizeInBytes / 2;
+		return r;
+	}
+	/* the meta file of a recording is a copy of the settings INI (octprozapp.cpp:294-298); returns its path, empty if not written */
+	std::string saveMeta(const std::string& settingsFile) const {
+		if (!saveMetaData) return {};
+		const std::string dst = sessionPrefix() + "_meta.txt";
+		FILE* in = std::fopen(settingsFile.c_str(), "rb");
+		if (!in) return {};
+		FILE* out = std::fopen(dst.c_str(), "wb");
+		if (!out) { std::fclose(in); return {}; }
+		char buf[4096]; size_t k;
+		while ((k = std::fread(buf, 1, sizeof(buf), in)) > 0) std::fwrite(buf, 1, k, out);
+		std::fclose(in); std::fclose(out);
+		return dst;
+	}
+};
+
+/* octproz/src/recorder.cpp.  Two ways in:
+ *   Recorder(path, bytesPerBuffer, buffersToRecord) + record(buf): N buffers (raw or processed, whatever the caller connects) appended to ONE
+ *     headerless little-endian file -- the format the Virtual OCT System replays (docs/docs/faq.md:5); recorder.cpp:99-152 in its plainest form;
+ *   Recorder("raw" | "processed") + init(RecordingParams) + record(buf, currentBufferNr) + abort(): the reference's recording session -- file
+ *     <savePath>/<timestamp>[_<fileName>]_<name>.raw (:77-82), optional start at the first buffer of a volume (:116-119), capture in memory
+ *     and one write when the last buffer has arrived or on abort (:52-62, :124-131). */
 class Recorder {
 public:
 	Recorder(const std::string& path, size_t bytesPerBuffer, unsigned int buffersToRecord)
-	    : bytesPerBuffer_(bytesPerBuffer), buffersToRecord_(buffersToRecord), f_(std::fopen(path.c_str(), "wb")) {}
+	    : bytesPerBuffer_(bytesPerBuffer), buffersToRecord_(buffersToRecord), f_(std::fopen(path.c_str(), "wb")), path_(path) {}
+	explicit Recorder(const std::string& name) : bytesPerBuffer_(0), buffersToRecord_(0), f_(nullptr), name_(name), session_(true) {}
 	Recorder(const Recorder&) = delete;
 	Recorder& operator=(const Recorder&) = delete;
 	~Recorder() { close(); }
 	bool isOpen() const { return f_ != nullptr; }
 	unsigned int recordedBuffers() const { return recorded_; }
-	bool finished() const { return recorded_ >= buffersToRecord_; }
-	/* returns false once the requested number of buffers has been written (recorder.cpp:124-131: recording finished) */
+	bool finished() const { return session_ ? recordingFinished_ : recorded_ >= buffersToRecord_; }
+	const std::string& path() const { return path_; }
+	/* plain form: returns false once the requested number of buffers has been written (recorder.cpp:124-131: recording finished) */
 	bool record(const void* buffer) {
+		if (session_) return record(buffer, 0u);
 		if (!f_ || finished()) return false;
 		if (std::fwrite(buffer, 1, bytesPerBuffer_, f_) != bytesPerBuffer_) { close(); return false; }
 		if (++recorded_ == buffersToRecord_) close();
@@ -443,10 +482,64 @@ public:
 	}
 	void close() { if (f_) { std::fclose(f_); f_ = nullptr; } }
 
+	/* ---- the reference's session ---- */
+	std::function<void(bool)> readyToRecord;           /* signals of recorder.h */
+	std::function<void()> recordingDone;
+	std::function<void(const std::string&)> error, info;
+	bool recordingEnabled() const { return recordingEnabled_; }
+	bool init(const RecordingParams& p) {                                                         /* slot_init :64-89 */
+		params_ = p;
+		std::error_code ec;
+		if (p.savePath.empty() || !std::filesystem::is_directory(p.savePath, ec)) {
+			say(error, "Recording not initialized: save path is empty or invalid."); uninit(); return false;
+		}
+		path_ = p.sessionPrefix() + "_" + name_ + ".raw";
+		captured_.clear(); captured_.reserve((size_t)p.buffersToRecord * p.bufferSizeInBytes);
+		recorded_ = 0; initialized_ = true; recordingFinished_ = false; recordingEnabled_ = true; isRecording_ = false;
+		if (readyToRecord) readyToRecord(true);
+		say(info, "Recording initialized...");
+		return true;
+	}
+	/* slot_record :99-133; returns true if the buffer was taken */
+	bool record(const void* buffer, unsigned int currentBufferNr) {
+		if (!recordingEnabled_) return false;
+		if (!initialized_) { say(error, "Recording not possible. Record buffer not initialized."); return false; }
+		if (params_.startWithFirstBuffer && !isRecording_ && currentBufferNr != 0) return false;
+		isRecording_ = true;
+		const char* b = static_cast<const char*>(buffer);
+		captured_.insert(captured_.end(), b, b + params_.bufferSizeInBytes);
+		if (++recorded_ >= params_.buffersToRecord) { recordingEnabled_ = false; isRecording_ = false; saveToDisk(); uninit(); }
+		return true;
+	}
+	void abort() {                                                                                /* slot_abortRecording :52-62 */
+		if (recordingEnabled_ && !recordingFinished_) { say(error, "Recording aborted!"); recordingEnabled_ = false; saveToDisk(); uninit(); }
+	}
+
 private:
+	static void say(const std::function<void(const std::string&)>& f, const std::string& m) { if (f) f(m); }
+	void uninit() {
+		captured_.clear(); captured_.shrink_to_fit();
+		initialized_ = false; recordingFinished_ = true; recorded_ = 0;
+		if (readyToRecord) readyToRecord(false);
+		if (recordingDone) recordingDone();
+	}
+	void saveToDisk() {
+		if (!initialized_) { say(error, "Save recording to disk not possible. Record buffer not initialized."); return; }
+		FILE* out = std::fopen(path_.c_str(), "wb");
+		if (!out) { say(error, "Recording failed! Could not write file to disk."); return; }
+		say(info, "Captured buffers: " + std::to_string(recorded_) + "/" + std::to_string(params_.buffersToRecord));
+		const bool ok = std::fwrite(captured_.data(), 1, captured_.size(), out) == captured_.size();
+		std::fclose(out);
+		say(ok ? info : error, ok ? "Data written to disk! " + path_ : std::string("Recording failed! Could not write file to disk."));
+	}
+
 	size_t bytesPerBuffer_;
 	unsigned int buffersToRecord_, recorded_ = 0;
 	FILE* f_;
+	std::string path_, name_;
+	bool session_ = false, recordingEnabled_ = false, recordingFinished_ = false, isRecording_ = false, initialized_ = false;
+	RecordingParams params_;
+	std::vector<char> captured_;
 };
 
 /* run `buffers` buffers of a raw file through `pipeline` with the reference's thread structure (acquisition thread + processing loop) */

@@ -167,6 +167,59 @@ int main(int argc, char** argv) {
 		for (int k = 0; k < 3; ++k) CHECK(back[(size_t)k * n * a * b] == fp.firstSample[k]);                     /* the buffers that were processed, in order */
 	}
 
+	/* Recorder, session form (recorder.cpp:64-152): file name rule, start with the first buffer of a volume, completion, abort, bad save path, meta file */
+	{
+		const std::string dir = path.substr(0, path.find_last_of('/'));
+		RecordingParams rp; rp.timestamp = "20261017_101500"; rp.fileName = "phantom"; rp.savePath = dir; rp.bufferSizeInBytes = 16; rp.buffersToRecord = 3;
+		rp.startWithFirstBuffer = true; rp.saveMetaData = true;
+		std::vector<std::string> infos, errors; int done = 0;
+		Recorder r("raw");
+		r.info = [&](const std::string& m) { infos.push_back(m); }; r.error = [&](const std::string& m) { errors.push_back(m); }; r.recordingDone = [&] { ++done; };
+		unsigned short x[4][8];
+		for (int k = 0; k < 4; ++k) for (int i = 0; i < 8; ++i) x[k][i] = (unsigned short)(100 * k + i);
+		CHECK(!r.record(x[0], 0u));                                                  /* not enabled yet */
+		CHECK(r.init(rp) && r.path() == dir + "/20261017_101500_phantom_raw.raw" && r.recordingEnabled());
+		CHECK(!r.record(x[3], 1u) && r.recordedBuffers() == 0);                      /* waits for the first buffer of a volume */
+		CHECK(r.record(x[0], 0u) && r.record(x[1], 1u) && r.record(x[2], 0u) && !r.record(x[3], 1u));
+		CHECK(done == 1 && r.finished() && !r.recordingEnabled());
+		FILE* f = std::fopen(r.path().c_str(), "rb");
+		CHECK(f);
+		unsigned short back[24];
+		CHECK(std::fread(back, 2, 24, f) == 24 && std::fgetc(f) == EOF);
+		std::fclose(f);
+		for (int k = 0; k < 3; ++k) for (int i = 0; i < 8; ++i) CHECK(back[8 * k + i] == x[k][i]);
+		CHECK(!infos.empty() && infos[1] == "Captured buffers: 3/3");
+		/* processed-data sizes (processing.cpp:243-249) */
+		AcquisitionParams acq; acq.samplesPerLine = 64; acq.ascansPerBscan = 4; acq.bscansPerBuffer = 3; acq.buffersPerVolume = 1; acq.bitDepth = 12;
+		RecordingParams raw = rp; raw.bufferSizeInBytes = 64 * 4 * 3 * 2;
+		CHECK(raw.forProcessedData(acq).bufferSizeInBytes == 64 * 4 * 3);
+		raw.saveAs32bitFloat = true;
+		CHECK(raw.forProcessedData(acq).bufferSizeInBytes == 32 * 4 * 3 * 4);
+		/* abort keeps what was captured; no user file name -> no extra underscore */
+		RecordingParams rp2 = rp; rp2.fileName.clear(); rp2.timestamp = "t"; rp2.buffersToRecord = 5; rp2.startWithFirstBuffer = false;
+		Recorder r2("processed");
+		r2.error = [&](const std::string& m) { errors.push_back(m); };
+		CHECK(r2.init(rp2) && r2.path() == dir + "/t_processed.raw");
+		CHECK(r2.record(x[0], 1u) && r2.record(x[3], 0u));
+		r2.abort(); r2.abort();
+		CHECK(errors.size() == 1 && errors[0] == "Recording aborted!" && r2.finished());
+		f = std::fopen(r2.path().c_str(), "rb");
+		CHECK(f && std::fread(back, 2, 24, f) == 16 && back[8] == x[3][0]);
+		std::fclose(f);
+		/* meta file = copy of the settings file */
+		const std::string ini = dir + "/settings_for_meta.ini";
+		f = std::fopen(ini.c_str(), "wb"); CHECK(f); std::fputs("[processing]\nbitshift=false\n", f); std::fclose(f);
+		const std::string meta = rp.saveMeta(ini);
+		CHECK(meta == dir + "/20261017_101500_phantom_meta.txt");
+		f = std::fopen(meta.c_str(), "rb"); CHECK(f);
+		char txt[64] = {}; CHECK(std::fread(txt, 1, 63, f) > 0 && std::string(txt) == "[processing]\nbitshift=false\n"); std::fclose(f);
+		/* invalid save path */
+		RecordingParams bad = rp; bad.savePath = dir + "/does_not_exist";
+		Recorder r3("raw");
+		r3.error = [&](const std::string& m) { errors.push_back(m); };
+		CHECK(!r3.init(bad) && !r3.recordingEnabled() && errors.back().find("save path") != std::string::npos);
+	}
+
 	/* dispersion estimator search (dispersionestimationengine.cpp:21-116) against a synthetic metric with a known optimum */
 	{
 		struct FakeSweep {

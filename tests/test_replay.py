@@ -2,6 +2,7 @@
 file format and rate statistics of the reference (virtualoctsystem.cpp:163-224, processing.cpp:136-229), on CPU with a
 stand-in pipeline, and end to end on the GPU."""
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -134,3 +135,132 @@ def test_packed12_file_replay_delivers_packed_buffers(tmp_path):
     vos.startAcquisition()
     assert len(seen) == 2
     assert np.array_equal(seen[0].reshape(b, a, n), vol[:b]) and np.array_equal(seen[1].reshape(b, a, n), vol[b:])
+
+
+# ---------------------------------------------------------------- recording sessions (recorder.cpp, processing.cpp:231-266)
+class FakeStreamingPipeline(FakePipeline):
+    """stand-in with the streaming half of the kernels.h surface: the "processed" buffer is the raw buffer's first half + 1 (u16) or
+    the same as float32, delivered through the registered host buffers and the callback, alternating between the two buffers"""
+
+    def __init__(self):
+        super().__init__()
+        self.stream = self.fstream = None
+        self.cb = self.fcb = None
+        self.calls = 0
+        self.nr, self.q = 0, None
+
+    def initializeCuda(self, h1, h2, q):
+        self.q = q
+        self.nr = q.buffersPerVolume - 1
+        return super().initializeCuda(h1, h2, q)
+
+    def cuda_registerStreamingBuffers(self, h1, h2, nbytes):
+        self.stream = (h1, h2, nbytes)
+
+    def cuda_unregisterStreamingBuffers(self):
+        self.stream = None
+
+    def cuda_registerFloatStreamingBuffers(self, h1, h2, nbytes):
+        self.fstream = (h1, h2, nbytes)
+
+    def cuda_unregisterFloatStreamingBuffers(self):
+        self.fstream = None
+
+    def set_callbacks(self, streaming=None, float_streaming=None, background=None):
+        self.cb, self.fcb = streaming, float_streaming
+
+    def current_buffer_nr(self):
+        return self.nr
+
+    @staticmethod
+    def processed(raw_u16):
+        return (raw_u16[: raw_u16.size // 2] + 1).astype(np.uint16)
+
+    def octCudaPipeline(self, h):
+        super().octCudaPipeline(h)
+        self.nr = (self.nr + 1) % self.q.buffersPerVolume
+        raw = h.view(np.uint16).reshape(-1)
+        if self.q.streamToHost and self.stream and not self.q.saveAs32bitFloat:
+            dst = self.stream[self.calls & 1]
+            dst.view(np.uint16)[:] = self.processed(raw)
+            self.cb(dst.ctypes.data)
+        if self.q.saveAs32bitFloat and self.fstream:
+            dst = self.fstream[self.calls & 1]
+            dst.view(np.float32)[:] = self.processed(raw).astype(np.float32)
+            self.fcb(dst.ctypes.data)
+        self.calls += 1
+
+
+def test_recorder_session_file_name_first_buffer_rule_and_abort(tmp_path):
+    from octproz_b200.acquisition import RecordingParams
+    rp = RecordingParams(timestamp="20261017_101500", fileName="phantom", savePath=str(tmp_path), bufferSizeInBytes=20, buffersToRecord=3,
+                         startWithFirstBuffer=True)
+    done = []
+    r = Recorder("raw"); r.on_recording_done = lambda: done.append(1)
+    x = np.arange(10, dtype=np.uint16)
+    r.slot_record(x)                                              # not initialised, not enabled: ignored (recorder.cpp:107)
+    assert r.slot_init(rp) and r.path == str(tmp_path / "20261017_101500_phantom_raw.raw")
+    r.slot_record(x + 100, currentBufferNr=1)                     # waits for the first buffer of a volume (:116)
+    assert r.recordedBuffers == 0 and not r.isRecording
+    for i, nr in enumerate((0, 1, 0, 1)):                         # the fourth is past buffersToRecord
+        r.slot_record(x + i, currentBufferNr=nr)
+    assert done == [1] and r.recordingFinished and not r.recordingEnabled
+    assert np.array_equal(np.fromfile(r.path, np.uint16), np.concatenate([x, x + 1, x + 2]))
+    assert ("info", "Captured buffers: 3/3") in r.messages
+    # no user file name -> no extra underscore; abort keeps what was captured
+    rp2 = RecordingParams(timestamp="t", savePath=str(tmp_path), bufferSizeInBytes=20, buffersToRecord=5)
+    r2 = Recorder("processed"); assert r2.slot_init(rp2) and os.path.basename(r2.path) == "t_processed.raw"
+    r2.slot_record(x); r2.slot_record(x + 7)
+    r2.slot_abortRecording()
+    assert np.array_equal(np.fromfile(r2.path, np.uint16), np.concatenate([x, x + 7])) and ("error", "Recording aborted!") in r2.messages
+    r2.slot_abortRecording()                                       # second abort: nothing to do
+    # invalid save path
+    r3 = Recorder("raw")
+    assert not r3.slot_init(RecordingParams(timestamp="t", savePath=str(tmp_path / "missing"), bufferSizeInBytes=20, buffersToRecord=1))
+    assert r3.messages[0][0] == "error" and not r3.recordingEnabled
+
+
+@pytest.mark.parametrize("as_float", [False, True])
+def test_processing_records_raw_and_processed_sessions(tmp_path, as_float):
+    from octproz_b200.acquisition import RecordingParams
+    n, a, b = 64, 4, 3
+    vol = synth.make_volume(n, a, 2 * b, 12)
+    p = str(tmp_path / "v.raw"); write_raw_file(p, vol)
+    ini = tmp_path / "settings.ini"; ini.write_text("[processing]\nbitshift=false\n")
+    q = benchmark_params(n, a, b); q.buffersPerVolume = 2
+    q.streamToHost, q.streamingBuffersToSkip = False, 3
+    vos = VirtualOCTSystem(p, q.bitDepth, n, a, b, q.buffersPerVolume)
+    fake = FakeStreamingPipeline()
+    proc = Processing(fake, q)
+    rp = RecordingParams(timestamp="ts", fileName="", savePath=str(tmp_path), bufferSizeInBytes=n * a * b * 2, buffersToRecord=4,
+                         startWithFirstBuffer=True, recordRaw=True, recordProcessed=True, saveMetaData=True, saveAs32bitFloat=as_float)
+    proc.slot_enableRecording(rp, settings_file=str(ini))
+    assert q.streamToHost and q.streamingBuffersToSkip == 0                          # every buffer is streamed while the recording runs
+    proc.slot_enableRecording(rp)                                                     # a second request while one is running
+    assert ("error", "Recording of raw data is already running.") in proc.messages and ("error", "Recording of processed data is already running.") in proc.messages
+    import threading
+    started = threading.Event(); vos.on_acquisition_started = lambda s: started.set()
+    t = threading.Thread(target=vos.startAcquisition, daemon=True); t.start()
+    assert started.wait(30)
+    assert proc.slot_start(vos, max_buffers=9)
+    vos.stopAcquisition(); t.join(30)
+    assert (tmp_path / "ts_meta.txt").read_text() == ini.read_text()
+    halves = [vol[:b].reshape(-1), vol[b:].reshape(-1)]
+    raw = np.fromfile(str(tmp_path / "ts_raw.raw"), np.uint16).reshape(4, -1)
+    # four consecutive buffers; the recording started with a first buffer of a volume (currentBufferNr 0) and the file's two halves alternate
+    first = 0 if np.array_equal(raw[0], halves[0]) else 1
+    assert all(np.array_equal(raw[i], halves[(first + i) & 1]) for i in range(4))
+    if as_float:
+        got = np.fromfile(str(tmp_path / "ts_processed.raw"), np.float32).reshape(4, -1)
+        assert got.shape[1] == (n // 2) * a * b
+        want = [FakeStreamingPipeline.processed(h).astype(np.float32) for h in halves]
+    else:
+        got = np.fromfile(str(tmp_path / "ts_processed.raw"), np.uint16).reshape(4, -1)
+        assert got.shape[1] == (n // 2) * a * b                                     # half the raw buffer's bytes (processing.cpp:248)
+        want = [FakeStreamingPipeline.processed(h) for h in halves]
+    f0 = 0 if np.array_equal(got[0], want[0]) else 1
+    assert all(np.array_equal(got[i], want[(f0 + i) & 1]) for i in range(4))
+    # settings restored once the processed recording is complete (slot_resetGpu2HostSettings), streaming buffers released at the end
+    assert not q.streamToHost and q.streamingBuffersToSkip == 3 and not q.saveAs32bitFloat
+    assert fake.stream is None and fake.fstream is None
+    assert proc.rawRecorder.recordingFinished and proc.processedRecorder.recordingFinished
