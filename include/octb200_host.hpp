@@ -36,6 +36,7 @@
 #include <filesystem>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -295,6 +296,32 @@ struct OctAlgorithmParameters {
 	}
 };
 
+/* Gpu2HostNotifier (octproz/src/gpu2hostnotifier.h:35-62): the C callbacks carry no user pointer, so -- as in the reference -- one
+ * process-wide object receives them and forwards to whoever connected (Qt signals there, std::function here).  The callbacks arrive on a
+ * CUDA host-function thread; connect() / disconnect() are serialised with them. */
+class Gpu2HostNotifier {
+public:
+	using Slot = std::function<void(void*)>;
+	static Gpu2HostNotifier& getInstance() { static Gpu2HostNotifier n; return n; }
+	void connectProcessed(Slot s) { std::lock_guard<std::recursive_mutex> g(m_); newGpuDataAvailable_ = std::move(s); }
+	void connectFloat(Slot s) { std::lock_guard<std::recursive_mutex> g(m_); newGpuFloatDataAvailable_ = std::move(s); }
+	void connectBackground(Slot s) { std::lock_guard<std::recursive_mutex> g(m_); backgroundRecorded_ = std::move(s); }
+	void disconnectAll() { std::lock_guard<std::recursive_mutex> g(m_); newGpuDataAvailable_ = nullptr; newGpuFloatDataAvailable_ = nullptr; backgroundRecorded_ = nullptr; }
+	/* the three functions handed to octb200_set_callbacks (gpu2hostnotifier.h:47-49) */
+	static void dh2StreamingCallback(void* buffer) { getInstance().emit(&Gpu2HostNotifier::newGpuDataAvailable_, buffer); }
+	static void dh2FloatStreamingCallback(void* buffer) { getInstance().emit(&Gpu2HostNotifier::newGpuFloatDataAvailable_, buffer); }
+	static void backgroundSignalCallback(void* buffer) { getInstance().emit(&Gpu2HostNotifier::backgroundRecorded_, buffer); }
+
+private:
+	Gpu2HostNotifier() = default;
+	void emit(Slot Gpu2HostNotifier::*which, void* buffer) {
+		std::lock_guard<std::recursive_mutex> g(m_);
+		if (this->*which) (this->*which)(buffer);
+	}
+	std::recursive_mutex m_;          /* a slot may (dis)connect from inside a callback */
+	Slot newGpuDataAvailable_, newGpuFloatDataAvailable_, backgroundRecorded_;
+};
+
 /* kernels.h:63-84 over one octb200 handle.  Every failure throws std::runtime_error with octb200_last_error(): loud, no fallback. */
 class OctPipeline {
 public:
@@ -327,6 +354,23 @@ public:
 		if (h_) { octb200_destroy(h_); h_ = nullptr; }
 	}
 	void sync() { check(octb200_sync(h_), "sync"); }
+	/* kernels.h:71-76: the two host buffers the converted (or float) output is streamed into, delivered through Gpu2HostNotifier */
+	void cuda_registerStreamingBuffers(void* h1, void* h2, size_t bytesPerBuffer) {
+		check(octb200_register_streaming_buffers(h_, h1, h2, bytesPerBuffer), "register_streaming_buffers"); connectNotifier();
+	}
+	void cuda_unregisterStreamingBuffers() { check(octb200_unregister_streaming_buffers(h_), "unregister_streaming_buffers"); }
+	void cuda_registerFloatStreamingBuffers(void* h1, void* h2, size_t bytesPerBuffer) {
+		check(octb200_register_float_streaming_buffers(h_, h1, h2, bytesPerBuffer), "register_float_streaming_buffers"); connectNotifier();
+	}
+	void cuda_unregisterFloatStreamingBuffers() { check(octb200_unregister_float_streaming_buffers(h_), "unregister_float_streaming_buffers"); }
+	/* kernels.h:66-67 (without the GL mapping: the frame goes to caller-provided device memory) */
+	void changeDisplayedBscanFrame(unsigned frameNr, unsigned displayFunctionFrames, int displayFunction, float* dOut) {
+		check(octb200_bscan_frame(h_, frameNr, displayFunctionFrames, displayFunction, dOut), "bscan_frame");
+	}
+	void changeDisplayedEnFaceFrame(unsigned frameNr, unsigned displayFunctionFrames, int displayFunction, float* dOut) {
+		check(octb200_enface_frame(h_, frameNr, displayFunctionFrames, displayFunction, dOut), "enface_frame");
+	}
+	unsigned currentBufferNr() const { return h_ ? octb200_current_buffer_nr(h_) : 0u; }                /* params->currentBufferNr, cuda_code.cu:1602 */
 	void copyOutput(float* host, unsigned bufferNrInVolume = 0) { check(octb200_copy_output(h_, host, bufferNrInVolume), "copy_output"); }
 	unsigned long long launchCount() const { return h_ ? (unsigned long long)octb200_launch_count(h_) : 0ULL; }
 	octb200_pipeline* handle() { return h_; }
@@ -341,6 +385,10 @@ private:
 			lastError_ = std::string(what) + " failed (" + std::to_string(rc) + "): " + (octb200_last_error(h_) ? octb200_last_error(h_) : "");
 			throw std::runtime_error(lastError_);
 		}
+	}
+	void connectNotifier() {
+		check(octb200_set_callbacks(h_, &Gpu2HostNotifier::dh2StreamingCallback, &Gpu2HostNotifier::dh2FloatStreamingCallback,
+		                            &Gpu2HostNotifier::backgroundSignalCallback), "set_callbacks");
 	}
 	void pushParams(bool forceCurves) {
 		OctAlgorithmParameters& q = *params_;
@@ -363,65 +411,6 @@ private:
 	AcquisitionParams acq_;
 	OctAlgorithmParameters* params_ = nullptr;
 	std::string lastError_;
-};
-
-/* processing.cpp:194-207: what the sidebar shows */
-struct ProcessingStats {
-	double buffersPerSecond = 0, volumesPerSecond = 0, bscansPerSecond = 0, ascansPerSecond = 0, bufferSizeMB = 0, dataThroughputMBs = 0;
-	long long processedBuffers = 0;
-};
-
-/* Processing::slot_start (processing.cpp:136-229).  Pipeline needs initializeCuda(h1, h2, acq, params*), octCudaPipeline(h), sync(), cleanupCuda(). */
-template <class Pipeline>
-class Processing {
-public:
-	Processing(Pipeline* pipeline, OctAlgorithmParameters* octParams) : pipeline_(pipeline), octParams_(octParams) {}
-
-	/* signal rawData(void*, bitDepth, samplesPerLine, ascansPerBscan, bscansPerBuffer, buffersPerVolume, currentBufferNr) (processing.h:110) */
-	std::function<void(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned)> rawData;
-	ProcessingStats stats;
-
-	/* maxBuffers > 0: headless runs stop the acquisition after that many processed buffers (the GUI's Stop button) */
-	bool slot_start(AcquisitionSystem* system, long long maxBuffers = 0) {
-		AcquisitionBuffer* buffer = system->buffer;
-		for (int i = 0; i < buffer->bufferCnt; ++i) buffer->setReady(i, true);                  /* blockBuffersForAcquisitionSystem :124-128 */
-		const AcquisitionParams& a = system->params;
-		if (buffer->bufferCnt < 2 || !pipeline_->initializeCuda(buffer->bufferArray[0], buffer->bufferArray[1], a, octParams_)) {      /* :151 */
-			for (int i = 0; i < buffer->bufferCnt; ++i) buffer->setReady(i, false);
-			system->stopAcquisition();                                                            /* initializationFailed -> slot_stop (octprozapp.cpp:54) */
-			return false;
-		}
-		const unsigned perVolume = a.buffersPerVolume ? a.buffersPerVolume : 1;
-		unsigned currentBufferNr = perVolume - 1;
-		for (int i = 0; i < buffer->bufferCnt; ++i) buffer->setReady(i, false);                 /* unblock :130-134 */
-		const auto t0 = std::chrono::steady_clock::now();
-		long long n = 0;
-		while (system->acqusitionRunning.load()) {                                               /* :176-218 */
-			const int pos = buffer->currIndex.load();
-			if (pos >= 0 && buffer->ready(pos)) {
-				currentBufferNr = (currentBufferNr + 1) % perVolume;
-				if (rawData) rawData(buffer->bufferArray[pos], a.bitDepth, a.samplesPerLine, a.ascansPerBscan, a.bscansPerBuffer, perVolume, currentBufferNr);
-				pipeline_->octCudaPipeline(buffer->bufferArray[pos]);                           /* :187 */
-				buffer->setReady(pos, false);                                                    /* :191 */
-				++n;
-				if (maxBuffers > 0 && n >= maxBuffers) system->stopAcquisition();
-			} else {
-				std::this_thread::yield();
-			}
-		}
-		pipeline_->sync();
-		const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-		const double bps = dt > 0 ? (double)n / dt : 0.0;
-		stats.processedBuffers = n;
-		stats.buffersPerSecond = bps; stats.volumesPerSecond = bps / perVolume;                 /* :198-201 */
-		stats.bscansPerSecond = bps * a.bscansPerBuffer; stats.ascansPerSecond = stats.bscansPerSecond * a.ascansPerBscan;
-		stats.bufferSizeMB = (double)buffer->bytesPerBuffer / 1048576.0; stats.dataThroughputMBs = bps * stats.bufferSizeMB;
-		return true;
-	}
-
-private:
-	Pipeline* pipeline_;
-	OctAlgorithmParameters* octParams_;
 };
 
 /* OctAlgorithmParameters::RecordingParams (octproz/src/octalgorithmparameters.h:84-98) without the GUI-only screenshot switch */
@@ -540,6 +529,130 @@ private:
 	bool session_ = false, recordingEnabled_ = false, recordingFinished_ = false, isRecording_ = false, initialized_ = false;
 	RecordingParams params_;
 	std::vector<char> captured_;
+};
+
+/* processing.cpp:194-207: what the sidebar shows */
+struct ProcessingStats {
+	double buffersPerSecond = 0, volumesPerSecond = 0, bscansPerSecond = 0, ascansPerSecond = 0, bufferSizeMB = 0, dataThroughputMBs = 0;
+	long long processedBuffers = 0;
+};
+
+/* Processing::slot_start (processing.cpp:136-229).  Pipeline needs initializeCuda(h1, h2, acq, params*), octCudaPipeline(h), sync(), cleanupCuda(). */
+template <class Pipeline>
+class Processing {
+public:
+	Processing(Pipeline* pipeline, OctAlgorithmParameters* octParams) : pipeline_(pipeline), octParams_(octParams) {}
+
+	/* signal rawData(void*, bitDepth, samplesPerLine, ascansPerBscan, bscansPerBuffer, buffersPerVolume, currentBufferNr) (processing.h:110) */
+	std::function<void(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned)> rawData;
+	ProcessingStats stats;
+	Recorder rawRecorder{"raw"}, processedRecorder{"processed"};                              /* processing.cpp:49,60 */
+	std::function<void(const std::string&)> error;
+
+	/* Processing::slot_enableRecording (processing.cpp:231-266) with OCTproZApp::slot_prepareGpu2HostForProcessedRecording / slot_resetGpu2HostSettings
+	 * (octprozapp.cpp:408-422): raw buffers as this loop sees them and / or the processed buffers the pipeline streams to the host (converted
+	 * containers, or float32 with saveAs32bitFloat); the meta file is a copy of `settingsFile`.  Call before slot_start or from the rawData slot.
+	 * The pipeline type needs cuda_register[Float]StreamingBuffers / cuda_unregister... and currentBufferNr() (OctPipeline has them). */
+	void slot_enableRecording(const RecordingParams& rp, const AcquisitionParams& a, const std::string& settingsFile = std::string()) {
+		if (rp.recordRaw) {
+			if (rawRecorder.recordingEnabled()) say("Recording of raw data is already running.");
+			else rawRecorder.init(rp);
+		}
+		if (rp.recordProcessed) {
+			if (processedRecorder.recordingEnabled()) say("Recording of processed data is already running.");
+			else {
+				octb200_params& p = octParams_->p;
+				memorized_[0] = p.streamToHost; memorized_[1] = (int)p.streamingBuffersToSkip; memorized_[2] = p.streamFloatToHost; haveMemorized_ = true;
+				p.streamToHost = 1; p.streamingBuffersToSkip = 0; p.streamFloatToHost = rp.saveAs32bitFloat ? 1 : 0;     /* every buffer, while the recording runs */
+				processedRecorder.recordingDone = [this] {
+					if (!haveMemorized_) return;
+					octb200_params& q = octParams_->p;
+					q.streamToHost = memorized_[0]; q.streamingBuffersToSkip = (uint32_t)memorized_[1]; q.streamFloatToHost = memorized_[2]; haveMemorized_ = false;
+				};
+				if (processedRecorder.init(rp.forProcessedData(a))) {
+					streamingWanted_ = true; recordFloat_ = rp.saveAs32bitFloat; streamBytes_ = rp.forProcessedData(a).bufferSizeInBytes;
+					/* bound here, not in slot_start: only pipelines that record processed data need the streaming half of kernels.h */
+					enableStreaming_ = [this] { enableStreaming(); };
+					disableStreaming_ = [this] { disableStreaming(); };
+				}
+			}
+		}
+		if (!settingsFile.empty()) rp.saveMeta(settingsFile);
+	}
+
+	/* maxBuffers > 0: headless runs stop the acquisition after that many processed buffers (the GUI's Stop button) */
+	bool slot_start(AcquisitionSystem* system, long long maxBuffers = 0) {
+		AcquisitionBuffer* buffer = system->buffer;
+		for (int i = 0; i < buffer->bufferCnt; ++i) buffer->setReady(i, true);                  /* blockBuffersForAcquisitionSystem :124-128 */
+		const AcquisitionParams& a = system->params;
+		if (buffer->bufferCnt < 2 || !pipeline_->initializeCuda(buffer->bufferArray[0], buffer->bufferArray[1], a, octParams_)) {      /* :151 */
+			for (int i = 0; i < buffer->bufferCnt; ++i) buffer->setReady(i, false);
+			system->stopAcquisition();                                                            /* initializationFailed -> slot_stop (octprozapp.cpp:54) */
+			return false;
+		}
+		const unsigned perVolume = a.buffersPerVolume ? a.buffersPerVolume : 1;
+		unsigned currentBufferNr = perVolume - 1;
+		for (int i = 0; i < buffer->bufferCnt; ++i) buffer->setReady(i, false);                 /* unblock :130-134 */
+		const auto t0 = std::chrono::steady_clock::now();
+		long long n = 0;
+		while (system->acqusitionRunning.load()) {                                               /* :176-218 */
+			const int pos = buffer->currIndex.load();
+			if (pos >= 0 && buffer->ready(pos)) {
+				currentBufferNr = (currentBufferNr + 1) % perVolume;
+				if (streamingWanted_ && enableStreaming_) enableStreaming_();
+				if (rawData) rawData(buffer->bufferArray[pos], a.bitDepth, a.samplesPerLine, a.ascansPerBscan, a.bscansPerBuffer, perVolume, currentBufferNr);
+				rawRecorder.record(buffer->bufferArray[pos], currentBufferNr);                      /* connect(rawData, rawRecorder) :52; a no-op unless enabled */
+				pipeline_->octCudaPipeline(buffer->bufferArray[pos]);                           /* :187 */
+				buffer->setReady(pos, false);                                                    /* :191 */
+				++n;
+				if (maxBuffers > 0 && n >= maxBuffers) system->stopAcquisition();
+			} else {
+				std::this_thread::yield();
+			}
+		}
+		pipeline_->sync();
+		const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		if (disableStreaming_) disableStreaming_();
+		const double bps = dt > 0 ? (double)n / dt : 0.0;
+		stats.processedBuffers = n;
+		stats.buffersPerSecond = bps; stats.volumesPerSecond = bps / perVolume;                 /* :198-201 */
+		stats.bscansPerSecond = bps * a.bscansPerBuffer; stats.ascansPerSecond = stats.bscansPerSecond * a.ascansPerBscan;
+		stats.bufferSizeMB = (double)buffer->bytesPerBuffer / 1048576.0; stats.dataThroughputMBs = bps * stats.bufferSizeMB;
+		return true;
+	}
+
+private:
+	void say(const std::string& m) { if (error) error(m); }
+	/* enableGpu2HostStreaming / enableFloatGpu2HostStreaming (processing.cpp:316-362): two host buffers registered with the pipeline, every
+	 * delivered buffer handed to the processed recorder through the notifier */
+	void enableStreaming() {
+		streamingWanted_ = false;
+		if (!streamBuffer_.allocateMemory(2, streamBytes_)) { say("could not allocate the streaming buffers"); return; }
+		auto deliver = [this](void* b) { processedRecorder.record(b, pipeline_->currentBufferNr()); };
+		if (recordFloat_) {
+			Gpu2HostNotifier::getInstance().connectFloat(deliver);
+			pipeline_->cuda_registerFloatStreamingBuffers(streamBuffer_.bufferArray[0], streamBuffer_.bufferArray[1], streamBytes_);
+		} else {
+			Gpu2HostNotifier::getInstance().connectProcessed(deliver);
+			pipeline_->cuda_registerStreamingBuffers(streamBuffer_.bufferArray[0], streamBuffer_.bufferArray[1], streamBytes_);
+		}
+		streaming_ = true;
+	}
+	void disableStreaming() {
+		if (!streaming_) return;
+		if (recordFloat_) { pipeline_->cuda_unregisterFloatStreamingBuffers(); Gpu2HostNotifier::getInstance().connectFloat(nullptr); }
+		else { pipeline_->cuda_unregisterStreamingBuffers(); Gpu2HostNotifier::getInstance().connectProcessed(nullptr); }
+		streamBuffer_.releaseMemory();
+		streaming_ = false;
+	}
+
+	Pipeline* pipeline_;
+	OctAlgorithmParameters* octParams_;
+	AcquisitionBuffer streamBuffer_;
+	std::function<void()> enableStreaming_, disableStreaming_;
+	size_t streamBytes_ = 0;
+	bool streamingWanted_ = false, streaming_ = false, recordFloat_ = false, haveMemorized_ = false;
+	int memorized_[3] = {0, 0, 0};
 };
 
 /* run `buffers` buffers of a raw file through `pipeline` with the reference's thread structure (acquisition thread + processing loop) */

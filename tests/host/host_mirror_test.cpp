@@ -27,6 +27,41 @@ struct FakePipeline {
 	void cleanupCuda() { ++cleanups; }
 };
 
+/* stand-in with the streaming half of kernels.h: the "processed" buffer is the first half of the raw buffer + 1 (u16) or the same as float,
+ * written into the registered host buffers in turn and announced through the notifier's C callbacks, as the library does */
+struct FakeStreamingPipeline : FakePipeline {
+	OctAlgorithmParameters* q = nullptr;
+	void* stream[2] = {nullptr, nullptr}; void* fstream[2] = {nullptr, nullptr};
+	size_t bytes = 0, fbytes = 0;
+	unsigned nr = 0, perVolume = 1, count = 0;
+	int registered = 0, unregistered = 0;
+	bool initializeCuda(void* a, void* b, const AcquisitionParams& p, OctAlgorithmParameters* params) {
+		q = params; perVolume = p.buffersPerVolume ? p.buffersPerVolume : 1; nr = perVolume - 1;
+		return FakePipeline::initializeCuda(a, b, p, params);
+	}
+	void cuda_registerStreamingBuffers(void* h1, void* h2, size_t n) { stream[0] = h1; stream[1] = h2; bytes = n; ++registered; }
+	void cuda_unregisterStreamingBuffers() { stream[0] = stream[1] = nullptr; ++unregistered; }
+	void cuda_registerFloatStreamingBuffers(void* h1, void* h2, size_t n) { fstream[0] = h1; fstream[1] = h2; fbytes = n; ++registered; }
+	void cuda_unregisterFloatStreamingBuffers() { fstream[0] = fstream[1] = nullptr; ++unregistered; }
+	unsigned currentBufferNr() const { return nr; }
+	void octCudaPipeline(void* h) {
+		FakePipeline::octCudaPipeline(h);
+		nr = (nr + 1) % perVolume;
+		const unsigned short* raw = static_cast<const unsigned short*>(h);
+		if (q->p.streamToHost && stream[0] && !q->p.streamFloatToHost) {
+			unsigned short* dst = static_cast<unsigned short*>(stream[count & 1]);
+			for (size_t i = 0; i < bytes / 2; ++i) dst[i] = (unsigned short)(raw[i] + 1);
+			Gpu2HostNotifier::dh2StreamingCallback(dst);
+		}
+		if (q->p.streamFloatToHost && fstream[0]) {
+			float* dst = static_cast<float*>(fstream[count & 1]);
+			for (size_t i = 0; i < fbytes / 4; ++i) dst[i] = (float)(raw[i] + 1);
+			Gpu2HostNotifier::dh2FloatStreamingCallback(dst);
+		}
+		++count;
+	}
+};
+
 static bool writeFile(const std::string& path, unsigned n, unsigned a, unsigned b, unsigned buffers) {
 	FILE* f = std::fopen(path.c_str(), "wb");
 	if (!f) return false;
@@ -218,6 +253,58 @@ int main(int argc, char** argv) {
 		Recorder r3("raw");
 		r3.error = [&](const std::string& m) { errors.push_back(m); };
 		CHECK(!r3.init(bad) && !r3.recordingEnabled() && errors.back().find("save path") != std::string::npos);
+	}
+
+	/* Processing::slot_enableRecording (processing.cpp:231-266): raw + processed session over the replay loop, containers and float32 */
+	for (int asFloat = 0; asFloat < 2; ++asFloat) {
+		const std::string dir = path.substr(0, path.find_last_of('/'));
+		VirtualOCTSystem vos(path, 12, n, a, b, 2);                                /* two buffers per volume */
+		FakeStreamingPipeline fp;
+		OctAlgorithmParameters q;
+		q.p.streamToHost = 0; q.p.streamingBuffersToSkip = 3;
+		Processing<FakeStreamingPipeline> proc(&fp, &q);
+		std::vector<std::string> errors;
+		proc.error = [&](const std::string& m) { errors.push_back(m); };
+		RecordingParams rp; rp.timestamp = asFloat ? "tsf" : "ts"; rp.savePath = dir; rp.bufferSizeInBytes = (size_t)n * a * b * 2; rp.buffersToRecord = 4;
+		rp.startWithFirstBuffer = true; rp.recordRaw = true; rp.recordProcessed = true; rp.saveAs32bitFloat = asFloat != 0;
+		proc.slot_enableRecording(rp, vos.params);
+		CHECK(q.p.streamToHost == 1 && q.p.streamingBuffersToSkip == 0 && q.p.streamFloatToHost == asFloat);
+		proc.slot_enableRecording(rp, vos.params);                                 /* a second request while one is running */
+		CHECK(errors.size() == 2 && errors[0] == "Recording of raw data is already running." && errors[1] == "Recording of processed data is already running.");
+		std::atomic<bool> started{false};
+		vos.acquisitionStarted = [&](AcquisitionSystem*) { started.store(true); };
+		std::thread producer([&] { vos.startAcquisition(); });
+		while (!started.load()) std::this_thread::yield();
+		CHECK(proc.slot_start(&vos, 9));
+		vos.stopAcquisition();
+		producer.join();
+		CHECK(proc.rawRecorder.finished() && proc.processedRecorder.finished());
+		CHECK(q.p.streamToHost == 0 && q.p.streamingBuffersToSkip == 3 && q.p.streamFloatToHost == 0);        /* settings restored (octprozapp.cpp:418-422) */
+		CHECK(fp.registered == 1 && fp.unregistered == 1 && !fp.stream[0] && !fp.fstream[0]);
+		const size_t perBuf = (size_t)n * a * b;
+		std::vector<unsigned short> raw(perBuf * 4);
+		FILE* f = std::fopen((dir + "/" + rp.timestamp + "_raw.raw").c_str(), "rb");
+		CHECK(f && std::fread(raw.data(), 2, raw.size(), f) == raw.size() && std::fgetc(f) == EOF);
+		std::fclose(f);
+		/* four consecutive buffers of the file's two (first samples 1000 / 2000 & 0xFFF), alternating */
+		const unsigned short s0 = (unsigned short)(1000u & 0xFFFu), s1 = (unsigned short)(2000u & 0xFFFu);
+		CHECK(raw[0] == s0 || raw[0] == s1);
+		for (int k = 1; k < 4; ++k) CHECK(raw[k * perBuf] == (raw[(k - 1) * perBuf] == s0 ? s1 : s0));
+		f = std::fopen((dir + "/" + rp.timestamp + "_processed.raw").c_str(), "rb");
+		CHECK(f);
+		if (asFloat) {
+			std::vector<float> pr(perBuf / 2 * 4);
+			CHECK(std::fread(pr.data(), 4, pr.size(), f) == pr.size() && std::fgetc(f) == EOF);
+			for (int k = 0; k < 4; ++k) CHECK(pr[k * (perBuf / 2)] == (float)(s0 + 1) || pr[k * (perBuf / 2)] == (float)(s1 + 1));
+			for (int k = 1; k < 4; ++k) CHECK(pr[k * (perBuf / 2)] != pr[(k - 1) * (perBuf / 2)]);
+			CHECK(pr[1] == pr[0] + 1.0f);                                          /* the file's ramp, + 1 */
+		} else {
+			std::vector<unsigned short> pr(perBuf / 2 * 4);
+			CHECK(std::fread(pr.data(), 2, pr.size(), f) == pr.size() && std::fgetc(f) == EOF);              /* half the raw buffer's bytes (processing.cpp:248) */
+			for (int k = 0; k < 4; ++k) CHECK(pr[k * (perBuf / 2)] == s0 + 1 || pr[k * (perBuf / 2)] == s1 + 1);
+			for (int k = 1; k < 4; ++k) CHECK(pr[k * (perBuf / 2)] != pr[(k - 1) * (perBuf / 2)]);
+		}
+		std::fclose(f);
 	}
 
 	/* dispersion estimator search (dispersionestimationengine.cpp:21-116) against a synthetic metric with a known optimum */
