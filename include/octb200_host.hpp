@@ -9,9 +9,12 @@
  *                                            `buffer`, `params`, `acqusitionRunning` -- the reference's spelling; the Qt signals
  *                                            acquisitionStarted / acquisitionStopped are std::function members)
  *   VirtualOCTSystem                         octproz_plugins/octproz-virtual-oct-system/src/virtualoctsystem.cpp:59-224
- *   OctPipeline                              the kernels.h entry points (kernels.h:63-84) as methods over an octb200 handle
+ *   Gpu2HostNotifier                         octproz/src/gpu2hostnotifier.h:35-62 (process-wide receiver of the stream-to-host callbacks)
+ *   OctPipeline                              the kernels.h entry points (kernels.h:63-84) as methods over an octb200 handle, incl. the
+ *                                            streaming-buffer registration and the displayed-frame extraction into device memory
  *   Processing                               octproz/src/processing.cpp:124-229 (block the buffers, initializeCuda, poll the double
  *                                            buffer, octCudaPipeline, release the buffer, per-second statistics :194-207)
+ *                                            and :231-266 slot_enableRecording (raw / processed recording sessions)
  *   Recorder / RecordingParams               octproz/src/recorder.cpp, octalgorithmparameters.h:84-98 (N buffers into one headerless file; session
  *                                            file naming, start with the first buffer of a volume, abort, meta file = settings INI copy)
  *   DispersionEstimationEngine               octproz-dispersion-estimator-extension/src/dispersionestimationengine.cpp:21-158 (the
